@@ -1,0 +1,66 @@
+"""Builds the native parts IN-TREE (the .so files travel to the GPU box with the snapshot):
+
+    libppmx_gpu.so   CUDA kernels + the C ABI of include/ppmx_gpu.h   (nvcc, sm_100a only)
+    libppmx_host.so  the C host layer of include/ppmx_host.h          (gcc, links the above)
+    ppmx-b200        the command line                                  (gcc)
+
+No GPU is needed to build: nvcc cross-compiles for sm_100a.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+GPU_SO = os.path.join(PKG, "libppmx_gpu.so")
+HOST_SO = os.path.join(PKG, "libppmx_host.so")
+CLI = os.path.join(PKG, "ppmx-b200")
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-fmad=false",  # the FP64 operators must round every product and sum separately
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+# no -march=native / -mfma: contribution tables must match the reference's glibc doubles
+GCC_FLAGS = ["-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-std=gnu99"]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _newer(target: str, sources) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    hdrs = [os.path.join(PKG, "..", "include", "ppmx_gpu.h"), os.path.join(PKG, "..", "include", "ppmx_host.h"),
+            os.path.join(CSRC, "ppmx_kernels.h")]
+    cu = [os.path.join(CSRC, "ppmx_kernels.cu"), os.path.join(CSRC, "ppmx_gpu.cu")]
+    if force or _newer(GPU_SO, cu + hdrs):
+        _run([_nvcc()] + NVCC_FLAGS + ["-o", GPU_SO] + cu, verbose)
+    host_c = os.path.join(CSRC, "ppmx_host.c")
+    if force or _newer(HOST_SO, [host_c, GPU_SO] + hdrs):
+        _run(["gcc"] + GCC_FLAGS + ["-shared", "-o", HOST_SO, host_c, "-L" + PKG, "-lppmx_gpu", "-lm",
+                                    "-Wl,-rpath,$ORIGIN"], verbose)
+    cli_c = os.path.join(CSRC, "ppmx_cli.c")
+    if force or _newer(CLI, [cli_c, HOST_SO]):
+        _run(["gcc"] + GCC_FLAGS + ["-o", CLI, cli_c, "-L" + PKG, "-lppmx_host", "-lppmx_gpu", "-lm",
+                                    "-Wl,-rpath,$ORIGIN"], verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose=True)

@@ -1,0 +1,605 @@
+/*
+ * ppmx_host.c -- host side of ppmx-b200, in C like the reference (see include/ppmx_host.h).
+ *
+ * "ref:N" = /root/reference/ppmx-edward.c line N.  This file holds what the reference does
+ * on the CPU that is NOT a pixel loop: flag handling, the P6 tokenizer, header writing, the
+ * op ordering of doProcessPPM, and the libm-dependent tables (contributions, rotation size).
+ * Every pixel loop is a call into libppmx_gpu.so.  Build with -O2 -ffp-contract=off: the
+ * contribution weights must be bit-identical to the reference's (no FMA contraction).
+ */
+#include "../../include/ppmx_host.h"
+
+#include <ctype.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PPMX_PI 3.14159265358979323846 /* the reference's own literal, ref:12 */
+
+/* one-line message on stdout, then -1: the reference's CHECK_ERROR convention (ref:31-36) */
+#define BAIL(msg)            \
+    do {                     \
+        printf("%s", msg);   \
+        return PPMX_ERROR;   \
+    } while (0)
+
+static double half_up(double v) { return floor(v + 0.5); } /* the reference's round(), ref:27 */
+
+/* ------------------------------------------------------------------ host mathematics */
+
+double ppmx_cubic(double x)
+{
+    /* Keys kernel, a = -0.5; the grouping of every product and sum is the source's (ref:484-486) */
+    const double t = fabs(x), t2 = t * t, t3 = t2 * t;
+    double k = 0;
+    if (t <= 1) k = (1.5 * t3) - (2.5 * t2) + 1;
+    if ((1 < t) && (t <= 2)) k = k + ((-0.5 * t3) + (2.5 * t2) - (4 * t) + 2);
+    return k;
+}
+
+int ppmx_mod(int a, int b)
+{
+    int m = (b != 0) ? a % b : 0;
+    return m < 0 ? m + b : m;
+}
+
+void ppmx_calc_rot_size(double angle, unsigned int old_width, unsigned int old_height,
+                        unsigned int *new_width, unsigned int *new_height)
+{
+    const double th = (angle * PPMX_PI) / 180.0;
+    *new_width = (unsigned int)half_up((old_width * cos(th)) + (old_height * sin(th)));
+    *new_height = (unsigned int)half_up((old_width * sin(th)) + (old_height * cos(th)));
+}
+
+/* the size rotate() asks for: the angle is folded into [0,90] first (ref:687-691) */
+static void rotated_size(double angle, unsigned int w, unsigned int h, unsigned int *nw, unsigned int *nh)
+{
+    double a = angle;
+    if (a >= 270) a = 360 - a;
+    else if (a > 180) a = a - 180;
+    else if (a > 90) a = 180 - a;
+    ppmx_calc_rot_size(a, w, h, nw, nh);
+}
+
+/* One row of the contribution table before pruning: P candidate taps for output index y.
+ * ref:558-589 does this in five separate sweeps over the whole table; per row the values are
+ * the same because no step looks at another row. */
+static void contribution_row(int y, int in_size, double scale, double kw, int P, double *w, int *id)
+{
+    const double u = ((y + 1) / scale) + (0.5 * (1 - (1 / scale))); /* ref:562 */
+    const double left = floor(u - (kw / 2));
+    double sum = 0.0;
+    int x;
+    for (x = 0; x < P; x++) {
+        id[x] = (int)(left + (x - 1)); /* ref:563 */
+        if (scale < 1.0) w[x] = scale * ppmx_cubic((u - (double)id[x] - 1) * scale); /* ref:571-572 */
+        else w[x] = ppmx_cubic(u - (double)id[x] - 1);                               /* ref:578 */
+    }
+    for (x = 0; x < P; x++) sum += w[x]; /* ref:583 */
+    for (x = 0; x < P; x++) w[x] /= sum; /* ref:584 */
+    for (x = 0; x < P; x++) {            /* symmetric extension, ref:551-555 + 589 */
+        int m = ppmx_mod(id[x], 2 * in_size);
+        id[x] = (m < in_size) ? m : 2 * in_size - 1 - m;
+    }
+}
+
+int ppmx_calc_contributions(int in_size, int out_size, double scale, double k_width, ppmx_contributions *c)
+{
+    double kw = k_width, *row_w = NULL;
+    int P, x, y, kept = 0, *row_i = NULL;
+    unsigned char *keep = NULL;
+
+    memset(c, 0, sizeof(*c));
+    if (in_size < 1 || out_size < 1 || !(scale > 0)) BAIL("error: allocating ind2store\n"); /* what ref:595 ends in */
+    if (scale < 1.0) kw = kw / scale; /* ref:533 */
+    P = (int)ceil(kw) + 2;            /* ref:535 */
+
+    row_w = (double *)malloc(sizeof(double) * (size_t)P);
+    row_i = (int *)malloc(sizeof(int) * (size_t)P);
+    keep = (unsigned char *)calloc((size_t)P, 1);
+    if (!row_w || !row_i || !keep) goto nomem;
+
+    /* which tap columns survive is decided by output index 0 alone (ref:591-602) */
+    contribution_row(0, in_size, scale, kw, P, row_w, row_i);
+    for (x = 0; x < P; x++)
+        if (row_w[x] != 0.0f) { keep[x] = 1; kept++; }
+
+    c->weights = (double *)calloc((size_t)out_size * (size_t)(kept ? kept : 1), sizeof(double));
+    c->indices = (int32_t *)calloc((size_t)out_size * (size_t)(kept ? kept : 1), sizeof(int32_t));
+    if (!c->weights || !c->indices) goto nomem;
+    for (y = 0; y < out_size; y++) { /* ref:616-624 */
+        int k = 0;
+        contribution_row(y, in_size, scale, kw, P, row_w, row_i);
+        for (x = 0; x < P; x++)
+            if (keep[x]) {
+                c->weights[(size_t)y * kept + k] = row_w[x];
+                c->indices[(size_t)y * kept + k] = row_i[x];
+                k++;
+            }
+    }
+    c->weights_sz = kept;
+    c->out_size = out_size;
+    free(row_w); free(row_i); free(keep);
+    return PPMX_OK;
+nomem:
+    free(row_w); free(row_i); free(keep);
+    ppmx_contributions_free(c);
+    BAIL("error. allocating memory for weights and indices\n");
+}
+
+void ppmx_contributions_free(ppmx_contributions *c)
+{
+    if (!c) return;
+    free(c->weights);
+    free(c->indices);
+    memset(c, 0, sizeof(*c));
+}
+
+/* ------------------------------------------------------------------ operators on device rasters */
+
+static void set_new(ppmx_image_handler *h, ppmx_gpu_image *img)
+{
+    unsigned int w = 0, hh = 0;
+    h->imginfo.new_buff = img;
+    ppmx_gpu_image_info(img, &w, &hh, NULL, NULL, NULL);
+    h->imginfo.new_width = w;
+    h->imginfo.new_height = hh;
+}
+
+static int run_simple(ppmx_image_handler *h, int kind, int flip_dir)
+{
+    ppmx_op op;
+    ppmx_gpu_image *out = NULL;
+    memset(&op, 0, sizeof(op));
+    op.kind = kind;
+    op.flip_direction = flip_dir;
+    if (!h || !h->ctx || !h->imginfo.buff) BAIL("Error: no image loaded\n");
+    if (ppmx_gpu_op(h->ctx, &op, h->imginfo.buff, &out, NULL) != PPMX_OK) return PPMX_ERROR;
+    set_new(h, out);
+    return PPMX_OK;
+}
+
+int ppmx_gray(ppmx_image_handler *h)
+{
+    if (run_simple(h, PPMX_OP_GRAY, 0) != PPMX_OK) return PPMX_ERROR;
+    h->imginfo.file_type = PPMX_FILETYPE_PGM; /* ref:991 */
+    return PPMX_OK;
+}
+
+int ppmx_mono(ppmx_image_handler *h)
+{
+    if (run_simple(h, PPMX_OP_MONO, 0) != PPMX_OK) return PPMX_ERROR;
+    h->imginfo.file_type = PPMX_FILETYPE_PBM; /* ref:956 */
+    return PPMX_OK;
+}
+
+int ppmx_flip(ppmx_image_handler *h, unsigned char flip_direction)
+{
+    /* the reference swaps inside buff and points new_buff at it (ref:896); the device kernel
+     * writes a fresh raster which then takes buff's place */
+    if (run_simple(h, PPMX_OP_FLIP, flip_direction ? 1 : 0) != PPMX_OK) return PPMX_ERROR;
+    ppmx_gpu_image_free(h->ctx, h->imginfo.buff);
+    h->imginfo.buff = h->imginfo.new_buff;
+    return PPMX_OK;
+}
+
+static void fill_rotate_op(ppmx_op *op, double angle, unsigned int w, unsigned int h)
+{
+    const double th = (angle * PPMX_PI) / 180.0; /* ref:692 */
+    memset(op, 0, sizeof(*op));
+    op->kind = PPMX_OP_ROTATE;
+    op->angle_deg = (int32_t)angle;
+    op->cos_t = cos(th); /* the two loop-invariant libm values of ref:741-742 */
+    op->sin_t = sin(th);
+    rotated_size(angle, w, h, &op->new_width, &op->new_height);
+}
+
+int ppmx_rotate(ppmx_image_handler *h)
+{
+    ppmx_op op;
+    ppmx_gpu_image *out = NULL;
+    if (!h || !h->ctx || !h->imginfo.buff) BAIL("Error: no image loaded\n");
+    fill_rotate_op(&op, h->angle, h->imginfo.width, h->imginfo.height);
+    h->imginfo.new_width = op.new_width;
+    h->imginfo.new_height = op.new_height;
+    if (h->angle == 0) { /* ref:701-705 */
+        h->norotate = 1;
+        h->imginfo.new_buff = h->imginfo.buff;
+        return PPMX_OK;
+    }
+    if (ppmx_gpu_op(h->ctx, &op, h->imginfo.buff, &out, NULL) != PPMX_OK) return PPMX_ERROR;
+    set_new(h, out);
+    return PPMX_OK;
+}
+
+int ppmx_imresize(ppmx_image_handler *h, int out_size, int dim, const double *weights, const int32_t *indices,
+                  int weights_sz)
+{
+    ppmx_op op;
+    ppmx_gpu_image *out = NULL;
+    if (!h || !h->ctx || !h->imginfo.buff) BAIL("Error: no image loaded\n");
+    memset(&op, 0, sizeof(op));
+    op.kind = PPMX_OP_IMRESIZE;
+    op.dim = dim;
+    op.out_size = out_size;
+    op.weights_sz = weights_sz;
+    op.weights = weights;
+    op.indices = indices;
+    if (ppmx_gpu_op(h->ctx, &op, h->imginfo.buff, &out, NULL) != PPMX_OK) return PPMX_ERROR;
+    set_new(h, out);
+    return PPMX_OK;
+}
+
+void ppmx_renewBuffer(ppmx_image_handler *h)
+{
+    if (h->imginfo.buff && h->imginfo.buff != h->imginfo.new_buff) ppmx_gpu_image_free(h->ctx, h->imginfo.buff);
+    h->imginfo.buff = h->imginfo.new_buff;
+    h->imginfo.height = h->imginfo.new_height;
+    h->imginfo.width = h->imginfo.new_width;
+    h->imginfo.new_buff = NULL;
+}
+
+/* ------------------------------------------------------------------ the op chain as data */
+
+int ppmx_plan_chain(const ppmx_args_flag *f, unsigned int output_width_size, double angle, unsigned int width,
+                    unsigned int height, ppmx_plan *plan)
+{
+    unsigned int w = width, h = height;
+    const int renew = f->resize_enable || f->rotate_enable; /* the condition of ref:1138,1143,1148,1153 */
+    int n = 0;
+    memset(plan, 0, sizeof(*plan));
+
+    if (f->resize_enable) { /* ref:1084-1130 */
+        double scale[2];
+        unsigned int new_w = output_width_size, new_h;
+        int first, second, pass;
+        if ((int)new_w < 1) BAIL("invalid option for new width\n"); /* ref:1096 */
+        scale[1] = (double)((double)new_w / w);                      /* ref:1098 */
+        new_h = (unsigned int)((double)h * scale[1]);                /* ref:1099 */
+        scale[0] = (double)((double)new_h / h);                      /* ref:1100 */
+        if (scale[0] < scale[1]) { first = 0; second = 1; }          /* ref:1102-1103 */
+        else { first = 1; second = 0; }
+        if (ppmx_calc_contributions((int)h, (int)new_h, scale[0], 4.0, &plan->contrib[0]) != PPMX_OK) goto bad;
+        if (ppmx_calc_contributions((int)w, (int)new_w, scale[1], 4.0, &plan->contrib[1]) != PPMX_OK) goto bad;
+        for (pass = 0; pass < 2; pass++) { /* ref:1115-1120 */
+            int dim = pass ? second : first;
+            ppmx_op *op = &plan->ops[n++];
+            op->kind = PPMX_OP_IMRESIZE;
+            op->renew_before = pass; /* renewBuffer between the passes, ref:1118 */
+            op->dim = dim;
+            op->out_size = dim ? (int)new_w : (int)new_h;
+            op->weights_sz = plan->contrib[dim].weights_sz;
+            op->weights = plan->contrib[dim].weights;
+            op->indices = plan->contrib[dim].indices;
+        }
+        w = new_w;
+        h = new_h;
+    }
+    if (f->rotate_enable) { /* ref:1132-1135 */
+        ppmx_op *op = &plan->ops[n++];
+        fill_rotate_op(op, angle, w, h);
+        op->renew_before = f->resize_enable ? 1 : 0;
+        if (angle != 0) { w = op->new_width; h = op->new_height; }
+    }
+    if (f->gray_enable) { /* ref:1137-1140 */
+        plan->ops[n].kind = PPMX_OP_GRAY;
+        plan->ops[n++].renew_before = renew;
+    }
+    if (f->mono_enable) { /* ref:1142-1145 */
+        plan->ops[n].kind = PPMX_OP_MONO;
+        plan->ops[n++].renew_before = renew;
+    }
+    if (f->flipv_enable) { /* ref:1147-1150 */
+        plan->ops[n].kind = PPMX_OP_FLIP;
+        plan->ops[n].flip_direction = 1;
+        plan->ops[n++].renew_before = renew;
+    }
+    if (f->fliph_enable) { /* ref:1152-1155 */
+        plan->ops[n].kind = PPMX_OP_FLIP;
+        plan->ops[n].flip_direction = 0;
+        plan->ops[n++].renew_before = renew;
+    }
+    plan->nops = n;
+    return PPMX_OK;
+bad:
+    ppmx_plan_free(plan);
+    return PPMX_ERROR;
+}
+
+void ppmx_plan_free(ppmx_plan *plan)
+{
+    if (!plan) return;
+    ppmx_contributions_free(&plan->contrib[0]);
+    ppmx_contributions_free(&plan->contrib[1]);
+    plan->nops = 0;
+}
+
+/* ------------------------------------------------------------------ P6 in, P6/P5/P4 out */
+
+/* cursor over the in-memory file with the reference's lookahead rules (ref:333-347) */
+typedef struct {
+    const unsigned char *p;
+    size_t n, i;
+    int cur; /* current character or EOF */
+} hdr_cursor;
+
+static void hdr_next(hdr_cursor *c)
+{
+    if (c->cur == EOF) return;
+    c->cur = (c->i < c->n) ? c->p[c->i++] : EOF;
+    if (c->cur == '#') { /* a comment reads as one newline, ref:341-346 */
+        while (c->i < c->n && c->p[c->i] != '\n') c->i++;
+        if (c->i < c->n) c->i++;
+        c->cur = '\n';
+    }
+}
+
+/* returns 0 for a number (value in *v), 1 for the magic word P6, -1 otherwise (ref:360-394) */
+static int hdr_token(hdr_cursor *c, unsigned int *v)
+{
+    char word[16];
+    int k = 0;
+    while (c->cur != EOF && isspace(c->cur)) hdr_next(c);
+    if (c->cur != EOF && isdigit(c->cur)) {
+        do {
+            if (k < (int)sizeof(word) - 1) word[k++] = (char)c->cur;
+            hdr_next(c);
+        } while (c->cur != EOF && isdigit(c->cur));
+        word[k] = 0;
+        *v = (unsigned int)atoi(word);
+        return 0;
+    }
+    if (c->cur != EOF && isalpha(c->cur)) {
+        do {
+            if (k < (int)sizeof(word) - 1) word[k++] = (char)c->cur;
+            hdr_next(c);
+        } while (c->cur != EOF && isalnum(c->cur));
+        word[k] = 0;
+        hdr_next(c); /* the reference steps once more after a word, ref:388 */
+        return strcmp(word, "P6") == 0 ? 1 : -2;
+    }
+    return -1;
+}
+
+int ppmx_parse_header(const unsigned char *file, size_t filesize, unsigned int *width, unsigned int *height,
+                      unsigned int *max_color, size_t *raster_offset)
+{
+    hdr_cursor c;
+    unsigned int v = 0;
+    size_t need;
+    int t;
+    c.p = file; c.n = filesize; c.i = 0; c.cur = '\n'; /* ref:1072-1073 */
+
+    t = hdr_token(&c, &v);
+    if (t == -1) BAIL("error in getting next token. wrong format.\n"); /* ref:416 */
+    if (t != 1) BAIL("error. invalid file format.\n");                  /* ref:417: only P6 */
+    t = hdr_token(&c, width);
+    if (t == -1) BAIL("error in getting next token. wrong format.\n");
+    if (t != 0) BAIL("error. invalid file format. unable to parse width from input file.\n");
+    t = hdr_token(&c, height);
+    if (t == -1) BAIL("error in getting next token. wrong format.\n");
+    if (t != 0) BAIL("error. invalid file format. unable to parse height from input file.\n");
+    t = hdr_token(&c, max_color);
+    if (t == -1) BAIL("error in getting next token. wrong format.\n");
+    if (t != 0) BAIL("error. invalid file format. unable to parse maximum color from input file.\n");
+
+    /* one byte per channel always (ref:316-318); the file must end exactly with the raster */
+    need = (size_t)(*width) * (size_t)(*height) * 3;
+    if (need >= 3 && c.i + need - 3 > filesize) BAIL("Error: unexpected end of file.\n"); /* ref:315 */
+    if (c.i + need != filesize) BAIL("file format error\n");                              /* ref:453 */
+    *raster_offset = c.i;
+    return PPMX_OK;
+}
+
+int ppmx_format_header(char *dst, size_t cap, int file_type, unsigned int width, unsigned int height,
+                       unsigned int max_color)
+{
+    const char *magic = (file_type == PPMX_FILETYPE_PGM) ? "P5" : (file_type == PPMX_FILETYPE_PBM) ? "P4" : "P6";
+    if (file_type == PPMX_FILETYPE_PBM) /* P4 carries no maxval line, ref:258 */
+        return snprintf(dst, cap, "%s\n# generated by ppmx_edward\n%u %u\n", magic, width, height);
+    return snprintf(dst, cap, "%s\n# generated by ppmx_edward\n%u %u\n%u\n", magic, width, height, max_color);
+}
+
+static int read_whole_file(ppmx_image_handler *h)
+{
+    FILE *fp = fopen(h->filename, "rb");
+    long sz;
+    if (!fp) BAIL("error. can not open file\n"); /* ref:1059 */
+    if (fseek(fp, 0, SEEK_END) < 0) { fclose(fp); BAIL("error. can not set file position in fseek.\n"); }
+    sz = ftell(fp);
+    rewind(fp);
+    h->filesize = (size_t)(sz < 0 ? 0 : sz);
+    /* straight into pinned memory: after the header this IS the packed raster (ref:316-318) */
+    h->file_buffer = (unsigned char *)ppmx_gpu_host_alloc(h->ctx, h->filesize + 1);
+    if (!h->file_buffer) { fclose(fp); BAIL("error. can not allocate memory\n"); }
+    if (fread(h->file_buffer, 1, h->filesize, fp) != h->filesize) {
+        fclose(fp);
+        BAIL("error in reading input file.\n"); /* ref:1069 */
+    }
+    fclose(fp);
+    return PPMX_OK;
+}
+
+int ppmx_getImageInfo(ppmx_image_handler *h)
+{
+    unsigned int w = 0, hh = 0, mx = 0;
+    size_t off = 0;
+    if (ppmx_parse_header(h->file_buffer, h->filesize, &w, &hh, &mx, &off) != PPMX_OK) return PPMX_ERROR;
+    h->imginfo.file_type = PPMX_FILETYPE_PPM; /* ref:418 */
+    h->imginfo.width = w;
+    h->imginfo.height = hh;
+    h->imginfo.max_color = mx;
+    h->imginfo.size = hh * w;
+    h->imginfo.new_width = h->imginfo.new_height = 0;
+    h->index_buffer = off;
+    if (ppmx_gpu_upload(h->ctx, h->file_buffer + off, w, hh, PPMX_LAYOUT_RGB8, &h->imginfo.buff) != PPMX_OK)
+        BAIL("error. can not allocate memory\n");
+    return PPMX_OK;
+}
+
+static int write_output(const char *in_name, int file_type, unsigned int w, unsigned int h, unsigned int maxval,
+                        const unsigned char *raster, size_t nbytes)
+{
+    char header[96];
+    size_t len = strlen(in_name);
+    char *name = (char *)malloc(len + 5);
+    FILE *fp;
+    int hl;
+    if (!name) BAIL("error. can not allocate memory\n");
+    memcpy(name, in_name, len);
+    memcpy(name + len, ".out", 5); /* ref:229-233 */
+    fp = fopen(name, "wb");
+    free(name);
+    if (!fp) BAIL("Error: unable to open file for writing\n"); /* ref:237 */
+    hl = ppmx_format_header(header, sizeof(header), file_type, w, h, maxval);
+    if (fwrite(header, 1, (size_t)hl, fp) != (size_t)hl || (nbytes && fwrite(raster, 1, nbytes, fp) != nbytes)) {
+        fclose(fp);
+        BAIL("Error: failed in writing to file\n");
+    }
+    fclose(fp);
+    return PPMX_OK;
+}
+
+int ppmx_putImageToFile(ppmx_image_handler *h)
+{
+    size_t cap, n = 0;
+    unsigned char *out;
+    int rc;
+    if (h->imginfo.new_buff == NULL) BAIL("Error: no data to write\n"); /* ref:235 */
+    cap = (size_t)h->imginfo.new_width * h->imginfo.new_height * 3 + 16;
+    out = (unsigned char *)ppmx_gpu_host_alloc(h->ctx, cap);
+    if (!out) BAIL("error. can not allocate memory\n");
+    rc = ppmx_gpu_download(h->ctx, h->imginfo.new_buff, (int)h->imginfo.file_type, out, cap, &n);
+    if (rc == PPMX_OK)
+        rc = write_output(h->filename, (int)h->imginfo.file_type, h->imginfo.new_width, h->imginfo.new_height,
+                          h->imginfo.max_color, out, n);
+    ppmx_gpu_host_free(h->ctx, out);
+    /* the writer releases new_buff (ref:293-298); buff goes with it when it is the same raster */
+    if (h->imginfo.new_buff == h->imginfo.buff) h->imginfo.buff = NULL;
+    ppmx_gpu_image_free(h->ctx, h->imginfo.new_buff);
+    h->imginfo.new_buff = NULL;
+    return rc;
+}
+
+int ppmx_doProcessPPM(ppmx_image_handler *h)
+{
+    ppmx_plan plan;
+    unsigned int w = 0, hh = 0, mx = 0, ow = 0, oh = 0;
+    size_t off = 0, cap, n = 0, i;
+    unsigned char *out = NULL;
+    int own_ctx = 0, ft = PPMX_FILETYPE_PPM, rc = PPMX_ERROR;
+
+    memset(&plan, 0, sizeof(plan));
+    if (!h->ctx) {
+        const char *dev = getenv("PPMX_DEVICE");
+        if (ppmx_gpu_init(&h->ctx, dev ? atoi(dev) : 0) != PPMX_OK) return PPMX_ERROR;
+        own_ctx = 1;
+    }
+    if (read_whole_file(h) != PPMX_OK) goto done;
+    if (ppmx_parse_header(h->file_buffer, h->filesize, &w, &hh, &mx, &off) != PPMX_OK) goto done;
+    h->imginfo.width = w; h->imginfo.height = hh; h->imginfo.max_color = mx; h->index_buffer = off;
+
+    if (ppmx_plan_chain(&h->arg_flag, h->output_width_size, h->angle, w, hh, &plan) != PPMX_OK) goto done;
+    if (plan.nops == 0) { printf("Error: no data to write\n"); goto done; } /* ref:235 */
+
+    /* the largest raster any stage can hand to the writer is RGB at the final size */
+    ow = w; oh = hh;
+    for (i = 0; i < (size_t)plan.nops; i++) {
+        int lay = PPMX_LAYOUT_RGB8;
+        if (plan.ops[i].kind == PPMX_OP_IMRESIZE || plan.ops[i].kind == PPMX_OP_ROTATE)
+            ppmx_gpu_op_output(&plan.ops[i], ow, oh, PPMX_LAYOUT_RGB8, &ow, &oh, &lay);
+    }
+    cap = (size_t)ow * oh * 3 + 16;
+    out = (unsigned char *)ppmx_gpu_host_alloc(h->ctx, cap);
+    if (!out) { printf("error. can not allocate memory\n"); goto done; }
+
+    if (ppmx_gpu_apply(h->ctx, plan.ops, plan.nops, h->file_buffer + off, w, hh, out, cap, &n, &ow, &oh, &ft) != PPMX_OK)
+        goto done;
+    h->imginfo.new_width = ow; h->imginfo.new_height = oh; h->imginfo.file_type = (unsigned int)ft;
+    rc = write_output(h->filename, ft, ow, oh, mx, out, n);
+done:
+    ppmx_plan_free(&plan);
+    if (out) ppmx_gpu_host_free(h->ctx, out);
+    if (h->file_buffer) { ppmx_gpu_host_free(h->ctx, h->file_buffer); h->file_buffer = NULL; }
+    if (own_ctx) { ppmx_gpu_free(h->ctx); h->ctx = NULL; }
+    return rc;
+}
+
+/* ------------------------------------------------------------------ command line */
+
+void ppmx_usage(void)
+{
+    printf("ppmx-edward [options] (input filename)\n");
+    printf("Options -fv  Flip vertically\n");
+    printf("        -fh  Flip horizontally\n");
+    printf("        -w(new width) Scale to the new width\n");
+    printf("        -w100 means new width is 100\n");
+    printf("        -r(angle)  Rotate (CW)\n");
+    printf("        -r30 means rotate 30 degree CW.\n");
+    printf("        -mono Convert to bilevel (.pbm) format\n");
+    printf("        -gray  Convert to grayscale (.pgm) format\n");
+}
+
+static int all_digits(const char *s)
+{
+    for (; *s; s++)
+        if (!isdigit((unsigned char)*s)) return 0;
+    return 1;
+}
+
+int ppmx_main(int argc, char *argv[])
+{
+    ppmx_image_handler hd;
+    int i, have_file = 0;
+    memset(&hd, 0, sizeof(hd));
+
+    for (i = 1; i < argc; i++) { /* same options, checks and messages as ref:125-183 */
+        const char *a = argv[i];
+        if (a[0] != '-') {
+            if (have_file) BAIL("Error: invalid options\n");
+            hd.filename = a;
+            have_file = 1;
+        } else if (a[1] == 'f') {
+            if (a[2] == 'h') {
+                if (hd.arg_flag.fliph_enable) BAIL("Error: Duplicate options not allowed\n");
+                if (hd.arg_flag.flipv_enable) BAIL("Error: Conflicting options not allowed\n");
+                hd.arg_flag.fliph_enable = 1;
+            } else if (a[2] == 'v') {
+                if (hd.arg_flag.flipv_enable) BAIL("Error: Duplicate options not allowed\n");
+                if (hd.arg_flag.fliph_enable) BAIL("Error: Conflicting options not allowed\n");
+                hd.arg_flag.flipv_enable = 1;
+            } else {
+                BAIL("Error: invalid option for flip.\nallowed options are -fh -fv only.\n");
+            }
+        } else if (a[1] == 'w') {
+            if (!all_digits(a + 2)) BAIL("Error: invalid option for scaling.\n");
+            if (hd.arg_flag.resize_enable) BAIL("Error: Duplicate options not allowed\n");
+            hd.arg_flag.resize_enable = 1;
+            hd.output_width_size = (unsigned int)atoi(a + 2);
+        } else if (a[1] == 'r') {
+            if (a[2] == 0) BAIL("Error: invalid option for rotate\n");
+            if (hd.arg_flag.rotate_enable) BAIL("Error: Duplicate options not allowed\n");
+            hd.arg_flag.rotate_enable = 1;
+            if (!all_digits(a + 2)) BAIL("Error: invalid option for rotate.\n");
+            hd.angle = (double)atoi(a + 2);
+            if (hd.angle < 0 || hd.angle >= 360) BAIL("Error: invalid option for rotate.\n");
+        } else if (strcmp(a + 1, "gray") == 0) {
+            if (hd.arg_flag.gray_enable) BAIL("Error: Duplicate options not allowed\n");
+            if (hd.arg_flag.mono_enable) BAIL("Error: Conflicting options not allowed\n");
+            hd.arg_flag.gray_enable = 1;
+        } else if (strcmp(a + 1, "mono") == 0) {
+            if (hd.arg_flag.mono_enable) BAIL("Error: Duplicate options not allowed\n");
+            if (hd.arg_flag.gray_enable) BAIL("Error: Conflicting options not allowed\n");
+            hd.arg_flag.mono_enable = 1;
+        } else {
+            printf("Error: invalid option: %s\n", a + 1);
+            ppmx_usage();
+            return PPMX_ERROR;
+        }
+    }
+    if (!have_file) {
+        ppmx_usage();
+        return PPMX_ERROR;
+    }
+    return ppmx_doProcessPPM(&hd) != 0 ? PPMX_ERROR : 0;
+}

@@ -1,0 +1,812 @@
+// ppmx_kernels.cu -- hand-written sm_100a kernels for the per-pixel loops of ppmx-edward.c.
+//
+// "ref:N" = /root/reference/ppmx-edward.c line N.  Rasters are flat, packed, row-major:
+// RGB8 = 3 bytes per pixel (the reference's `pixel`, ref:39-43), R8 = the .r member only.
+// Everything integer is done in integers; the two bicubic operators run in FP64 with
+// explicit round-to-nearest multiplies and adds (never an FMA) in the reference's order.
+//
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
+#include "ppmx_kernels.h"
+
+#include <cuda.h>
+
+namespace ppmx {
+
+int g_variant = 0;
+static unsigned long long g_launches = 0;
+unsigned long long launch_count() { return g_launches; }
+
+static int g_sm_count = 0;
+static int sm_count()
+{
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
+            g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+#define PPMX_LAUNCHED() (++g_launches, cudaGetLastError())
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned4(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+// grid size for a grid-stride kernel: whole waves of the 148 SMs, capped by the work
+static inline unsigned wave_grid(size_t work_items, unsigned block, unsigned ctas_per_sm)
+{
+    size_t need = (work_items + block - 1) / block;
+    size_t wave = (size_t)sm_count() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (unsigned)(need < wave ? need : wave);
+}
+
+// ------------------------------------------------------------------------------------------
+// integer helpers
+// ------------------------------------------------------------------------------------------
+
+// s / 3 for 0 <= s <= 765, exact (checked exhaustively in tests/test_host_logic.py)
+__device__ __forceinline__ uint32_t div3(uint32_t s) { return (s * 43691u) >> 17; }
+
+// grey of 4 consecutive pixels held in 3 little-endian words (12 bytes r0 g0 b0 r1 ...),
+// ref:1000 -- one byte per pixel, pixel 0 in the low byte.
+__device__ __forceinline__ uint32_t gray4(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t s0 = __dp4a(a, 0x00010101u, 0u);
+    uint32_t s1 = __dp4a(a, 0x01000000u, __dp4a(b, 0x00000101u, 0u));
+    uint32_t s2 = __dp4a(b, 0x01010000u, __dp4a(c, 0x00000001u, 0u));
+    uint32_t s3 = __dp4a(c, 0x01010100u, 0u);
+    return div3(s0) | (div3(s1) << 8) | (div3(s2) << 16) | (div3(s3) << 24);
+}
+
+// 16 pixels = 48 bytes = three 16-byte vectors -> 16 grey bytes
+__device__ __forceinline__ uint4 gray16(uint4 p, uint4 q, uint4 r)
+{
+    uint4 o;
+    o.x = gray4(p.x, p.y, p.z);
+    o.y = gray4(p.w, q.x, q.y);
+    o.z = gray4(q.z, q.w, r.x);
+    o.w = gray4(r.y, r.z, r.w);
+    return o;
+}
+
+// Bayer thresholds of ref:954 times 255 (all exact), in the reference's own index order
+// (x%4)*4 + (y%4), ref:967.  bit = grey < threshold  <=>  !(grey >= matrix*255).
+__constant__ uint8_t c_bayer[16] = {32, 255, 48, 208, 160, 96, 176, 112, 64, 224, 16, 240, 192, 128, 144, 80};
+
+// thresholds for 4 consecutive pixels starting at x % 4 == 0 on row y, packed like gray4's result
+__device__ __forceinline__ uint32_t bayer_row4(uint32_t y)
+{
+    uint32_t yy = y & 3u;
+    return (uint32_t)c_bayer[yy] | ((uint32_t)c_bayer[4 + yy] << 8) | ((uint32_t)c_bayer[8 + yy] << 16) |
+           ((uint32_t)c_bayer[12 + yy] << 24);
+}
+
+// 4 packed greys vs 4 packed thresholds -> nibble, pixel 0 in bit 3 (MSB first, ref:273)
+__device__ __forceinline__ uint32_t mono_nibble(uint32_t g4, uint32_t t4)
+{
+    uint32_t m = __vcmpltu4(g4, t4) & 0x01010101u;  // byte i = 1 iff grey_i < thr_i
+    return ((m * 0x08040201u) >> 24) & 0xFu;        // b0<<3 | b1<<2 | b2<<1 | b3
+}
+
+// ------------------------------------------------------------------------------------------
+// gray  (ref:998-1000)  RGB8 -> R8, flat over the raster; optional fused histogram (extension)
+// ------------------------------------------------------------------------------------------
+
+// per-CTA histogram: one 256-bin copy per warp in shared memory, merged once at the end
+template <int WARPS>
+struct SmemHist {
+    uint32_t bins[WARPS][256];
+    __device__ void clear()
+    {
+        for (int i = threadIdx.x; i < WARPS * 256; i += blockDim.x) (&bins[0][0])[i] = 0;
+    }
+    __device__ __forceinline__ void add4(uint32_t g4)
+    {
+        uint32_t *b = bins[threadIdx.x >> 5];
+        atomicAdd(&b[g4 & 0xFF], 1u);
+        atomicAdd(&b[(g4 >> 8) & 0xFF], 1u);
+        atomicAdd(&b[(g4 >> 16) & 0xFF], 1u);
+        atomicAdd(&b[g4 >> 24], 1u);
+    }
+    __device__ __forceinline__ void add1(uint32_t g) { atomicAdd(&bins[threadIdx.x >> 5][g & 0xFF], 1u); }
+    __device__ void flush(unsigned long long *d_hist)
+    {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            unsigned long long t = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) t += bins[w][i];
+            if (t) atomicAdd(&d_hist[i], t);
+        }
+    }
+};
+
+template <bool HIST, bool STORE>
+__global__ void __launch_bounds__(256) gray_vec_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
+                                                       size_t ngroups, size_t npix, unsigned long long *d_hist)
+{
+    __shared__ SmemHist<HIST ? 8 : 1> sh;
+    if (HIST) {
+        sh.clear();
+        __syncthreads();
+    }
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+        const uint4 *p = src + 3 * g;
+        uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        uint4 o = gray16(a, b, c);
+        if (STORE) dst[g] = o;
+        if (HIST) {
+            sh.add4(o.x);
+            sh.add4(o.y);
+            sh.add4(o.z);
+            sh.add4(o.w);
+        }
+    }
+    // the last (npix % 16) pixels, scalar
+    if (blockIdx.x == 0 && threadIdx.x < (npix - ngroups * 16)) {
+        size_t i = ngroups * 16 + threadIdx.x;
+        const uint8_t *s8 = reinterpret_cast<const uint8_t *>(src) + 3 * i;
+        uint32_t g = div3((uint32_t)s8[0] + s8[1] + s8[2]);
+        if (STORE) reinterpret_cast<uint8_t *>(dst)[i] = (uint8_t)g;
+        if (HIST) sh.add1(g);
+    }
+    if (HIST) {
+        __syncthreads();
+        sh.flush(d_hist);
+    }
+}
+
+// any alignment: one pixel per thread
+template <bool HIST, bool STORE>
+__global__ void __launch_bounds__(256) gray_scalar_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                          size_t npix, unsigned long long *d_hist)
+{
+    __shared__ SmemHist<HIST ? 8 : 1> sh;
+    if (HIST) {
+        sh.clear();
+        __syncthreads();
+    }
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        uint32_t g = div3((uint32_t)src[3 * i] + src[3 * i + 1] + src[3 * i + 2]);
+        if (STORE) dst[i] = (uint8_t)g;
+        if (HIST) sh.add1(g);
+    }
+    if (HIST) {
+        __syncthreads();
+        sh.flush(d_hist);
+    }
+}
+
+template <bool HIST, bool STORE>
+static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, unsigned long long *d_hist,
+                                 cudaStream_t s)
+{
+    if (npix == 0) return cudaSuccess;
+    if (aligned16(src) && (!STORE || aligned16(dst))) {
+        size_t ngroups = npix / 16;
+        unsigned grid = wave_grid(ngroups ? ngroups : 1, 256, 8);
+        gray_vec_kernel<HIST, STORE><<<grid, 256, 0, s>>>(reinterpret_cast<const uint4 *>(src),
+                                                          reinterpret_cast<uint4 *>(dst), ngroups, npix, d_hist);
+    } else {
+        gray_scalar_kernel<HIST, STORE><<<wave_grid(npix, 256, 8), 256, 0, s>>>(src, dst, npix, d_hist);
+    }
+    return PPMX_LAUNCHED();
+}
+
+cudaError_t gray(const uint8_t *src, uint8_t *dst, size_t npix, unsigned long long *d_hist, cudaStream_t s)
+{
+    return d_hist ? gray_dispatch<true, true>(src, dst, npix, d_hist, s)
+                  : gray_dispatch<false, true>(src, dst, npix, nullptr, s);
+}
+
+cudaError_t hist_gray(const uint8_t *src, size_t npix, unsigned long long *d_hist, cudaStream_t s)
+{
+    return gray_dispatch<true, false>(src, nullptr, npix, d_hist, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// mono  (ref:964-969), alone (R8 of 0/1) and fused with the P4 packer (ref:268-284)
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) mono_plane_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                         uint32_t w, uint32_t h, uint32_t y0)
+{
+    const size_t n = (size_t)w * h, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t y = (uint32_t)(i / w), x = (uint32_t)(i - (size_t)y * w);
+        uint32_t g = div3((uint32_t)src[3 * i] + src[3 * i + 1] + src[3 * i + 2]);
+        dst[i] = (g < c_bayer[(x & 3u) * 4 + ((y + y0) & 3u)]) ? 1 : 0;
+    }
+}
+
+// w % 32 == 0 and 16-byte aligned rasters: one thread = 32 pixels (96 B in) = one output word
+__global__ void __launch_bounds__(256) mono_bits_vec_kernel(const uint4 *__restrict__ src, uint32_t *__restrict__ dst,
+                                                            uint32_t words_per_row, size_t nwords, uint32_t y0)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
+        uint32_t y = (uint32_t)(i / words_per_row) + y0;
+        uint32_t t4 = bayer_row4(y);
+        const uint4 *p = src + 6 * i;
+        uint32_t out = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {  // 16 pixels per half -> two output bytes
+            uint4 a = __ldg(p + 3 * half), b = __ldg(p + 3 * half + 1), c = __ldg(p + 3 * half + 2);
+            uint32_t n0 = mono_nibble(gray4(a.x, a.y, a.z), t4);
+            uint32_t n1 = mono_nibble(gray4(a.w, b.x, b.y), t4);
+            uint32_t n2 = mono_nibble(gray4(b.z, b.w, c.x), t4);
+            uint32_t n3 = mono_nibble(gray4(c.y, c.z, c.w), t4);
+            uint32_t two = ((n0 << 4) | n1) | (((n2 << 4) | n3) << 8);
+            out |= two << (16 * half);
+        }
+        dst[i] = out;
+    }
+}
+
+// any width / alignment: one thread = one output byte (up to 8 pixels of one row)
+__global__ void __launch_bounds__(256) mono_bits_generic_kernel(const uint8_t *__restrict__ src,
+                                                                uint8_t *__restrict__ dst, uint32_t w, uint32_t h,
+                                                                uint32_t row_bytes, uint32_t y0)
+{
+    const size_t n = (size_t)row_bytes * h, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t y = (uint32_t)(i / row_bytes), bx = (uint32_t)(i - (size_t)y * row_bytes);
+        uint32_t x0 = bx * 8, cnt = min(8u, w - x0), yy = (y + y0) & 3u;
+        const uint8_t *p = src + ((size_t)y * w + x0) * 3;
+        uint32_t out = 0;
+        for (uint32_t j = 0; j < cnt; j++) {
+            uint32_t g = div3((uint32_t)p[3 * j] + p[3 * j + 1] + p[3 * j + 2]);
+            if (g < c_bayer[((x0 + j) & 3u) * 4 + yy]) out |= 0x80u >> j;
+        }
+        dst[i] = (uint8_t)out;
+    }
+}
+
+cudaError_t mono_plane(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t y0, cudaStream_t s)
+{
+    size_t n = (size_t)w * h;
+    if (!n) return cudaSuccess;
+    mono_plane_kernel<<<wave_grid(n, 256, 8), 256, 0, s>>>(src, dst, w, h, y0);
+    return PPMX_LAUNCHED();
+}
+
+cudaError_t mono_bits(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t y0, cudaStream_t s)
+{
+    if (!w || !h) return cudaSuccess;
+    if ((w % 32u) == 0 && aligned16(src) && aligned4(dst)) {
+        size_t nwords = (size_t)(w / 32u) * h;
+        mono_bits_vec_kernel<<<wave_grid(nwords, 256, 8), 256, 0, s>>>(
+            reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint32_t *>(dst), w / 32u, nwords, y0);
+    } else {
+        uint32_t rb = (w + 7u) / 8u;
+        mono_bits_generic_kernel<<<wave_grid((size_t)rb * h, 256, 8), 256, 0, s>>>(src, dst, w, h, rb, y0);
+    }
+    return PPMX_LAUNCHED();
+}
+
+// the P4 writer alone (ref:268-284) on arbitrary .r bytes: byte |= (r << (7 - x%8)) & 0xff
+__global__ void __launch_bounds__(256) pack_pbm_kernel(const uint8_t *__restrict__ src, int bpp,
+                                                       uint8_t *__restrict__ dst, uint32_t w, uint32_t h,
+                                                       uint32_t row_bytes)
+{
+    const size_t n = (size_t)row_bytes * h, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t y = (uint32_t)(i / row_bytes), bx = (uint32_t)(i - (size_t)y * row_bytes);
+        uint32_t x0 = bx * 8, cnt = min(8u, w - x0);
+        const uint8_t *p = src + ((size_t)y * w + x0) * bpp;
+        uint32_t out = 0;
+        for (uint32_t j = 0; j < cnt; j++) out |= ((uint32_t)p[(size_t)j * bpp] << (7 - j));
+        dst[i] = (uint8_t)(out & 0xFFu);
+    }
+}
+
+cudaError_t pack_pbm(const uint8_t *src, int src_bpp, uint8_t *dst, uint32_t w, uint32_t h, cudaStream_t s)
+{
+    if (!w || !h) return cudaSuccess;
+    uint32_t rb = (w + 7u) / 8u;
+    pack_pbm_kernel<<<wave_grid((size_t)rb * h, 256, 8), 256, 0, s>>>(src, src_bpp, dst, w, h, rb);
+    return PPMX_LAUNCHED();
+}
+
+// the PGM writer's gather (ref:263-267): .r of every pixel
+__global__ void __launch_bounds__(256) extract_r_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                        size_t npix)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) dst[i] = src[3 * i];
+}
+
+cudaError_t extract_r(const uint8_t *src, uint8_t *dst, size_t npix, cudaStream_t s)
+{
+    if (!npix) return cudaSuccess;
+    extract_r_kernel<<<wave_grid(npix, 256, 8), 256, 0, s>>>(src, dst, npix);
+    return PPMX_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// flip  (ref:898-911).  The reference swaps in place; here dst != src, same bytes out.
+// ------------------------------------------------------------------------------------------
+
+// vertical: row y of dst = row h-1-y of src; T = widest type the row pitch and pointers allow
+template <typename T>
+__global__ void __launch_bounds__(256) flipv_kernel(const T *__restrict__ src, T *__restrict__ dst,
+                                                    uint32_t row_elems, uint32_t h)
+{
+    const size_t n = (size_t)row_elems * h, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t y = (uint32_t)(i / row_elems), e = (uint32_t)(i - (size_t)y * row_elems);
+        dst[i] = src[(size_t)(h - 1 - y) * row_elems + e];
+    }
+}
+
+// horizontal, any pixel size / alignment: one byte per thread
+__global__ void __launch_bounds__(256) fliph_generic_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                            uint32_t w, uint32_t h, int bpp)
+{
+    const size_t row = (size_t)w * bpp, n = row * h, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        size_t y = i / row;
+        uint32_t b = (uint32_t)(i - y * row), x = b / bpp, c = b - x * bpp;
+        dst[i] = src[y * row + (size_t)(w - 1 - x) * bpp + c];
+    }
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[12], int i) { return (w[i >> 2] >> (8 * (i & 3))) & 0xFFu; }
+
+// reverse the order of 16 RGB pixels held in 12 words
+__device__ __forceinline__ void reverse16px(const uint32_t (&in)[12], uint32_t (&out)[12])
+{
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int o = 4 * k + j;                       // output byte
+            int i = 3 * (15 - o / 3) + (o % 3);      // input byte: same channel of the mirrored pixel
+            v |= byte_of(in, i) << (8 * j);
+        }
+        out[k] = v;
+    }
+}
+
+// horizontal RGB8, w % 16 == 0, aligned: a thread moves one 16-pixel group (48 B) to its mirror slot
+__global__ void __launch_bounds__(256) fliph_rgb16_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
+                                                          uint32_t groups_per_row, size_t ngroups)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ngroups; i += stride) {
+        size_t y = i / groups_per_row;
+        uint32_t g = (uint32_t)(i - y * groups_per_row);
+        const uint4 *p = src + 3 * (y * groups_per_row + (groups_per_row - 1 - g));
+        uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        uint32_t in[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w}, o[12];
+        reverse16px(in, o);
+        uint4 *q = dst + 3 * i;
+        q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        q[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    }
+}
+
+cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int bpp, int vertical, cudaStream_t s)
+{
+    if (!w || !h) return cudaSuccess;
+    size_t row = (size_t)w * bpp;
+    if (vertical) {
+        if (row % 16 == 0 && aligned16(src) && aligned16(dst)) {
+            size_t n = row / 16 * h;
+            flipv_kernel<uint4><<<wave_grid(n, 256, 8), 256, 0, s>>>(reinterpret_cast<const uint4 *>(src),
+                                                                    reinterpret_cast<uint4 *>(dst), (uint32_t)(row / 16), h);
+        } else if (row % 4 == 0 && aligned4(src) && aligned4(dst)) {
+            size_t n = row / 4 * h;
+            flipv_kernel<uint32_t><<<wave_grid(n, 256, 8), 256, 0, s>>>(
+                reinterpret_cast<const uint32_t *>(src), reinterpret_cast<uint32_t *>(dst), (uint32_t)(row / 4), h);
+        } else {
+            flipv_kernel<uint8_t><<<wave_grid(row * h, 256, 8), 256, 0, s>>>(src, dst, (uint32_t)row, h);
+        }
+    } else {
+        if (bpp == 3 && (w % 16u) == 0 && aligned16(src) && aligned16(dst)) {
+            size_t n = (size_t)(w / 16u) * h;
+            fliph_rgb16_kernel<<<wave_grid(n, 256, 8), 256, 0, s>>>(reinterpret_cast<const uint4 *>(src),
+                                                                   reinterpret_cast<uint4 *>(dst), w / 16u, n);
+        } else {
+            fliph_generic_kernel<<<wave_grid(row * h, 256, 8), 256, 0, s>>>(src, dst, w, h, bpp);
+        }
+    }
+    return PPMX_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// rotate 90 / 180 / 270  (ref:714-725): pure byte moves
+// ------------------------------------------------------------------------------------------
+
+// 180 degrees reverses the whole pixel sequence: out[n-1-p] = in[p]  (ref:721)
+__global__ void __launch_bounds__(256) reverse_pixels_kernel(const uint8_t *__restrict__ src,
+                                                             uint8_t *__restrict__ dst, size_t npix)
+{
+    const size_t n = npix * 3, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        size_t p = i / 3;
+        uint32_t c = (uint32_t)(i - p * 3);
+        dst[i] = src[(npix - 1 - p) * 3 + c];
+    }
+}
+
+// 90 / 270: transpose through a 32 x 32 pixel shared-memory tile.
+//   90:  out[x][h-1-y] = in[y][x]   (ref:717)      out is h wide, w tall
+//   270: out[w-1-x][y] = in[y][x]   (ref:725)
+constexpr int RT = 32;            // tile edge in pixels
+constexpr int RT_PITCH = RT * 3 + 4;  // bytes; +4 keeps column reads off a single bank
+
+template <bool CW>
+__global__ void __launch_bounds__(256) rotate_transpose_kernel(const uint8_t *__restrict__ src,
+                                                               uint8_t *__restrict__ dst, uint32_t w, uint32_t h)
+{
+    __shared__ uint8_t tile[RT][RT_PITCH];
+    const uint32_t tx0 = blockIdx.x * RT, ty0 = blockIdx.y * RT;
+    const uint32_t tw = min((uint32_t)RT, w - tx0), th = min((uint32_t)RT, h - ty0);
+    const size_t in_pitch = (size_t)w * 3, out_pitch = (size_t)h * 3;
+
+    for (uint32_t i = threadIdx.x; i < th * tw * 3; i += blockDim.x) {
+        uint32_t r = i / (tw * 3), b = i - r * (tw * 3);
+        tile[r][b] = src[(size_t)(ty0 + r) * in_pitch + (size_t)tx0 * 3 + b];
+    }
+    __syncthreads();
+    // the output tile has tw rows of th pixels
+    for (uint32_t i = threadIdx.x; i < tw * th * 3; i += blockDim.x) {
+        uint32_t orow = i / (th * 3), ob = i - orow * (th * 3), opx = ob / 3, ch = ob - opx * 3;
+        if (CW) {  // out row = x, out col = h-1-y: columns run against y
+            uint32_t r = th - 1 - opx;
+            size_t ocol0 = (size_t)(h - ty0 - th);
+            dst[(size_t)(tx0 + orow) * out_pitch + (ocol0 + opx) * 3 + ch] = tile[r][orow * 3 + ch];
+        } else {  // out row = w-1-x, out col = y
+            uint32_t c = tw - 1 - orow;
+            size_t orow_g = (size_t)(w - tx0 - tw) + orow;
+            dst[orow_g * out_pitch + ((size_t)ty0 + opx) * 3 + ch] = tile[opx][c * 3 + ch];
+        }
+    }
+}
+
+cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int angle, cudaStream_t s)
+{
+    if (!w || !h) return cudaSuccess;
+    if (angle == 180) {
+        size_t npix = (size_t)w * h;
+        if (npix % 16 == 0 && aligned16(src) && aligned16(dst)) {
+            size_t n = npix / 16;  // one long row of npix pixels, mirrored
+            if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+            fliph_rgb16_kernel<<<wave_grid(n, 256, 8), 256, 0, s>>>(reinterpret_cast<const uint4 *>(src),
+                                                                   reinterpret_cast<uint4 *>(dst), (uint32_t)n, n);
+        } else {
+            reverse_pixels_kernel<<<wave_grid(npix * 3, 256, 8), 256, 0, s>>>(src, dst, npix);
+        }
+        return PPMX_LAUNCHED();
+    }
+    dim3 grid((w + RT - 1) / RT, (h + RT - 1) / RT);
+    if (grid.y > 65535u) return cudaErrorInvalidValue;
+    if (angle == 90) rotate_transpose_kernel<true><<<grid, 256, 0, s>>>(src, dst, w, h);
+    else if (angle == 270) rotate_transpose_kernel<false><<<grid, 256, 0, s>>>(src, dst, w, h);
+    else return cudaErrorInvalidValue;
+    return PPMX_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 helpers: every operation is a separately rounded IEEE multiply or add, in the
+// reference's order; nvcc may not contract them (intrinsics) and the file is built -fmad=false.
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+// exact u8 -> double without the slow I2F.F64 path: 2^52 + v has v in its low mantissa bits
+__device__ __forceinline__ double u8_to_double(uint32_t v)
+{
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+
+// Keys cubic convolution kernel, a = -0.5 (ref:477-489), same association as the source
+__device__ __forceinline__ double cubic(double x)
+{
+    double a1 = fabs(x), a2 = dmul(a1, a1), a3 = dmul(a2, a1), r = 0.0;
+    if (a1 <= 1.0) r = dadd(dsub(dmul(1.5, a3), dmul(2.5, a2)), 1.0);
+    if (1.0 < a1 && a1 <= 2.0) {
+        double t = dadd(dmul(-0.5, a3), dmul(2.5, a2));
+        t = dsub(t, dmul(4.0, a1));
+        t = dadd(t, 2.0);
+        r = dadd(r, t);
+    }
+    return r;
+}
+
+__device__ __forceinline__ double round_half_up(double v) { return floor(dadd(v, 0.5)); }  // ref:27
+
+// ------------------------------------------------------------------------------------------
+// rotate, arbitrary angle  (ref:726-786): inverse map + 4x4 bicubic, nearest on a 2-pixel ring
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__restrict__ src,
+                                                             uint8_t *__restrict__ dst, uint32_t w, uint32_t h,
+                                                             uint32_t nw, uint32_t nh, double cs, double sn,
+                                                             int xc, int yc, int xo, int yo)
+{
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nw || y >= nh) return;
+    uint8_t *out = dst + ((size_t)y * nw + x) * 3;
+
+    const int x0 = ((int)x - xo) - xc, y0 = ((int)y - yo) - yc;                              // ref:731-735
+    const double nX = dadd(dadd(dmul(cs, (double)x0), dmul(sn, (double)y0)), (double)xc);     // ref:741
+    const double nY = dadd(dadd(-dmul(sn, (double)x0), dmul(cs, (double)y0)), (double)yc);    // ref:742
+    const double rx = round_half_up(nX), ry = round_half_up(nY);
+
+    uint32_t r = 0, g = 0, b = 0;  // uncovered output stays 0 (ref:727)
+    if (rx < (double)w && ry < (double)h && ry >= 0.0 && rx >= 0.0) {                         // ref:744
+        if (rx > 1.0 && ry > 1.0 && rx < (double)(uint32_t)(w - 2u) && ry < (double)(uint32_t)(h - 2u)) {  // ref:752
+            const double fx = floor(nX), fy = floor(nY);
+            double wx[4], wy[4];
+            int u0 = (int)(fx - 1.0), v0 = (int)(fy - 1.0);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int u = (int)dadd(dsub(fx, 1.0), (double)i);  // ref:761
+                int v = (int)dadd(dsub(fy, 1.0), (double)i);  // ref:758
+                wx[i] = cubic(dsub(nX, (double)u));
+                wy[i] = cubic(dsub(nY, (double)v));
+            }
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint8_t *row = src + ((size_t)(v0 + j) * w + u0) * 3;
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {  // ref:762-764
+                    p0 = dadd(p0, dmul(u8_to_double(row[3 * i]), wx[i]));
+                    p1 = dadd(p1, dmul(u8_to_double(row[3 * i + 1]), wx[i]));
+                    p2 = dadd(p2, dmul(u8_to_double(row[3 * i + 2]), wx[i]));
+                }
+                q0 = dadd(q0, dmul(p0, wy[j]));  // ref:766-768
+                q1 = dadd(q1, dmul(p1, wy[j]));
+                q2 = dadd(q2, dmul(p2, wy[j]));
+            }
+            if (q0 < 0.0) q0 = 0.0;  // ref:771-777
+            if (q1 < 0.0) q1 = 0.0;
+            if (q2 < 0.0) q2 = 0.0;
+            if (q0 >= 256.0) q0 = 255.0;
+            if (q1 >= 256.0) q1 = 255.0;
+            if (q2 >= 256.0) q2 = 255.0;
+            r = (uint32_t)__double2int_rz(q0);  // truncation, ref:779-781
+            g = (uint32_t)__double2int_rz(q1);
+            b = (uint32_t)__double2int_rz(q2);
+        } else {  // nearest, ref:783
+            const uint8_t *p = src + ((size_t)(int)ry * w + (size_t)(int)rx) * 3;
+            r = p[0];
+            g = p[1];
+            b = p[2];
+        }
+    }
+    out[0] = (uint8_t)r;
+    out[1] = (uint8_t)g;
+    out[2] = (uint8_t)b;
+}
+
+cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t nw, uint32_t nh,
+                           double cos_t, double sin_t, cudaStream_t s)
+{
+    if (!nw || !nh) return cudaSuccess;
+    // centre and offset exactly as ref:694-698 (integer halves)
+    int xc = (int)(w / 2u), yc = (int)(h / 2u);
+    int xo = (int)(nw / 2u) - (int)(w / 2u), yo = (int)(nh / 2u) - (int)(h / 2u);
+    dim3 block(32, 8), grid((nw + 31) / 32, (nh + 7) / 8);
+    if (grid.y > 65535u) return cudaErrorInvalidValue;
+    rotate_bicubic_kernel<<<grid, block, 0, s>>>(src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+    return PPMX_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// imresize  (ref:820-838 height pass, ref:846-868 width pass): K-tap gather, FP64 accumulate
+// in tap order, floor(s + 0.5), clamp, u8 store.
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t quantise(double s)
+{
+    s = round_half_up(s);                                           // ref:831
+    return (s < 0.0) ? 0u : (s >= 256.0) ? 255u : (uint32_t)__double2int_rz(s);  // ref:835
+}
+
+// height pass: every byte of an output row uses the same K source rows and weights, so the
+// raster is treated as rows of 3*w independent bytes; VEC bytes per thread.
+template <int VEC>
+__global__ void __launch_bounds__(256) imresize_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                            uint32_t row_bytes, int out_h, int taps,
+                                                            const double *__restrict__ wts, const int *__restrict__ idx)
+{
+    const uint32_t xb = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const int y = blockIdx.y;
+    if (xb >= row_bytes || y >= out_h) return;
+    const double *wy = wts + (size_t)y * taps;
+    const int *iy = idx + (size_t)y * taps;
+    double acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) acc[v] = 0.0;
+    for (int z = 0; z < taps; z++) {
+        const double wz = __ldg(wy + z);
+        const uint8_t *p = src + (size_t)__ldg(iy + z) * row_bytes + xb;
+        if (VEC == 4) {
+            uint32_t v4 = __ldg(reinterpret_cast<const uint32_t *>(p));
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[v] = dadd(acc[v], dmul(u8_to_double((v4 >> (8 * v)) & 0xFFu), wz));
+        } else {
+            acc[0] = dadd(acc[0], dmul(u8_to_double(p[0]), wz));
+        }
+    }
+    uint8_t *o = dst + (size_t)y * row_bytes + xb;
+    if (VEC == 4) {
+        uint32_t v4 = quantise(acc[0]) | (quantise(acc[1]) << 8) | (quantise(acc[2]) << 16) | (quantise(acc[3]) << 24);
+        *reinterpret_cast<uint32_t *>(o) = v4;
+    } else {
+        o[0] = (uint8_t)quantise(acc[0]);
+    }
+}
+
+// width pass: one thread = one output pixel; taps gather 3-byte pixels along the row
+__global__ void __launch_bounds__(256) imresize_cols_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                            uint32_t w, uint32_t h, int out_w, int taps,
+                                                            const double *__restrict__ wts, const int *__restrict__ idx)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out_w || y >= h) return;
+    const double *wx = wts + (size_t)x * taps;
+    const int *ix = idx + (size_t)x * taps;
+    const uint8_t *row = src + (size_t)y * w * 3;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int z = 0; z < taps; z++) {
+        const double wz = __ldg(wx + z);
+        const uint8_t *p = row + (size_t)__ldg(ix + z) * 3;
+        s0 = dadd(s0, dmul(u8_to_double(p[0]), wz));
+        s1 = dadd(s1, dmul(u8_to_double(p[1]), wz));
+        s2 = dadd(s2, dmul(u8_to_double(p[2]), wz));
+    }
+    uint8_t *o = dst + ((size_t)y * out_w + x) * 3;
+    o[0] = (uint8_t)quantise(s0);
+    o[1] = (uint8_t)quantise(s1);
+    o[2] = (uint8_t)quantise(s2);
+}
+
+cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int out_size, int dim, int taps,
+                     const double *d_weights, const int *d_indices, cudaStream_t s)
+{
+    if (out_size <= 0 || !w || !h) return cudaSuccess;
+    if (dim == 0) {
+        uint32_t row_bytes = w * 3u;
+        if (row_bytes % 4 == 0 && aligned4(src) && aligned4(dst)) {
+            dim3 grid((row_bytes / 4 + 255) / 256, 1);
+            // rows go on grid.y in slabs of <= 65535
+            for (int y0 = 0; y0 < out_size; y0 += 65535) {
+                int rows = min(65535, out_size - y0);
+                grid.y = rows;
+                imresize_rows_kernel<4><<<grid, 256, 0, s>>>(src, dst + (size_t)y0 * row_bytes, row_bytes, rows, taps,
+                                                             d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+                ++g_launches;
+            }
+        } else {
+            dim3 grid((row_bytes + 255) / 256, 1);
+            for (int y0 = 0; y0 < out_size; y0 += 65535) {
+                int rows = min(65535, out_size - y0);
+                grid.y = rows;
+                imresize_rows_kernel<1><<<grid, 256, 0, s>>>(src, dst + (size_t)y0 * row_bytes, row_bytes, rows, taps,
+                                                             d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+                ++g_launches;
+            }
+        }
+        return cudaGetLastError();
+    }
+    dim3 block(64, 4), grid((out_size + 63) / 64, (h + 3) / 4);
+    if (grid.y > 65535u) {
+        for (uint32_t y0 = 0; y0 < h; y0 += 65535u * 4u) {
+            uint32_t rows = min(65535u * 4u, h - y0);
+            dim3 g2(grid.x, (rows + 3) / 4);
+            imresize_cols_kernel<<<g2, block, 0, s>>>(src + (size_t)y0 * w * 3, dst + (size_t)y0 * out_size * 3, w, rows,
+                                                     out_size, taps, d_weights, d_indices);
+            ++g_launches;
+        }
+        return cudaGetLastError();
+    }
+    imresize_cols_kernel<<<grid, block, 0, s>>>(src, dst, w, h, out_size, taps, d_weights, d_indices);
+    return PPMX_LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// EXTENSION (no reference counterpart, parity unpinned): k x k integer convolution.
+// Border = symmetric mirror (the aux-table idiom of ref:551-555,589); result =
+// floor(acc/div + 0.5) + bias computed in integers, clamped like ref:835.
+// ------------------------------------------------------------------------------------------
+
+constexpr int CONV_MAXK = 15;
+__constant__ int32_t c_conv_coef[CONV_MAXK * CONV_MAXK];
+
+__device__ __forceinline__ int mirror_index(int i, int n)
+{
+    int m = i % (2 * n);
+    if (m < 0) m += 2 * n;
+    return m < n ? m : 2 * n - 1 - m;
+}
+
+// resolves a row of the WHOLE raster to memory: own band, halo above, halo below
+struct RowSource {
+    const uint8_t *own, *top, *bottom;
+    int y0, h, halo, full_h;
+    __device__ __forceinline__ const uint8_t *row(int gy, size_t pitch) const
+    {
+        gy = mirror_index(gy, full_h);
+        if (gy >= y0 && gy < y0 + h) return own + (size_t)(gy - y0) * pitch;
+        if (gy < y0) return top + (size_t)(gy - (y0 - halo)) * pitch;
+        return bottom + (size_t)(gy - (y0 + h)) * pitch;
+    }
+};
+
+constexpr int CONV_TW = 64;  // output tile: 64 pixels x 16 rows per CTA
+constexpr int CONV_TH = 16;
+
+__global__ void __launch_bounds__(256) conv_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t w, int k,
+                                                   int32_t div, int32_t bias)
+{
+    extern __shared__ uint8_t tile[];  // (CONV_TH + k - 1) rows x (CONV_TW + k - 1) pixels x 3
+    const int r = k / 2, tw = CONV_TW + k - 1, th = CONV_TH + k - 1, tpitch = tw * 3;
+    const int tx0 = blockIdx.x * CONV_TW, ty0 = blockIdx.y * CONV_TH;  // band-local output origin
+    const size_t pitch = (size_t)w * 3;
+
+    for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
+        int ty = i / tw, tx = i - ty * tw;
+        int gx = mirror_index(tx0 + tx - r, (int)w);
+        const uint8_t *p = rs.row(rs.y0 + ty0 + ty - r, pitch) + (size_t)gx * 3;
+        uint8_t *t = tile + ty * tpitch + tx * 3;
+        t[0] = p[0];
+        t[1] = p[1];
+        t[2] = p[2];
+    }
+    __syncthreads();
+
+    for (int i = threadIdx.x; i < CONV_TH * CONV_TW * 3; i += blockDim.x) {
+        int ty = i / (CONV_TW * 3), b = i - ty * (CONV_TW * 3);
+        int x = tx0 + b / 3, y = ty0 + ty;
+        if (x >= (int)w || y >= rs.h) continue;
+        long long acc = 0;
+        for (int dy = 0; dy < k; dy++) {
+            const uint8_t *t = tile + (ty + dy) * tpitch + b;
+            for (int dx = 0; dx < k; dx++) acc += (long long)c_conv_coef[dy * k + dx] * (int)t[dx * 3];
+        }
+        // floor((2*acc + div) / (2*div)) for div > 0
+        long long num = 2 * acc + div, den = 2 * (long long)div, q = num / den;
+        if ((num % den != 0) && (num < 0)) q--;
+        q += bias;
+        dst[(size_t)y * pitch + (size_t)tx0 * 3 + b] = (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q);
+    }
+}
+
+cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef, int32_t div,
+                 int32_t bias, const Band &band, cudaStream_t s)
+{
+    if (k < 1 || k > CONV_MAXK || !(k & 1) || div < 1) return cudaErrorInvalidValue;
+    if (!w || !h) return cudaSuccess;
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_conv_coef, coef, sizeof(int32_t) * k * k, 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    RowSource rs;
+    rs.own = src;
+    rs.top = band.top;
+    rs.bottom = band.bottom;
+    rs.y0 = band.full_h ? (int)band.y0 : 0;
+    rs.h = (int)h;
+    rs.halo = (int)band.halo;
+    rs.full_h = band.full_h ? (int)band.full_h : (int)h;
+    dim3 grid((w + CONV_TW - 1) / CONV_TW, (h + CONV_TH - 1) / CONV_TH);
+    if (grid.y > 65535u) return cudaErrorInvalidValue;
+    size_t smem = (size_t)(CONV_TH + k - 1) * (CONV_TW + k - 1) * 3;
+    conv_kernel<<<grid, 256, smem, s>>>(rs, dst, w, k, div, bias);
+    return PPMX_LAUNCHED();
+}
+
+}  // namespace ppmx

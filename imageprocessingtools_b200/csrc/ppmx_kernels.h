@@ -1,0 +1,43 @@
+// ppmx_kernels.h -- internal launch interface between the C ABI (ppmx_gpu.cu) and the
+// sm_100a kernels (ppmx_kernels.cu).  Not part of the public boundary (include/ppmx_gpu.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ppmx {
+
+// Row-band context for operators whose result depends on the absolute row (Bayer phase,
+// mirror border) or on rows owned by a neighbouring GPU (halo).  Zero-initialised = whole image.
+struct Band {
+    uint32_t full_h = 0;           // height of the whole raster (0: the band IS the raster)
+    uint32_t y0 = 0;               // first row of this band within the whole raster
+    const uint8_t *top = nullptr;  // `halo` rows directly above the band (may be peer memory)
+    const uint8_t *bottom = nullptr;
+    uint32_t halo = 0;
+};
+
+// which implementation of an operator to launch; 0 = the default (best measured)
+extern int g_variant;
+
+cudaError_t gray(const uint8_t *src, uint8_t *dst, size_t npix, unsigned long long *d_hist, cudaStream_t s);
+cudaError_t hist_gray(const uint8_t *src, size_t npix, unsigned long long *d_hist, cudaStream_t s);
+cudaError_t mono_plane(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t y0, cudaStream_t s);
+cudaError_t mono_bits(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t y0, cudaStream_t s);
+cudaError_t pack_pbm(const uint8_t *src, int src_bpp, uint8_t *dst, uint32_t w, uint32_t h, cudaStream_t s);
+cudaError_t extract_r(const uint8_t *src, uint8_t *dst, size_t npix, cudaStream_t s);
+cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int bpp, int vertical, cudaStream_t s);
+cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int angle, cudaStream_t s);
+cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t nw, uint32_t nh,
+                           double cos_t, double sin_t, cudaStream_t s);
+// one separable pass; d_weights/d_indices are [out_size][taps] in device memory
+cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int out_size, int dim, int taps,
+                     const double *d_weights, const int *d_indices, cudaStream_t s);
+// extension operators (no reference counterpart)
+cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef /*host*/,
+                 int32_t div, int32_t bias, const Band &band, cudaStream_t s);
+
+unsigned long long launch_count();
+
+}  // namespace ppmx

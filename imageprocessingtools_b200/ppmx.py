@@ -1,0 +1,413 @@
+"""ctypes binding of the C ABI (include/ppmx_gpu.h) and the C host layer (include/ppmx_host.h).
+
+Method names follow the reference's functions (/root/reference/ppmx-edward.c: gray ref:986,
+mono ref:949, flip ref:888, rotate ref:673, imresize ref:808, calc_contributions ref:516) so the
+parity tests read like calls into the reference.  Nothing here computes pixels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+GPU_SO = os.path.join(PKG, "libppmx_gpu.so")
+HOST_SO = os.path.join(PKG, "libppmx_host.so")
+CLI = os.path.join(PKG, "ppmx-b200")
+
+FT_PPM, FT_PGM, FT_PBM = 0, 1, 2
+LAYOUT_RGB8, LAYOUT_R8, LAYOUT_BITS = 0, 1, 2
+OP_GRAY, OP_MONO, OP_FLIP, OP_ROTATE, OP_IMRESIZE, OP_MONO_BITS, OP_PACK_PBM, OP_EXTRACT_R = range(8)
+OP_CONV, OP_HIST_GRAY, OP_GRAY_HIST = 16, 17, 18
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_i32p = C.POINTER(C.c_int32)
+_dblp = C.POINTER(C.c_double)
+
+
+class PpmxError(RuntimeError):
+    pass
+
+
+class PpmxOp(C.Structure):
+    """struct ppmx_op of include/ppmx_gpu.h"""
+    _fields_ = [("kind", C.c_int32), ("renew_before", C.c_int32), ("flip_direction", C.c_int32),
+                ("angle_deg", C.c_int32), ("cos_t", C.c_double), ("sin_t", C.c_double),
+                ("new_width", C.c_uint32), ("new_height", C.c_uint32),
+                ("dim", C.c_int32), ("out_size", C.c_int32), ("weights_sz", C.c_int32),
+                ("weights", _dblp), ("indices", _i32p),
+                ("conv_k", C.c_int32), ("conv_div", C.c_int32), ("conv_bias", C.c_int32), ("conv_coef", _i32p)]
+
+
+class PpmxBand(C.Structure):
+    """struct ppmx_band of include/ppmx_gpu.h"""
+    _fields_ = [("full_h", C.c_uint32), ("y0", C.c_uint32), ("d_top", C.c_void_p), ("d_bottom", C.c_void_p),
+                ("halo", C.c_uint32)]
+
+
+class _ArgsFlag(C.Structure):
+    _fields_ = [(n, C.c_char) for n in ("resize_enable", "rotate_enable", "flipv_enable", "fliph_enable",
+                                        "gray_enable", "mono_enable")]
+
+
+class _Contrib(C.Structure):
+    _fields_ = [("weights", _dblp), ("indices", _i32p), ("weights_sz", C.c_int), ("out_size", C.c_int)]
+
+
+class _Plan(C.Structure):
+    _fields_ = [("ops", PpmxOp * 8), ("nops", C.c_int), ("contrib", _Contrib * 2)]
+
+
+_gpu = None
+_host = None
+
+
+def gpu_lib() -> C.CDLL:
+    """libppmx_gpu.so; raises if it has not been built (no fallback)."""
+    global _gpu
+    if _gpu is None:
+        if not os.path.exists(GPU_SO):
+            raise PpmxError("libppmx_gpu.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(GPU_SO, mode=C.RTLD_GLOBAL)
+        vp = C.c_void_p
+        L.ppmx_gpu_init.argtypes = [C.POINTER(vp), C.c_int]
+        L.ppmx_gpu_free.argtypes = [vp]
+        L.ppmx_gpu_free.restype = None
+        L.ppmx_gpu_host_alloc.argtypes = [vp, C.c_size_t]
+        L.ppmx_gpu_host_alloc.restype = vp
+        L.ppmx_gpu_host_free.argtypes = [vp, vp]
+        L.ppmx_gpu_host_free.restype = None
+        L.ppmx_gpu_apply.argtypes = [vp, C.POINTER(PpmxOp), C.c_int, vp, C.c_uint32, C.c_uint32, vp, C.c_size_t,
+                                     C.POINTER(C.c_size_t), _u32p, _u32p, C.POINTER(C.c_int)]
+        L.ppmx_gpu_apply_batch.argtypes = [vp, C.POINTER(PpmxOp), C.c_int, vp, C.c_uint32, C.c_uint32, C.c_int, vp,
+                                           C.c_size_t, C.POINTER(C.c_size_t), _u32p, _u32p, C.POINTER(C.c_int)]
+        L.ppmx_gpu_upload.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]
+        L.ppmx_gpu_image_alloc.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]
+        L.ppmx_gpu_image_free.argtypes = [vp, vp]
+        L.ppmx_gpu_image_free.restype = None
+        L.ppmx_gpu_image_info.argtypes = [vp, _u32p, _u32p, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(vp)]
+        L.ppmx_gpu_op.argtypes = [vp, C.POINTER(PpmxOp), vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+        L.ppmx_gpu_download.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.ppmx_gpu_sync.argtypes = [vp]
+        L.ppmx_gpu_launch.argtypes = [C.POINTER(PpmxOp), vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.POINTER(PpmxBand),
+                                      vp, vp, vp]
+        L.ppmx_gpu_tables_upload.argtypes = [C.POINTER(PpmxOp), C.POINTER(vp)]
+        L.ppmx_gpu_tables_free.argtypes = [vp]
+        L.ppmx_gpu_tables_free.restype = None
+        L.ppmx_gpu_layout_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+        L.ppmx_gpu_layout_bytes.restype = C.c_size_t
+        L.ppmx_gpu_op_output.argtypes = [C.POINTER(PpmxOp), C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p,
+                                         C.POINTER(C.c_int)]
+        L.ppmx_gpu_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        L.ppmx_gpu_device_free.argtypes = [vp, vp]
+        L.ppmx_gpu_device_free.restype = None
+        L.ppmx_gpu_ipc_export.argtypes = [vp, vp, _u8p]
+        L.ppmx_gpu_ipc_open.argtypes = [vp, _u8p, C.POINTER(vp)]
+        L.ppmx_gpu_ipc_close.argtypes = [vp, vp]
+        L.ppmx_gpu_launch_count.restype = C.c_uint64
+        L.ppmx_gpu_version.restype = C.c_char_p
+        _gpu = L
+    return _gpu
+
+
+def host_lib() -> C.CDLL:
+    """libppmx_host.so (C host layer); raises if it has not been built."""
+    global _host
+    if _host is None:
+        gpu_lib()
+        if not os.path.exists(HOST_SO):
+            raise PpmxError("libppmx_host.so is not built")
+        H = C.CDLL(HOST_SO)
+        H.ppmx_cubic.argtypes = [C.c_double]
+        H.ppmx_cubic.restype = C.c_double
+        H.ppmx_mod.argtypes = [C.c_int, C.c_int]
+        H.ppmx_calc_contributions.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(_Contrib)]
+        H.ppmx_contributions_free.argtypes = [C.POINTER(_Contrib)]
+        H.ppmx_contributions_free.restype = None
+        H.ppmx_calc_rot_size.argtypes = [C.c_double, C.c_uint, C.c_uint, _u32p, _u32p]
+        H.ppmx_calc_rot_size.restype = None
+        H.ppmx_plan_chain.argtypes = [C.POINTER(_ArgsFlag), C.c_uint, C.c_double, C.c_uint, C.c_uint, C.POINTER(_Plan)]
+        H.ppmx_plan_free.argtypes = [C.POINTER(_Plan)]
+        H.ppmx_plan_free.restype = None
+        H.ppmx_parse_header.argtypes = [C.c_char_p, C.c_size_t, _u32p, _u32p, _u32p, C.POINTER(C.c_size_t)]
+        H.ppmx_format_header.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_uint]
+        _host = H
+    return _host
+
+
+def _img(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError("expected an (h, w, 3) uint8 raster, got %r" % (a.shape,))
+    return a
+
+
+def _vp(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+# ---- host-only helpers (no GPU needed) ----------------------------------------------------
+
+def calc_contributions(in_size: int, out_size: int, scale: float, k_width: float = 4.0):
+    """ppmx_calc_contributions (host C, ref:516-641) -> (weights[out][K] f64, indices[out][K] i32)."""
+    H = host_lib()
+    c = _Contrib()
+    if H.ppmx_calc_contributions(in_size, out_size, float(scale), float(k_width), C.byref(c)) != 0:
+        raise PpmxError("ppmx_calc_contributions failed")
+    k = c.weights_sz
+    w = np.ctypeslib.as_array(c.weights, shape=(out_size, max(k, 1))).copy()[:, :k]
+    i = np.ctypeslib.as_array(c.indices, shape=(out_size, max(k, 1))).copy()[:, :k]
+    H.ppmx_contributions_free(C.byref(c))
+    return np.ascontiguousarray(w), np.ascontiguousarray(i)
+
+
+def rotate_size(angle: float, w: int, h: int) -> Tuple[int, int]:
+    """Output size rotate() uses: angle folded into [0,90] (ref:687-691) then ppmx_calc_rot_size."""
+    a = float(angle)
+    if a >= 270:
+        a = 360 - a
+    elif a > 180:
+        a = a - 180
+    elif a > 90:
+        a = 180 - a
+    nw, nh = C.c_uint32(), C.c_uint32()
+    host_lib().ppmx_calc_rot_size(a, w, h, C.byref(nw), C.byref(nh))
+    return nw.value, nh.value
+
+
+def parse_header(data: bytes):
+    w, h, m = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    off = C.c_size_t()
+    rc = host_lib().ppmx_parse_header(data, len(data), C.byref(w), C.byref(h), C.byref(m), C.byref(off))
+    if rc != 0:
+        raise PpmxError("ppmx_parse_header failed")
+    return w.value, h.value, m.value, off.value
+
+
+def format_header(file_type: int, w: int, h: int, maxval: int = 255) -> bytes:
+    buf = C.create_string_buffer(128)
+    n = host_lib().ppmx_format_header(buf, 128, file_type, w, h, maxval)
+    return buf.raw[:n]
+
+
+class _PlanHolder:
+    def __init__(self, resize_w=None, angle=None, gray=False, mono=False, flipv=False, fliph=False, w=0, h=0):
+        self.plan = _Plan()
+        f = _ArgsFlag(bytes([int(resize_w is not None)]), bytes([int(angle is not None)]), bytes([int(flipv)]),
+                      bytes([int(fliph)]), bytes([int(gray)]), bytes([int(mono)]))
+        rc = host_lib().ppmx_plan_chain(C.byref(f), int(resize_w or 0), float(angle or 0), w, h, C.byref(self.plan))
+        if rc != 0:
+            raise PpmxError("ppmx_plan_chain failed")
+
+    def close(self):
+        host_lib().ppmx_plan_free(C.byref(self.plan))
+
+
+# ---- the device context --------------------------------------------------------------------
+
+class Ppmx:
+    """One ppmx_gpu_ctx.  Every method goes through the C ABI; rasters are numpy (h, w, 3) uint8."""
+
+    def __init__(self, device: int = 0):
+        self.L = gpu_lib()
+        self.ctx = C.c_void_p()
+        if self.L.ppmx_gpu_init(C.byref(self.ctx), device) != 0:
+            raise PpmxError("ppmx_gpu_init failed (no B200 visible?) -- there is no CPU fallback")
+        self.device = device
+
+    def close(self):
+        if self.ctx:
+            self.L.ppmx_gpu_free(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- device rasters ---------------------------------------------------------------------
+    def upload(self, arr: np.ndarray, layout: int = LAYOUT_RGB8) -> C.c_void_p:
+        arr = np.ascontiguousarray(arr, np.uint8)
+        h, w = arr.shape[0], arr.shape[1]
+        img = C.c_void_p()
+        if self.L.ppmx_gpu_upload(self.ctx, _vp(arr), w, h, layout, C.byref(img)) != 0:
+            raise PpmxError("ppmx_gpu_upload failed")
+        self.L.ppmx_gpu_sync(self.ctx)  # arr may be a temporary
+        return img
+
+    def info(self, img):
+        w, h, lay = C.c_uint32(), C.c_uint32(), C.c_int()
+        nb = C.c_size_t()
+        ptr = C.c_void_p()
+        self.L.ppmx_gpu_image_info(img, C.byref(w), C.byref(h), C.byref(lay), C.byref(nb), C.byref(ptr))
+        return w.value, h.value, lay.value, nb.value, ptr.value
+
+    def op(self, op: PpmxOp, img, hist: bool = False):
+        out = C.c_void_p()
+        bins = (C.c_uint64 * 256)()
+        if self.L.ppmx_gpu_op(self.ctx, C.byref(op), img, C.byref(out), bins if hist else None) != 0:
+            raise PpmxError("ppmx_gpu_op failed (kind %d)" % op.kind)
+        return (out, np.array(bins[:], np.uint64)) if hist else out
+
+    def download(self, img, file_type: int) -> np.ndarray:
+        w, h, lay, nb, _ = self.info(img)
+        out = np.empty(max(w * h * 3, 1) + 16, np.uint8)
+        n = C.c_size_t()
+        if self.L.ppmx_gpu_download(self.ctx, img, file_type, _vp(out), out.size, C.byref(n)) != 0:
+            raise PpmxError("ppmx_gpu_download failed")
+        return out[:n.value].copy()
+
+    def release(self, img):
+        self.L.ppmx_gpu_image_free(self.ctx, img)
+
+    def _one(self, img: np.ndarray, op: PpmxOp, file_type: int, hist: bool = False):
+        img = _img(img)
+        d = self.upload(img)
+        try:
+            res = self.op(op, d, hist)
+            out, bins = (res if hist else (res, None))
+            try:
+                if out:
+                    w, h, lay, nb, _ = self.info(out)
+                    data = self.download(out, file_type)
+                else:
+                    w = h = 0
+                    lay, data = -1, None
+            finally:
+                if out:
+                    self.release(out)
+        finally:
+            self.release(d)
+        return data, w, h, lay, bins
+
+    # -- reference operators (same names as the oracle) --------------------------------------
+    def gray(self, img) -> np.ndarray:
+        data, w, h, _, _ = self._one(img, PpmxOp(kind=OP_GRAY), FT_PGM)
+        return data.reshape(h, w)
+
+    def mono(self, img) -> np.ndarray:
+        """(h, w) plane of 0/1 (the .r members)."""
+        data, w, h, _, _ = self._one(img, PpmxOp(kind=OP_MONO), FT_PGM)
+        return data.reshape(h, w)
+
+    def mono_bits(self, img) -> np.ndarray:
+        """mono fused with the P4 packer: the bytes of a P4 raster."""
+        data, _, _, _, _ = self._one(img, PpmxOp(kind=OP_MONO_BITS), FT_PBM)
+        return data
+
+    def pack_pbm(self, plane) -> np.ndarray:
+        plane = np.ascontiguousarray(plane, np.uint8)
+        d = self.upload(plane, LAYOUT_R8)
+        try:
+            return self.download(d, FT_PBM)
+        finally:
+            self.release(d)
+
+    def flip(self, img, direction: int) -> np.ndarray:
+        data, w, h, _, _ = self._one(img, PpmxOp(kind=OP_FLIP, flip_direction=int(direction)), FT_PPM)
+        return data.reshape(h, w, 3)
+
+    def rotate_op(self, angle: int, w: int, h: int) -> PpmxOp:
+        import math
+        nw, nh = rotate_size(angle, w, h)
+        th = (float(angle) * 3.14159265358979323846) / 180.0  # ref:692, host libm for cos/sin
+        return PpmxOp(kind=OP_ROTATE, angle_deg=int(angle), cos_t=math.cos(th), sin_t=math.sin(th), new_width=nw,
+                      new_height=nh)
+
+    def rotate(self, img, angle: int) -> np.ndarray:
+        img = _img(img)
+        op = self.rotate_op(angle, img.shape[1], img.shape[0])
+        data, w, h, _, _ = self._one(img, op, FT_PPM)
+        return data.reshape(h, w, 3)
+
+    @staticmethod
+    def calc_contributions(in_size, out_size, scale, k_width=4.0):
+        return calc_contributions(in_size, out_size, scale, k_width)
+
+    @staticmethod
+    def imresize_op(out_size: int, dim: int, weights: np.ndarray, indices: np.ndarray) -> PpmxOp:
+        return PpmxOp(kind=OP_IMRESIZE, dim=dim, out_size=out_size, weights_sz=weights.shape[1],
+                      weights=weights.ctypes.data_as(_dblp), indices=indices.ctypes.data_as(_i32p))
+
+    def imresize(self, img, out_size: int, dim: int, weights, indices) -> np.ndarray:
+        weights = np.ascontiguousarray(weights, np.float64)
+        indices = np.ascontiguousarray(indices, np.int32)
+        data, w, h, _, _ = self._one(img, self.imresize_op(out_size, dim, weights, indices), FT_PPM)
+        return data.reshape(h, w, 3)
+
+    def process(self, img, resize_w: Optional[int] = None, angle: Optional[int] = None, gray=False, mono=False,
+                flipv=False, fliph=False):
+        """The whole chain through ppmx_plan_chain + ppmx_gpu_apply (host raster in, writer bytes out)."""
+        img = _img(img)
+        h, w, _ = img.shape
+        ph = _PlanHolder(resize_w, angle, gray, mono, flipv, fliph, w, h)
+        try:
+            if ph.plan.nops == 0:
+                raise PpmxError("Error: no data to write")
+            ow, oh = w, h
+            for i in range(ph.plan.nops):
+                o = ph.plan.ops[i]
+                if o.kind in (OP_IMRESIZE, OP_ROTATE):
+                    a, b, c = C.c_uint32(), C.c_uint32(), C.c_int()
+                    self.L.ppmx_gpu_op_output(C.byref(o), ow, oh, LAYOUT_RGB8, C.byref(a), C.byref(b), C.byref(c))
+                    ow, oh = a.value, b.value
+            out = np.empty(ow * oh * 3 + 16, np.uint8)
+            n = C.c_size_t()
+            rw, rh, ft = C.c_uint32(), C.c_uint32(), C.c_int()
+            rc = self.L.ppmx_gpu_apply(self.ctx, ph.plan.ops, ph.plan.nops, _vp(img), w, h, _vp(out), out.size,
+                                       C.byref(n), C.byref(rw), C.byref(rh), C.byref(ft))
+            if rc != 0:
+                raise PpmxError("ppmx_gpu_apply failed")
+            return out[:n.value].copy(), rw.value, rh.value, ft.value
+        finally:
+            ph.close()
+
+    @staticmethod
+    def header(file_type: int, w: int, h: int, maxval: int = 255) -> bytes:
+        return format_header(file_type, w, h, maxval)
+
+    # -- extensions (no reference counterpart; parity unpinned) -------------------------------
+    @staticmethod
+    def conv_op(coef, div: int = 1, bias: int = 0) -> PpmxOp:
+        coef = np.ascontiguousarray(coef, np.int32)
+        op = PpmxOp(kind=OP_CONV, conv_k=coef.shape[0], conv_div=div, conv_bias=bias,
+                    conv_coef=coef.ctypes.data_as(_i32p))
+        op._keep = coef
+        return op
+
+    def conv(self, img, coef, div: int = 1, bias: int = 0) -> np.ndarray:
+        data, w, h, _, _ = self._one(img, self.conv_op(coef, div, bias), FT_PPM)
+        return data.reshape(h, w, 3)
+
+    def hist_gray(self, img) -> np.ndarray:
+        _, _, _, _, bins = self._one(img, PpmxOp(kind=OP_HIST_GRAY), FT_PGM, hist=True)
+        return bins
+
+    def gray_hist(self, img):
+        data, w, h, _, bins = self._one(img, PpmxOp(kind=OP_GRAY_HIST), FT_PGM, hist=True)
+        return data.reshape(h, w), bins
+
+    # -- raw launch on caller-owned device memory (bench.py, multi-GPU bands) -----------------
+    def launch(self, op: PpmxOp, d_src: int, w: int, h: int, layout: int, d_dst: int, band: Optional[PpmxBand] = None,
+               d_hist: int = 0, d_tables: int = 0, stream: int = 0) -> None:
+        rc = self.L.ppmx_gpu_launch(C.byref(op), C.c_void_p(d_src), w, h, layout, C.c_void_p(d_dst),
+                                    C.byref(band) if band is not None else None, C.c_void_p(d_hist),
+                                    C.c_void_p(d_tables), C.c_void_p(stream))
+        if rc != 0:
+            raise PpmxError("ppmx_gpu_launch failed (kind %d)" % op.kind)
+
+    def tables_upload(self, op: PpmxOp) -> int:
+        p = C.c_void_p()
+        if self.L.ppmx_gpu_tables_upload(C.byref(op), C.byref(p)) != 0:
+            raise PpmxError("ppmx_gpu_tables_upload failed")
+        return p.value
+
+    def tables_free(self, p: int) -> None:
+        self.L.ppmx_gpu_tables_free(C.c_void_p(p))
+
+    def launch_count(self) -> int:
+        return int(self.L.ppmx_gpu_launch_count())
