@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- megapixels/s of the per-pixel hot path of ppmx-edward.c on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the operator over a batch of
+BATCH distinct synthetic rasters (the batch is larger than the 126 MB L2, so every step reads
+its input from HBM).  `value` is device-resident throughput (inputs already in HBM, CUDA events
+on the launching stream, max over ranks); `e2e` is the same operator through the C ABI call
+ppmx_gpu_apply_batch with pinned HOST buffers, H2D and D2H copies inside the timed region.
+`roofline` is for the operator's kernel: algorithmic bytes / measured duration
+against MEASURED_PEAKS.json.  `cpu_baseline` is the compiled reference (oracle/_ref) timed on
+this box's host cores on a bounded sample.  Multi-GPU: one process per GPU under torchrun,
+rasters sharded across ranks with no data-path collective ("weak"); the fused gray+histogram
+workload adds the one real exchange, an NCCL all-reduce of the 256 bins.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref) of the same
+operator on the host cores (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "megapixels/sec per op"
+UNIT = "Mpix/s"
+
+# workload -> (w, h, batch, algorithmic bytes per input pixel, description)
+WORKLOADS = {
+    "gray": (4096, 4096, 16, 4.0, "4096x4096 P6 RGB->greyscale (config 2), 16 distinct rasters per step"),
+    "gray_hist": (4096, 4096, 16, 4.0, "4096x4096 P6 RGB->greyscale + histogram fused (config 2), 16 rasters per step"),
+    "mono": (4096, 4096, 16, 3.125, "4096x4096 P6 -> Bayer bilevel P4 bits, 16 rasters per step"),
+    "fliph": (4096, 4096, 8, 6.0, "4096x4096 horizontal flip, 8 rasters per step"),
+    "flipv": (4096, 4096, 8, 6.0, "4096x4096 vertical flip, 8 rasters per step"),
+    "rot90": (4096, 4096, 8, 6.0, "4096x4096 rotate 90, 8 rasters per step"),
+    "rot180": (4096, 4096, 8, 6.0, "4096x4096 rotate 180, 8 rasters per step"),
+    "conv3": (8192, 8192, 2, 6.0, "8192x8192 3x3 blur (extension, config 3), 2 rasters per step"),
+    "conv7": (8192, 8192, 2, 6.0, "8192x8192 7x7 box (extension, config 3), 2 rasters per step"),
+    "resize_up": (4096, 4096, 2, None, "4096x4096 -w6144 bicubic resize (FP64), 2 rasters per step"),
+    "resize_down": (4096, 4096, 2, None, "4096x4096 -w2048 bicubic resize (FP64), 2 rasters per step"),
+    "rot30": (4096, 4096, 2, None, "4096x4096 -r30 bicubic rotate (FP64), 2 rasters per step"),
+}
+DEFAULT_WORKLOAD = "gray"
+PER_OP = ["gray", "gray_hist", "mono", "fliph", "flipv", "rot90", "rot180", "conv3", "conv7", "resize_up",
+          "resize_down", "rot30"]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (pynvml, else nvidia-smi)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake_slowdown"}
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.02)
+        except Exception:
+            pass
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+
+class Runner:
+    """Builds the op + device buffers of one workload and launches it through ppmx_gpu_launch."""
+
+    def __init__(self, torch, g, name, device, seed):
+        import numpy as np
+        from imageprocessingtools_b200 import ppmx as pp
+        self.torch, self.g, self.name, self.pp = torch, g, name, pp
+        w, h, batch, bpp, desc = WORKLOADS[name]
+        self.w, self.h, self.batch, self.bpp, self.desc = w, h, batch, bpp, desc
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        self.src = torch.randint(0, 256, (batch, h, w, 3), dtype=torch.uint8, device=device, generator=gen)
+        self.tables = 0
+        self.hist = None
+        self.mid = None
+        self.ops = []  # (op, out_w, out_h, out_bytes_per_raster, src_layout)
+        self.keep = []
+        L = pp
+        if name in ("gray", "gray_hist"):
+            kind = L.OP_GRAY if name == "gray" else L.OP_GRAY_HIST
+            self.ops = [(L.PpmxOp(kind=kind), w, h, w * h)]
+            if name == "gray_hist":
+                self.hist = torch.zeros(256, dtype=torch.int64, device=device)
+        elif name == "mono":
+            self.ops = [(L.PpmxOp(kind=L.OP_MONO_BITS), w, h, ((w + 7) // 8) * h)]
+        elif name in ("fliph", "flipv"):
+            self.ops = [(L.PpmxOp(kind=L.OP_FLIP, flip_direction=int(name == "flipv")), w, h, w * h * 3)]
+        elif name in ("rot90", "rot180", "rot30"):
+            op = g.rotate_op(int(name[3:]), w, h)
+            self.ops = [(op, op.new_width, op.new_height, op.new_width * op.new_height * 3)]
+        elif name in ("conv3", "conv7"):
+            if name == "conv3":
+                coef, div = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], np.int32), 16
+            else:
+                coef, div = np.ones((7, 7), np.int32), 49
+            self.ops = [(g.conv_op(coef, div, 0), w, h, w * h * 3)]
+        elif name in ("resize_up", "resize_down"):
+            new_w = w * 3 // 2 if name == "resize_up" else w // 2
+            ph = pp._PlanHolder(resize_w=new_w, w=w, h=h)
+            self.keep.append(ph)
+            cw, chh = w, h
+            for i in range(ph.plan.nops):
+                op = ph.plan.ops[i]
+                ow, oh = (cw, op.out_size) if op.dim == 0 else (op.out_size, chh)
+                self.ops.append((op, ow, oh, ow * oh * 3))
+                cw, chh = ow, oh
+        else:
+            raise SystemExit("unknown workload " + name)
+        self.out_w, self.out_h = self.ops[-1][1], self.ops[-1][2]
+        self.dst = [torch.empty((batch, o[3]), dtype=torch.uint8, device=device) for o in self.ops]
+        self.tabs = [g.tables_upload(o[0]) if o[0].kind == L.OP_IMRESIZE else 0 for o in self.ops]
+        self.launches_per_step = batch * len(self.ops)
+        self.pixels_per_step = batch * w * h  # input pixels (resize/rotate: also reported per output px)
+
+    def step(self, stream):
+        L = self.pp
+        for b in range(self.batch):
+            src, w, h = self.src[b].data_ptr(), self.w, self.h
+            for i, (op, ow, oh, nbytes) in enumerate(self.ops):
+                dst = self.dst[i][b].data_ptr()
+                self.g.launch(op, src, w, h, L.LAYOUT_RGB8, dst, None, self.hist.data_ptr() if self.hist is not None else 0,
+                              self.tabs[i], stream)
+                src, w, h = dst, ow, oh
+
+    def close(self):
+        for t in self.tabs:
+            if t:
+                self.g.tables_free(t)
+        for k in self.keep:
+            k.close()
+
+
+def time_steps(torch, runner, steps, warmup, dist=None, after_step=None):
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(warmup):
+        runner.step(stream)
+        if after_step:
+            after_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        runner.step(stream)
+        if after_step:
+            after_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def e2e_run(torch, g, name, steps, warmup, device, dist=None):
+    """Same operator through ppmx_gpu_apply_batch: pinned host rasters in, pinned host results out."""
+    import ctypes as C
+    from imageprocessingtools_b200 import ppmx as pp
+    w, h, batch, _, _ = WORKLOADS[name]
+    batch = min(batch, 8)
+    if name == "gray":
+        ops = (pp.PpmxOp * 1)(pp.PpmxOp(kind=pp.OP_GRAY))
+        out_each = w * h
+    elif name == "gray_hist":  # the chain API has no histogram output: gray through the chain
+        ops = (pp.PpmxOp * 1)(pp.PpmxOp(kind=pp.OP_GRAY))
+        out_each = w * h
+    elif name == "mono":
+        ops = (pp.PpmxOp * 1)(pp.PpmxOp(kind=pp.OP_MONO))
+        out_each = ((w + 7) // 8) * h
+    elif name in ("fliph", "flipv"):
+        ops = (pp.PpmxOp * 1)(pp.PpmxOp(kind=pp.OP_FLIP, flip_direction=int(name == "flipv")))
+        out_each = w * h * 3
+    elif name in ("rot90", "rot180", "rot30"):
+        op = g.rotate_op(int(name[3:]), w, h)
+        ops = (pp.PpmxOp * 1)(op)
+        out_each = op.new_width * op.new_height * 3
+    else:
+        return None
+    src = torch.randint(0, 256, (batch, h, w, 3), dtype=torch.uint8).pin_memory()
+    dst = torch.empty((batch, out_each + 16), dtype=torch.uint8).pin_memory()
+    each, ow, oh, ft = C.c_size_t(), C.c_uint32(), C.c_uint32(), C.c_int()
+
+    def one():
+        rc = g.L.ppmx_gpu_apply_batch(g.ctx, ops, 1, C.c_void_p(src.data_ptr()), w, h, batch, C.c_void_p(dst.data_ptr()),
+                                      out_each + 16, C.byref(each), C.byref(ow), C.byref(oh), C.byref(ft))
+        if rc != 0:
+            raise SystemExit("ppmx_gpu_apply_batch failed")
+
+    for _ in range(max(1, warmup)):
+        one()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()  # returns after the last D2H copy has landed (the call synchronises its streams)
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    world = dist.get_world_size() if dist is not None else 1
+    return {"value": round(world * steps * batch * w * h / dt / 1e6, 1), "unit": UNIT,
+            "h2d_bytes_per_step": batch * w * h * 3, "d2h_bytes_per_step": batch * int(each.value),
+            "rasters_per_step": batch, "api": "ppmx_gpu_apply_batch (pinned host in/out)"}
+
+
+def cpu_baseline_sample(name, threads, seconds_budget=12.0):
+    """The compiled reference (oracle/_ref) on this box's host cores; bounded sample."""
+    import numpy as np
+    import oracle
+    ref = oracle.ref()
+    kind = "reference"
+    if ref is None:
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": "oracle/_ref missing"}
+    w, h, _, _, _ = WORKLOADS[name]
+    rng = np.random.default_rng(1)
+
+    def call(r, img):
+        if name in ("gray", "gray_hist"):
+            r.gray(img)
+        elif name == "mono":
+            r.mono(img)
+        elif name in ("fliph", "flipv"):
+            r.flip(img, int(name == "flipv"))
+        elif name in ("rot90", "rot180", "rot30"):
+            r.rotate(img, int(name[3:]))
+        else:
+            r.gray(img)
+        return r.last_seconds
+
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(threads)]
+    refs = [oracle.Ref() for _ in range(threads)]
+    op_time = [0.0] * threads
+    count = [0] * threads
+    t_end = time.perf_counter() + seconds_budget
+
+    def work(i):
+        while True:
+            op_time[i] += call(refs[i], imgs[i])
+            count[i] += 1
+            if time.perf_counter() > t_end or count[i] >= 64:
+                break
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    total_px = sum(count) * w * h
+    return {"value": round(total_px / max(op_time) / 1e6, 1), "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": "%d calls of the reference's %s() on %dx%d rasters over %d thread(s); time inside the "
+                      "reference function only (its own image_buff_alloc included)" % (sum(count), name, w, h, threads)}
+
+
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=device)
+        dist = dist_mod
+    import imageprocessingtools_b200 as ip
+    g = ip.Ppmx(local)  # raises if libppmx_gpu.so is missing or no B200 is visible: no fallback
+
+    name = args.workload
+    w, h, batch, bpp, desc = WORKLOADS[name]
+    peak, peak_src = peaks()
+    runner = Runner(torch, g, name, device, seed=0xC0FFEE ^ (rank + 2))
+
+    after = None
+    if name == "gray_hist" and dist is not None:
+        def after():  # the one real exchange of this path: sum the 256 bins over ranks (NCCL)
+            dist.all_reduce(runner.hist, op=dist.ReduceOp.SUM)
+
+    n0 = g.launch_count()
+    with ClockSampler(local) as clk:
+        ms = time_steps(torch, runner, args.steps, args.warmup, dist, after)
+    launches = (g.launch_count() - n0) - args.warmup * runner.launches_per_step
+    px = world * args.steps * runner.pixels_per_step
+    value = px / (ms / 1e3) / 1e6
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": desc, "op": name, "raster": "%dx%d" % (w, h), "rasters_per_step_per_gpu": batch,
+                   "l2": "inputs larger than L2 (%d MB per step per GPU)" % (batch * w * h * 3 // 1000000),
+                   "sharding": "rasters sharded across ranks, no data-path collective" +
+                               ("; NCCL all-reduce of the 256 histogram bins per step" if after else "")},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+    }
+    if bpp is not None:
+        per_launch_ms = ms / (args.steps * runner.launches_per_step)
+        achieved = bpp * w * h / (per_launch_ms / 1e3) / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                            "kernel": name, "algorithmic_bytes_per_pixel": bpp,
+                            "avg_launch_us": round(per_launch_ms * 1e3, 2)}
+    else:
+        line["roofline"] = {"bound": "fp64 issue (not HBM, not tensor)", "achieved": None, "peak": None, "unit": "GB/s",
+                            "frac": None, "traffic": None, "kernel": name}
+
+    e2e = e2e_run(torch, g, name, max(2, args.steps // 4), 1, device, dist)
+    if e2e is not None:
+        line["e2e"] = e2e
+
+    if not args.no_per_op and world == 1:
+        per = {}
+        for op_name in PER_OP:
+            if op_name == name:
+                per[op_name] = {"mpix_s": round(value, 1), "gbs": line["roofline"].get("achieved"),
+                                "frac": line["roofline"].get("frac")}
+                continue
+            ow, oh, ob, obpp, _ = WORKLOADS[op_name]
+            r = Runner(torch, g, op_name, device, seed=7)
+            t = time_steps(torch, r, 3, 3)
+            mp = 3 * r.pixels_per_step / (t / 1e3) / 1e6
+            ent = {"mpix_s": round(mp, 1), "raster": "%dx%d" % (ow, oh)}
+            if obpp is not None:
+                gbs = obpp * mp * 1e6 / 1e9
+                ent.update({"gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+            else:
+                ent["out_mpix_s"] = round(3 * r.batch * r.out_w * r.out_h / (t / 1e3) / 1e6, 1)
+            per[op_name] = ent
+            r.close()
+            del r
+            torch.cuda.empty_cache()
+        line["per_op"] = per
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_sample(name, 1)
+    runner.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    g.close()
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU code on the host cores
+# --------------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    w, h, batch, _, desc = WORKLOADS[name]
+    threads = min(os.cpu_count() or 1, 64)
+    t0 = time.perf_counter()
+    # steps*: each "step" is a bounded sample; total CPU time is capped to stay within minutes
+    budget = min(60.0, max(4.0, 2.0 * (args.steps + args.warmup)))
+    cb = cpu_baseline_sample(name, threads, seconds_budget=budget)
+    dt = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(dt * 1e3 / max(args.steps, 1), 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": desc, "op": name, "raster": "%dx%d" % (w, h)},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-per-op", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
