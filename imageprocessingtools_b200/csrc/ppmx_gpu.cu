@@ -70,6 +70,14 @@ extern "C" size_t ppmx_gpu_layout_bytes(uint32_t w, uint32_t h, int layout)
     }
 }
 
+extern "C" int ppmx_gpu_set_tuning(const char *key, int value)
+{
+    if (key && !strcmp(key, "variant")) ppmx::g_variant = value;
+    else if (key && !strcmp(key, "pdl")) ppmx::g_pdl = value ? 1 : 0;
+    else return PPMX_ERROR;
+    return PPMX_OK;
+}
+
 extern "C" const char *ppmx_gpu_version(void) { return PPMX_VERSION; }
 extern "C" uint64_t ppmx_gpu_launch_count(void) { return ppmx::launch_count(); }
 

@@ -19,7 +19,7 @@ unsigned long long launch_count() { return g_launches; }
 static int g_sm_count = 0;
 static int sm_count()
 {
-    if (!g_sm_count) {
+    if (!g_sm_count) {  // every device a process sees in this pool is the same B200 part
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
@@ -28,7 +28,47 @@ static int sm_count()
     return g_sm_count;
 }
 
-#define PPMX_LAUNCHED() (++g_launches, cudaGetLastError())
+#define PPMX_LAUNCHED() (cudaGetLastError())
+
+// Programmatic dependent launch (sm_90+): every kernel in this file starts with pdl_wait(), so a
+// launch may be scheduled while its predecessor in the stream is still draining; only index
+// arithmetic runs before the wait, all global-memory traffic after it.
+int g_pdl = 1;  // ppmx_gpu_set_tuning("pdl", 0/1)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define PDL_PROLOGUE() \
+    do {               \
+        pdl_trigger(); \
+        pdl_wait();    \
+    } while (0)
+
+// opt in to > 48 KB dynamic shared memory once per (kernel, device)
+template <typename K>
+static void allow_smem(K kernel, size_t bytes, bool (&done)[64])
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || done[dev]) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    done[dev] = true;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ++g_launches;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned4(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
@@ -126,6 +166,7 @@ template <bool HIST, bool STORE>
 __global__ void __launch_bounds__(256) gray_vec_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
                                                        size_t ngroups, size_t npix, unsigned long long *d_hist)
 {
+    PDL_PROLOGUE();
     __shared__ SmemHist<HIST ? 8 : 1> sh;
     if (HIST) {
         sh.clear();
@@ -163,6 +204,7 @@ template <bool HIST, bool STORE>
 __global__ void __launch_bounds__(256) gray_scalar_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                           size_t npix, unsigned long long *d_hist)
 {
+    PDL_PROLOGUE();
     __shared__ SmemHist<HIST ? 8 : 1> sh;
     if (HIST) {
         sh.clear();
@@ -180,6 +222,208 @@ __global__ void __launch_bounds__(256) gray_scalar_kernel(const uint8_t *__restr
     }
 }
 
+// ---- histogram with contention-free, thread-private byte counters ---------------------------
+// Each thread owns one 4-byte column in each of 64 shared-memory rows: byte (bin & 3) of row
+// (bin >> 2).  A lane therefore always hits its own bank, needs no atomics and takes the same
+// time on a constant image as on noise.  A byte counter holds 255, so after at most 15 groups
+// of 16 pixels per thread the CTA folds the counters into 256 per-CTA totals (dp4a column sums)
+// and clears them; the totals go to global memory in one atomic pass at the end.
+constexpr int HP_THREADS = 256;
+constexpr int HP_MAX_GROUPS = 15;
+constexpr size_t HP_SMEM = (64 * HP_THREADS + 256) * sizeof(uint32_t);
+
+__device__ __forceinline__ void hp_bump(uint8_t *mine, uint32_t g)
+{
+    uint8_t *p = mine + ((g & 0xFCu) << 8) + (g & 3u);  // row (g>>2) is 256 words = 1024 bytes long
+    *p = (uint8_t)(*p + 1);
+}
+
+__device__ __forceinline__ void hp_bump4(uint8_t *mine, uint32_t g4)
+{
+    hp_bump(mine, g4 & 0xFFu);
+    hp_bump(mine, (g4 >> 8) & 0xFFu);
+    hp_bump(mine, (g4 >> 16) & 0xFFu);
+    hp_bump(mine, g4 >> 24);
+}
+
+template <bool STORE>
+__global__ void __launch_bounds__(HP_THREADS, 3) gray_hist_private_kernel(const uint4 *__restrict__ src,
+                                                                          uint4 *__restrict__ dst, size_t ngroups,
+                                                                          size_t npix, uint32_t per_thread,
+                                                                          unsigned long long *d_hist)
+{
+    PDL_PROLOGUE();
+    extern __shared__ __align__(16) uint32_t hp_smem[];
+    uint32_t *counters = hp_smem, *total = hp_smem + 64 * HP_THREADS;
+    const uint32_t tid = threadIdx.x;
+    uint8_t *mine = reinterpret_cast<uint8_t *>(counters + tid);
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < 64 * HP_THREADS / 4; i += HP_THREADS) reinterpret_cast<uint4 *>(counters)[i] = zero4;
+    total[tid] = 0;
+    __syncthreads();
+
+    const size_t chunk = (size_t)per_thread * HP_THREADS;  // groups per CTA between two folds
+    for (size_t base = (size_t)blockIdx.x * chunk; base < ngroups; base += (size_t)gridDim.x * chunk) {
+        size_t g = base + tid;
+        const size_t end = (base + chunk < ngroups) ? base + chunk : ngroups;
+        uint4 a, b, c;
+        if (g < end) {
+            a = __ldg(src + 3 * g);
+            b = __ldg(src + 3 * g + 1);
+            c = __ldg(src + 3 * g + 2);
+        }
+        while (g < end) {
+            const size_t gn = g + HP_THREADS;
+            uint4 na, nb, nc;
+            if (gn < end) {  // next group's loads fly while this one is counted
+                na = __ldg(src + 3 * gn);
+                nb = __ldg(src + 3 * gn + 1);
+                nc = __ldg(src + 3 * gn + 2);
+            }
+            const uint4 o = gray16(a, b, c);
+            if (STORE) dst[g] = o;
+            hp_bump4(mine, o.x);
+            hp_bump4(mine, o.y);
+            hp_bump4(mine, o.z);
+            hp_bump4(mine, o.w);
+            a = na;
+            b = nb;
+            c = nc;
+            g = gn;
+        }
+        __syncthreads();
+        {  // fold: thread `tid` sums bin `tid` over all 256 columns, rows skewed across banks
+            const uint32_t row = tid >> 2, sel = 1u << (8u * (tid & 3u));
+            const uint4 *rowp = reinterpret_cast<const uint4 *>(counters + row * HP_THREADS);
+            uint32_t acc = 0;
+#pragma unroll 8
+            for (uint32_t k = 0; k < 64; k++) {
+                const uint4 v = rowp[(k + row) & 63u];
+                acc = __dp4a(v.x, sel, acc);
+                acc = __dp4a(v.y, sel, acc);
+                acc = __dp4a(v.z, sel, acc);
+                acc = __dp4a(v.w, sel, acc);
+            }
+            total[tid] += acc;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < 64 * HP_THREADS / 4; i += HP_THREADS) reinterpret_cast<uint4 *>(counters)[i] = zero4;
+        __syncthreads();
+    }
+    // the last (npix % 16) pixels, scalar, straight into the per-CTA totals
+    if (blockIdx.x == 0 && tid < (npix - ngroups * 16)) {
+        const size_t i = ngroups * 16 + tid;
+        const uint8_t *s8 = reinterpret_cast<const uint8_t *>(src) + 3 * i;
+        const uint32_t g = div3((uint32_t)s8[0] + s8[1] + s8[2]);
+        if (STORE) reinterpret_cast<uint8_t *>(dst)[i] = (uint8_t)g;
+        atomicAdd(&total[g], 1u);
+    }
+    __syncthreads();
+    if (total[tid]) atomicAdd(&d_hist[tid], (unsigned long long)total[tid]);
+}
+
+// variant: one 16-pixel group per thread, one CTA per 256 groups (no grid-stride loop)
+__global__ void __launch_bounds__(256) gray_flat_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
+                                                        size_t ngroups, size_t npix)
+{
+    PDL_PROLOGUE();
+    const size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (g < ngroups) {
+        const uint4 *p = src + 3 * g;
+        const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        dst[g] = gray16(a, b, c);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (npix - ngroups * 16)) {
+        const size_t i = ngroups * 16 + threadIdx.x;
+        const uint8_t *s8 = reinterpret_cast<const uint8_t *>(src) + 3 * i;
+        reinterpret_cast<uint8_t *>(dst)[i] = (uint8_t)div3((uint32_t)s8[0] + s8[1] + s8[2]);
+    }
+}
+
+// ---- TMA bulk-copy pipeline (cp.async.bulk + mbarrier): one elected thread streams 12 KB tiles
+// of the raster into a ring of shared-memory stages; the CTA reads each tile conflict-free
+// (48 B per thread), computes, and stores 16 B per thread straight to global memory.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr int GT_STAGES = 4;
+constexpr int GT_TILE_GROUPS = 256;                 // one 16-pixel group per thread
+constexpr int GT_TILE_BYTES = GT_TILE_GROUPS * 48;  // 12288
+constexpr size_t GT_SMEM = (size_t)GT_STAGES * GT_TILE_BYTES + 128;
+
+__global__ void __launch_bounds__(256) gray_tma_kernel(const uint8_t *__restrict__ src, uint4 *__restrict__ dst,
+                                                       size_t ngroups, size_t npix)
+{
+    PDL_PROLOGUE();
+    extern __shared__ __align__(128) uint8_t gt_smem[];
+    __shared__ __align__(8) uint64_t full[GT_STAGES];
+    const uint32_t tid = threadIdx.x;
+    const size_t ntiles = (ngroups + GT_TILE_GROUPS - 1) / GT_TILE_GROUPS;
+    if (tid == 0) {
+        for (int s = 0; s < GT_STAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](size_t tile, int s) {
+        const size_t g0 = tile * GT_TILE_GROUPS;
+        const uint32_t groups = (uint32_t)((ngroups - g0 < GT_TILE_GROUPS) ? ngroups - g0 : GT_TILE_GROUPS);
+        mbar_expect_tx(&full[s], groups * 48u);
+        bulk_g2s(gt_smem + (size_t)s * GT_TILE_BYTES, src + g0 * 48, groups * 48u, &full[s]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < GT_STAGES; s++) {
+            const size_t t = (size_t)blockIdx.x + (size_t)s * gridDim.x;
+            if (t < ntiles) issue(t, s);
+        }
+    uint32_t it = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int s = it % GT_STAGES;
+        mbar_wait(&full[s], (it / GT_STAGES) & 1u);
+        const uint4 *p = reinterpret_cast<const uint4 *>(gt_smem + (size_t)s * GT_TILE_BYTES) + 3 * tid;
+        const uint4 a = p[0], b = p[1], c = p[2];
+        __syncthreads();  // every thread has read stage s: it may be refilled
+        if (tid == 0) {
+            const size_t nt = tile + (size_t)GT_STAGES * gridDim.x;
+            if (nt < ntiles) issue(nt, s);
+        }
+        const size_t g = tile * GT_TILE_GROUPS + tid;
+        if (g < ngroups) dst[g] = gray16(a, b, c);
+    }
+    if (blockIdx.x == 0 && tid < (npix - ngroups * 16)) {
+        const size_t i = ngroups * 16 + tid;
+        const uint8_t *s8 = src + 3 * i;
+        reinterpret_cast<uint8_t *>(dst)[i] = (uint8_t)div3((uint32_t)s8[0] + s8[1] + s8[2]);
+    }
+}
+
 template <bool HIST, bool STORE>
 static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, unsigned long long *d_hist,
                                  cudaStream_t s)
@@ -187,11 +431,40 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
     if (npix == 0) return cudaSuccess;
     if (aligned16(src) && (!STORE || aligned16(dst))) {
         size_t ngroups = npix / 16;
+        if (HIST && g_variant != 2) {
+            // thread-private byte counters: <= 15 groups per thread between folds, 3 CTAs per SM
+            static bool ok[64] = {};
+            allow_smem(gray_hist_private_kernel<STORE>, HP_SMEM, ok);
+            size_t wave = (size_t)sm_count() * 3 * HP_THREADS;
+            size_t per = (ngroups + wave - 1) / wave;
+            if (per < 1) per = 1;
+            if (per > HP_MAX_GROUPS) per = HP_MAX_GROUPS;
+            size_t chunks = (ngroups + per * HP_THREADS - 1) / (per * HP_THREADS);
+            if (chunks < 1) chunks = 1;
+            unsigned grid = (unsigned)(chunks < (size_t)sm_count() * 3 ? chunks : (size_t)sm_count() * 3);
+            launch(gray_hist_private_kernel<STORE>, dim3(grid), dim3(HP_THREADS), HP_SMEM, s,
+                   reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), ngroups, npix, (uint32_t)per, d_hist);
+            return PPMX_LAUNCHED();
+        }
+        if (!HIST && g_variant != 1 && g_variant != 4) {  // default: one group per thread, no loop
+            unsigned grid = (unsigned)((ngroups + 255) / 256);
+            launch(gray_flat_kernel, dim3(grid ? grid : 1), dim3(256), 0, s, reinterpret_cast<const uint4 *>(src),
+                   reinterpret_cast<uint4 *>(dst), ngroups, npix);
+            return PPMX_LAUNCHED();
+        }
+        if (!HIST && g_variant == 4) {
+            static bool ok[64] = {};
+            allow_smem(gray_tma_kernel, GT_SMEM, ok);
+            size_t ntiles = (ngroups + GT_TILE_GROUPS - 1) / GT_TILE_GROUPS;
+            unsigned grid = (unsigned)(ntiles < (size_t)sm_count() * 4 ? (ntiles ? ntiles : 1) : (size_t)sm_count() * 4);
+            launch(gray_tma_kernel, dim3(grid), dim3(256), GT_SMEM, s, src, reinterpret_cast<uint4 *>(dst), ngroups, npix);
+            return PPMX_LAUNCHED();
+        }
         unsigned grid = wave_grid(ngroups ? ngroups : 1, 256, 8);
-        gray_vec_kernel<HIST, STORE><<<grid, 256, 0, s>>>(reinterpret_cast<const uint4 *>(src),
+        launch(gray_vec_kernel<HIST, STORE>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const uint4 *>(src),
                                                           reinterpret_cast<uint4 *>(dst), ngroups, npix, d_hist);
     } else {
-        gray_scalar_kernel<HIST, STORE><<<wave_grid(npix, 256, 8), 256, 0, s>>>(src, dst, npix, d_hist);
+        launch(gray_scalar_kernel<HIST, STORE>, dim3(wave_grid(npix, 256, 8)), dim3(256), 0, s, src, dst, npix, d_hist);
     }
     return PPMX_LAUNCHED();
 }
@@ -214,6 +487,7 @@ cudaError_t hist_gray(const uint8_t *src, size_t npix, unsigned long long *d_his
 __global__ void __launch_bounds__(256) mono_plane_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                          uint32_t w, uint32_t h, uint32_t y0)
 {
+    PDL_PROLOGUE();
     const size_t n = (size_t)w * h, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t y = (uint32_t)(i / w), x = (uint32_t)(i - (size_t)y * w);
@@ -222,28 +496,23 @@ __global__ void __launch_bounds__(256) mono_plane_kernel(const uint8_t *__restri
     }
 }
 
-// w % 32 == 0 and 16-byte aligned rasters: one thread = 32 pixels (96 B in) = one output word
-__global__ void __launch_bounds__(256) mono_bits_vec_kernel(const uint4 *__restrict__ src, uint32_t *__restrict__ dst,
-                                                            uint32_t words_per_row, size_t nwords, uint32_t y0)
+// w % 16 == 0 and 16-byte aligned rasters: one thread = 16 pixels of one row (48 B in) = two
+// output bytes; one CTA per 256 such groups, no loop (same access pattern as gray)
+__global__ void __launch_bounds__(256) mono_bits_vec_kernel(const uint4 *__restrict__ src, uint16_t *__restrict__ dst,
+                                                            uint32_t groups_per_row, size_t ngroups, uint32_t y0)
 {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
-        uint32_t y = (uint32_t)(i / words_per_row) + y0;
-        uint32_t t4 = bayer_row4(y);
-        const uint4 *p = src + 6 * i;
-        uint32_t out = 0;
-#pragma unroll
-        for (int half = 0; half < 2; half++) {  // 16 pixels per half -> two output bytes
-            uint4 a = __ldg(p + 3 * half), b = __ldg(p + 3 * half + 1), c = __ldg(p + 3 * half + 2);
-            uint32_t n0 = mono_nibble(gray4(a.x, a.y, a.z), t4);
-            uint32_t n1 = mono_nibble(gray4(a.w, b.x, b.y), t4);
-            uint32_t n2 = mono_nibble(gray4(b.z, b.w, c.x), t4);
-            uint32_t n3 = mono_nibble(gray4(c.y, c.z, c.w), t4);
-            uint32_t two = ((n0 << 4) | n1) | (((n2 << 4) | n3) << 8);
-            out |= two << (16 * half);
-        }
-        dst[i] = out;
-    }
+    PDL_PROLOGUE();
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= ngroups) return;
+    const uint32_t y = (ngroups <= 0xFFFFFFFFull ? (uint32_t)i / groups_per_row : (uint32_t)(i / groups_per_row)) + y0;
+    const uint32_t t4 = bayer_row4(y);
+    const uint4 *p = src + 3 * i;
+    const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    const uint32_t n0 = mono_nibble(gray4(a.x, a.y, a.z), t4);
+    const uint32_t n1 = mono_nibble(gray4(a.w, b.x, b.y), t4);
+    const uint32_t n2 = mono_nibble(gray4(b.z, b.w, c.x), t4);
+    const uint32_t n3 = mono_nibble(gray4(c.y, c.z, c.w), t4);
+    dst[i] = (uint16_t)(((n0 << 4) | n1) | (((n2 << 4) | n3) << 8));  // little endian: pixels 0-7 first
 }
 
 // any width / alignment: one thread = one output byte (up to 8 pixels of one row)
@@ -251,6 +520,7 @@ __global__ void __launch_bounds__(256) mono_bits_generic_kernel(const uint8_t *_
                                                                 uint8_t *__restrict__ dst, uint32_t w, uint32_t h,
                                                                 uint32_t row_bytes, uint32_t y0)
 {
+    PDL_PROLOGUE();
     const size_t n = (size_t)row_bytes * h, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t y = (uint32_t)(i / row_bytes), bx = (uint32_t)(i - (size_t)y * row_bytes);
@@ -269,20 +539,20 @@ cudaError_t mono_plane(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h,
 {
     size_t n = (size_t)w * h;
     if (!n) return cudaSuccess;
-    mono_plane_kernel<<<wave_grid(n, 256, 8), 256, 0, s>>>(src, dst, w, h, y0);
+    launch(mono_plane_kernel, dim3(wave_grid(n, 256, 8)), dim3(256), 0, s, src, dst, w, h, y0);
     return PPMX_LAUNCHED();
 }
 
 cudaError_t mono_bits(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t y0, cudaStream_t s)
 {
     if (!w || !h) return cudaSuccess;
-    if ((w % 32u) == 0 && aligned16(src) && aligned4(dst)) {
-        size_t nwords = (size_t)(w / 32u) * h;
-        mono_bits_vec_kernel<<<wave_grid(nwords, 256, 8), 256, 0, s>>>(
-            reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint32_t *>(dst), w / 32u, nwords, y0);
+    if ((w % 16u) == 0 && aligned16(src) && aligned4(dst)) {
+        size_t ngroups = (size_t)(w / 16u) * h;
+        launch(mono_bits_vec_kernel, dim3((unsigned)((ngroups + 255) / 256)), dim3(256), 0, s,
+               reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint16_t *>(dst), w / 16u, ngroups, y0);
     } else {
         uint32_t rb = (w + 7u) / 8u;
-        mono_bits_generic_kernel<<<wave_grid((size_t)rb * h, 256, 8), 256, 0, s>>>(src, dst, w, h, rb, y0);
+        launch(mono_bits_generic_kernel, dim3(wave_grid((size_t)rb * h, 256, 8)), dim3(256), 0, s, src, dst, w, h, rb, y0);
     }
     return PPMX_LAUNCHED();
 }
@@ -292,6 +562,7 @@ __global__ void __launch_bounds__(256) pack_pbm_kernel(const uint8_t *__restrict
                                                        uint8_t *__restrict__ dst, uint32_t w, uint32_t h,
                                                        uint32_t row_bytes)
 {
+    PDL_PROLOGUE();
     const size_t n = (size_t)row_bytes * h, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t y = (uint32_t)(i / row_bytes), bx = (uint32_t)(i - (size_t)y * row_bytes);
@@ -307,7 +578,7 @@ cudaError_t pack_pbm(const uint8_t *src, int src_bpp, uint8_t *dst, uint32_t w, 
 {
     if (!w || !h) return cudaSuccess;
     uint32_t rb = (w + 7u) / 8u;
-    pack_pbm_kernel<<<wave_grid((size_t)rb * h, 256, 8), 256, 0, s>>>(src, src_bpp, dst, w, h, rb);
+    launch(pack_pbm_kernel, dim3(wave_grid((size_t)rb * h, 256, 8)), dim3(256), 0, s, src, src_bpp, dst, w, h, rb);
     return PPMX_LAUNCHED();
 }
 
@@ -315,6 +586,7 @@ cudaError_t pack_pbm(const uint8_t *src, int src_bpp, uint8_t *dst, uint32_t w, 
 __global__ void __launch_bounds__(256) extract_r_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                         size_t npix)
 {
+    PDL_PROLOGUE();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) dst[i] = src[3 * i];
 }
@@ -322,7 +594,7 @@ __global__ void __launch_bounds__(256) extract_r_kernel(const uint8_t *__restric
 cudaError_t extract_r(const uint8_t *src, uint8_t *dst, size_t npix, cudaStream_t s)
 {
     if (!npix) return cudaSuccess;
-    extract_r_kernel<<<wave_grid(npix, 256, 8), 256, 0, s>>>(src, dst, npix);
+    launch(extract_r_kernel, dim3(wave_grid(npix, 256, 8)), dim3(256), 0, s, src, dst, npix);
     return PPMX_LAUNCHED();
 }
 
@@ -333,19 +605,27 @@ cudaError_t extract_r(const uint8_t *src, uint8_t *dst, size_t npix, cudaStream_
 // vertical: row y of dst = row h-1-y of src; T = widest type the row pitch and pointers allow
 template <typename T>
 __global__ void __launch_bounds__(256) flipv_kernel(const T *__restrict__ src, T *__restrict__ dst,
-                                                    uint32_t row_elems, uint32_t h)
+                                                    uint32_t row_elems, uint32_t h, size_t n)
 {
-    const size_t n = (size_t)row_elems * h, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint32_t y = (uint32_t)(i / row_elems), e = (uint32_t)(i - (size_t)y * row_elems);
-        dst[i] = src[(size_t)(h - 1 - y) * row_elems + e];
+    PDL_PROLOGUE();
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t y, e;
+    if (n <= 0xFFFFFFFFull) {  // 32-bit division is several times cheaper than 64-bit
+        y = (uint32_t)i / row_elems;
+        e = (uint32_t)i - y * row_elems;
+    } else {
+        y = (uint32_t)(i / row_elems);
+        e = (uint32_t)(i - (size_t)y * row_elems);
     }
+    dst[i] = src[(size_t)(h - 1 - y) * row_elems + e];
 }
 
 // horizontal, any pixel size / alignment: one byte per thread
 __global__ void __launch_bounds__(256) fliph_generic_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                             uint32_t w, uint32_t h, int bpp)
 {
+    PDL_PROLOGUE();
     const size_t row = (size_t)w * bpp, n = row * h, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         size_t y = i / row;
@@ -376,19 +656,27 @@ __device__ __forceinline__ void reverse16px(const uint32_t (&in)[12], uint32_t (
 __global__ void __launch_bounds__(256) fliph_rgb16_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
                                                           uint32_t groups_per_row, size_t ngroups)
 {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ngroups; i += stride) {
-        size_t y = i / groups_per_row;
-        uint32_t g = (uint32_t)(i - y * groups_per_row);
-        const uint4 *p = src + 3 * (y * groups_per_row + (groups_per_row - 1 - g));
-        uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-        uint32_t in[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w}, o[12];
-        reverse16px(in, o);
-        uint4 *q = dst + 3 * i;
-        q[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        q[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        q[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    PDL_PROLOGUE();
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= ngroups) return;
+    size_t y;
+    uint32_t g;
+    if (ngroups <= 0xFFFFFFFFull) {
+        y = (uint32_t)i / groups_per_row;
+        g = (uint32_t)i - (uint32_t)y * groups_per_row;
+    } else {
+        y = i / groups_per_row;
+        g = (uint32_t)(i - y * groups_per_row);
     }
+    const uint4 *p = src + 3 * (y * groups_per_row + (groups_per_row - 1 - g));
+    const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    const uint32_t in[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    uint32_t o[12];
+    reverse16px(in, o);
+    uint4 *q = dst + 3 * i;
+    q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    q[2] = make_uint4(o[8], o[9], o[10], o[11]);
 }
 
 cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int bpp, int vertical, cudaStream_t s)
@@ -398,22 +686,23 @@ cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int b
     if (vertical) {
         if (row % 16 == 0 && aligned16(src) && aligned16(dst)) {
             size_t n = row / 16 * h;
-            flipv_kernel<uint4><<<wave_grid(n, 256, 8), 256, 0, s>>>(reinterpret_cast<const uint4 *>(src),
-                                                                    reinterpret_cast<uint4 *>(dst), (uint32_t)(row / 16), h);
+            launch(flipv_kernel<uint4>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
+                   reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), (uint32_t)(row / 16), h, n);
         } else if (row % 4 == 0 && aligned4(src) && aligned4(dst)) {
             size_t n = row / 4 * h;
-            flipv_kernel<uint32_t><<<wave_grid(n, 256, 8), 256, 0, s>>>(
-                reinterpret_cast<const uint32_t *>(src), reinterpret_cast<uint32_t *>(dst), (uint32_t)(row / 4), h);
+            launch(flipv_kernel<uint32_t>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
+                   reinterpret_cast<const uint32_t *>(src), reinterpret_cast<uint32_t *>(dst), (uint32_t)(row / 4), h, n);
         } else {
-            flipv_kernel<uint8_t><<<wave_grid(row * h, 256, 8), 256, 0, s>>>(src, dst, (uint32_t)row, h);
+            launch(flipv_kernel<uint8_t>, dim3((unsigned)((row * h + 255) / 256)), dim3(256), 0, s, src, dst, (uint32_t)row, h,
+                   row * h);
         }
     } else {
         if (bpp == 3 && (w % 16u) == 0 && aligned16(src) && aligned16(dst)) {
             size_t n = (size_t)(w / 16u) * h;
-            fliph_rgb16_kernel<<<wave_grid(n, 256, 8), 256, 0, s>>>(reinterpret_cast<const uint4 *>(src),
-                                                                   reinterpret_cast<uint4 *>(dst), w / 16u, n);
+            launch(fliph_rgb16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
+                   reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), w / 16u, n);
         } else {
-            fliph_generic_kernel<<<wave_grid(row * h, 256, 8), 256, 0, s>>>(src, dst, w, h, bpp);
+            launch(fliph_generic_kernel, dim3(wave_grid(row * h, 256, 8)), dim3(256), 0, s, src, dst, w, h, bpp);
         }
     }
     return PPMX_LAUNCHED();
@@ -427,6 +716,7 @@ cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int b
 __global__ void __launch_bounds__(256) reverse_pixels_kernel(const uint8_t *__restrict__ src,
                                                              uint8_t *__restrict__ dst, size_t npix)
 {
+    PDL_PROLOGUE();
     const size_t n = npix * 3, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         size_t p = i / 3;
@@ -445,6 +735,7 @@ template <bool CW>
 __global__ void __launch_bounds__(256) rotate_transpose_kernel(const uint8_t *__restrict__ src,
                                                                uint8_t *__restrict__ dst, uint32_t w, uint32_t h)
 {
+    PDL_PROLOGUE();
     __shared__ uint8_t tile[RT][RT_PITCH];
     const uint32_t tx0 = blockIdx.x * RT, ty0 = blockIdx.y * RT;
     const uint32_t tw = min((uint32_t)RT, w - tx0), th = min((uint32_t)RT, h - ty0);
@@ -470,6 +761,78 @@ __global__ void __launch_bounds__(256) rotate_transpose_kernel(const uint8_t *__
     }
 }
 
+// Fast path (w % 16 == 0, h % 16 == 0, 16-byte aligned rasters): 64 x 64 pixel tiles.
+//   phase 1: a thread loads 16 pixels of one source row (3 x 16 B), widens them to one word per
+//            pixel (r g b x) and stores 4 x 16 B into a swizzled shared tile (no bank conflicts);
+//   phase 2: a warp reads 32 neighbouring source columns, 16 source rows each, one word per
+//            lane and row (conflict free), repacks the 16 pixels to 48 B and writes them as
+//            three 16-byte stores into the destination row that column became.
+constexpr int XT = 64;
+
+__device__ __forceinline__ uint32_t xt_slot(uint32_t row, uint32_t chunk)
+{
+    // 16-byte chunk index inside a 256-byte tile row, swizzled so that both phases spread over all banks
+    return row * 64u + ((chunk ^ (((chunk >> 3) & 1u) << 1) ^ (row & 1u)) << 2);
+}
+
+template <bool CW>
+__global__ void __launch_bounds__(256) rotate_transpose64_kernel(const uint8_t *__restrict__ src,
+                                                                 uint8_t *__restrict__ dst, uint32_t w, uint32_t h)
+{
+    PDL_PROLOGUE();
+    __shared__ __align__(16) uint32_t tile[XT * 64];
+    const uint32_t tx0 = blockIdx.x * XT, ty0 = blockIdx.y * XT;
+    const size_t in_pitch = (size_t)w * 3, out_pitch = (size_t)h * 3;
+    {
+        const uint32_t row = threadIdx.x >> 2, q = threadIdx.x & 3u;
+        const uint32_t y = ty0 + row, x0 = tx0 + 16u * q;
+        if (y < h && x0 < w) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)y * in_pitch + (size_t)x0 * 3);
+            const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+            const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {  // 4 pixels = 3 words -> 4 words (byte 3 of each is don't-care)
+                uint4 o;
+                o.x = wd[3 * i];
+                o.y = __byte_perm(wd[3 * i], wd[3 * i + 1], 0x0543);
+                o.z = __byte_perm(wd[3 * i + 1], wd[3 * i + 2], 0x0432);
+                o.w = wd[3 * i + 2] >> 8;
+                *reinterpret_cast<uint4 *>(&tile[xt_slot(row, 4u * q + i)]) = o;
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        const uint32_t col = 32u * (warp & 1u) + lane, j = warp >> 1;  // source column, 16-row unit
+        const uint32_t x = tx0 + col, y0 = ty0 + 16u * j;
+        if (x < w && y0 < h) {
+            uint32_t px[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t r = 16u * j + k;
+                px[k] = tile[xt_slot(r, col >> 2) + (col & 3u)];
+            }
+            uint32_t o[12];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {  // 4 pixels -> 3 words; CW walks the source rows backwards
+                const uint32_t p0 = CW ? px[15 - 4 * i] : px[4 * i], p1 = CW ? px[14 - 4 * i] : px[4 * i + 1];
+                const uint32_t p2 = CW ? px[13 - 4 * i] : px[4 * i + 2], p3 = CW ? px[12 - 4 * i] : px[4 * i + 3];
+                o[3 * i] = __byte_perm(p0, p1, 0x4210);
+                o[3 * i + 1] = __byte_perm(p1, p2, 0x5421);
+                o[3 * i + 2] = __byte_perm(p2, p3, 0x6542);
+            }
+            size_t off;
+            if (CW) off = (size_t)x * out_pitch + (size_t)(h - y0 - 16u) * 3;        // out[x][h-1-y], ref:717
+            else off = (size_t)(w - 1u - x) * out_pitch + (size_t)y0 * 3;             // out[w-1-x][y], ref:725
+            uint4 *q = reinterpret_cast<uint4 *>(dst + off);
+            q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            q[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        }
+    }
+}
+
 cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int angle, cudaStream_t s)
 {
     if (!w || !h) return cudaSuccess;
@@ -478,17 +841,25 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
         if (npix % 16 == 0 && aligned16(src) && aligned16(dst)) {
             size_t n = npix / 16;  // one long row of npix pixels, mirrored
             if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
-            fliph_rgb16_kernel<<<wave_grid(n, 256, 8), 256, 0, s>>>(reinterpret_cast<const uint4 *>(src),
-                                                                   reinterpret_cast<uint4 *>(dst), (uint32_t)n, n);
+            launch(fliph_rgb16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
+                   reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), (uint32_t)n, n);
         } else {
-            reverse_pixels_kernel<<<wave_grid(npix * 3, 256, 8), 256, 0, s>>>(src, dst, npix);
+            launch(reverse_pixels_kernel, dim3(wave_grid(npix * 3, 256, 8)), dim3(256), 0, s, src, dst, npix);
         }
+        return PPMX_LAUNCHED();
+    }
+    if (angle != 90 && angle != 270) return cudaErrorInvalidValue;
+    if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && g_variant != 1) {
+        dim3 g64((w + XT - 1) / XT, (h + XT - 1) / XT);
+        if (g64.y > 65535u) return cudaErrorInvalidValue;
+        if (angle == 90) launch(rotate_transpose64_kernel<true>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+        else launch(rotate_transpose64_kernel<false>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
         return PPMX_LAUNCHED();
     }
     dim3 grid((w + RT - 1) / RT, (h + RT - 1) / RT);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
-    if (angle == 90) rotate_transpose_kernel<true><<<grid, 256, 0, s>>>(src, dst, w, h);
-    else if (angle == 270) rotate_transpose_kernel<false><<<grid, 256, 0, s>>>(src, dst, w, h);
+    if (angle == 90) launch(rotate_transpose_kernel<true>, dim3(grid), dim3(256), 0, s, src, dst, w, h);
+    else if (angle == 270) launch(rotate_transpose_kernel<false>, dim3(grid), dim3(256), 0, s, src, dst, w, h);
     else return cudaErrorInvalidValue;
     return PPMX_LAUNCHED();
 }
@@ -533,6 +904,7 @@ __global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__re
                                                              uint32_t nw, uint32_t nh, double cs, double sn,
                                                              int xc, int yc, int xo, int yo)
 {
+    PDL_PROLOGUE();
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= nw || y >= nh) return;
@@ -601,7 +973,7 @@ cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_
     int xo = (int)(nw / 2u) - (int)(w / 2u), yo = (int)(nh / 2u) - (int)(h / 2u);
     dim3 block(32, 8), grid((nw + 31) / 32, (nh + 7) / 8);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
-    rotate_bicubic_kernel<<<grid, block, 0, s>>>(src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+    launch(rotate_bicubic_kernel, dim3(grid), dim3(block), 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
     return PPMX_LAUNCHED();
 }
 
@@ -623,6 +995,7 @@ __global__ void __launch_bounds__(256) imresize_rows_kernel(const uint8_t *__res
                                                             uint32_t row_bytes, int out_h, int taps,
                                                             const double *__restrict__ wts, const int *__restrict__ idx)
 {
+    PDL_PROLOGUE();
     const uint32_t xb = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     const int y = blockIdx.y;
     if (xb >= row_bytes || y >= out_h) return;
@@ -656,6 +1029,7 @@ __global__ void __launch_bounds__(256) imresize_cols_kernel(const uint8_t *__res
                                                             uint32_t w, uint32_t h, int out_w, int taps,
                                                             const double *__restrict__ wts, const int *__restrict__ idx)
 {
+    PDL_PROLOGUE();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= out_w || y >= h) return;
@@ -688,19 +1062,17 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
             for (int y0 = 0; y0 < out_size; y0 += 65535) {
                 int rows = min(65535, out_size - y0);
                 grid.y = rows;
-                imresize_rows_kernel<4><<<grid, 256, 0, s>>>(src, dst + (size_t)y0 * row_bytes, row_bytes, rows, taps,
+                launch(imresize_rows_kernel<4>, dim3(grid), dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes, rows, taps,
                                                              d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
-                ++g_launches;
-            }
+                            }
         } else {
             dim3 grid((row_bytes + 255) / 256, 1);
             for (int y0 = 0; y0 < out_size; y0 += 65535) {
                 int rows = min(65535, out_size - y0);
                 grid.y = rows;
-                imresize_rows_kernel<1><<<grid, 256, 0, s>>>(src, dst + (size_t)y0 * row_bytes, row_bytes, rows, taps,
+                launch(imresize_rows_kernel<1>, dim3(grid), dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes, rows, taps,
                                                              d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
-                ++g_launches;
-            }
+                            }
         }
         return cudaGetLastError();
     }
@@ -709,13 +1081,12 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
         for (uint32_t y0 = 0; y0 < h; y0 += 65535u * 4u) {
             uint32_t rows = min(65535u * 4u, h - y0);
             dim3 g2(grid.x, (rows + 3) / 4);
-            imresize_cols_kernel<<<g2, block, 0, s>>>(src + (size_t)y0 * w * 3, dst + (size_t)y0 * out_size * 3, w, rows,
+            launch(imresize_cols_kernel, dim3(g2), dim3(block), 0, s, src + (size_t)y0 * w * 3, dst + (size_t)y0 * out_size * 3, w, rows,
                                                      out_size, taps, d_weights, d_indices);
-            ++g_launches;
-        }
+                    }
         return cudaGetLastError();
     }
-    imresize_cols_kernel<<<grid, block, 0, s>>>(src, dst, w, h, out_size, taps, d_weights, d_indices);
+    launch(imresize_cols_kernel, dim3(grid), dim3(block), 0, s, src, dst, w, h, out_size, taps, d_weights, d_indices);
     return PPMX_LAUNCHED();
 }
 
@@ -754,6 +1125,7 @@ constexpr int CONV_TH = 16;
 __global__ void __launch_bounds__(256) conv_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t w, int k,
                                                    int32_t div, int32_t bias)
 {
+    PDL_PROLOGUE();
     extern __shared__ uint8_t tile[];  // (CONV_TH + k - 1) rows x (CONV_TW + k - 1) pixels x 3
     const int r = k / 2, tw = CONV_TW + k - 1, th = CONV_TH + k - 1, tpitch = tw * 3;
     const int tx0 = blockIdx.x * CONV_TW, ty0 = blockIdx.y * CONV_TH;  // band-local output origin
@@ -805,7 +1177,7 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
     dim3 grid((w + CONV_TW - 1) / CONV_TW, (h + CONV_TH - 1) / CONV_TH);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
     size_t smem = (size_t)(CONV_TH + k - 1) * (CONV_TW + k - 1) * 3;
-    conv_kernel<<<grid, 256, smem, s>>>(rs, dst, w, k, div, bias);
+    launch(conv_kernel, dim3(grid), dim3(256), smem, s, rs, dst, w, k, div, bias);
     return PPMX_LAUNCHED();
 }
 

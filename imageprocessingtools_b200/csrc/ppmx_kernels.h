@@ -20,6 +20,7 @@ struct Band {
 
 // which implementation of an operator to launch; 0 = the default (best measured)
 extern int g_variant;
+extern int g_pdl;  // programmatic dependent launch on/off
 
 cudaError_t gray(const uint8_t *src, uint8_t *dst, size_t npix, unsigned long long *d_hist, cudaStream_t s);
 cudaError_t hist_gray(const uint8_t *src, size_t npix, unsigned long long *d_hist, cudaStream_t s);

@@ -107,6 +107,7 @@ def gpu_lib() -> C.CDLL:
         L.ppmx_gpu_ipc_export.argtypes = [vp, vp, _u8p]
         L.ppmx_gpu_ipc_open.argtypes = [vp, _u8p, C.POINTER(vp)]
         L.ppmx_gpu_ipc_close.argtypes = [vp, vp]
+        L.ppmx_gpu_set_tuning.argtypes = [C.c_char_p, C.c_int]
         L.ppmx_gpu_launch_count.restype = C.c_uint64
         L.ppmx_gpu_version.restype = C.c_char_p
         _gpu = L
@@ -408,6 +409,10 @@ class Ppmx:
 
     def tables_free(self, p: int) -> None:
         self.L.ppmx_gpu_tables_free(C.c_void_p(p))
+
+    def set_tuning(self, key: str, value: int) -> None:
+        if self.L.ppmx_gpu_set_tuning(key.encode(), int(value)) != 0:
+            raise PpmxError("unknown tuning key " + key)
 
     def launch_count(self) -> int:
         return int(self.L.ppmx_gpu_launch_count())

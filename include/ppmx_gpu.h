@@ -176,6 +176,11 @@ int ppmx_gpu_ipc_export(ppmx_gpu_ctx *ctx, const void *device_ptr, uint8_t handl
 int ppmx_gpu_ipc_open(ppmx_gpu_ctx *ctx, const uint8_t handle[64], void **device_ptr);
 int ppmx_gpu_ipc_close(ppmx_gpu_ctx *ctx, void *device_ptr);
 
+/* Experiment switches for benchmarking (not needed for correct results): key "variant" selects
+ * an alternative kernel implementation (0 = default), key "pdl" turns programmatic dependent
+ * launch on (1, default) or off (0).  Returns 0, or -1 for an unknown key. */
+int ppmx_gpu_set_tuning(const char *key, int value);
+
 /* number of kernel launches issued through this library since load (bench: gpu_launches) */
 uint64_t ppmx_gpu_launch_count(void);
 const char *ppmx_gpu_version(void);

@@ -1,0 +1,143 @@
+"""CPU-only checks of the host layer (C, libppmx_host.so) and of the ABI surface: no compute calls,
+no GPU.  Contribution tables and rotation sizes must be bit-identical to the oracle's."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import patterns as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pp():
+    from imageprocessingtools_b200 import build, ppmx
+    build.build_all()
+    return ppmx
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ppmx_[a-zA-Z0-9_]+)\s*\(", src)))
+
+
+def test_abi_exports_every_declared_symbol(pp):
+    """include/*.h is the contract: each declared function must be exported by the built libraries."""
+    for header, lib in (("ppmx_gpu.h", pp.GPU_SO), ("ppmx_host.h", pp.HOST_SO)):
+        names = _declared(header)
+        assert len(names) >= 15
+        out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+        exported = set(re.findall(r" T (\w+)", out))
+        missing = [n for n in names if n not in exported]
+        assert not missing, (header, missing)
+    L = pp.gpu_lib()
+    pp.host_lib()
+    assert b"sm_100a" in L.ppmx_gpu_version()
+
+
+def test_op_struct_layout(pp):
+    assert C.sizeof(pp.PpmxOp) == 96 and C.sizeof(pp.PpmxBand) == 32
+
+
+def test_library_holds_sm100a_code_only(pp):
+    out = subprocess.run(["cuobjdump", "-lelf", pp.GPU_SO], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_gpu_means_loud_failure(pp):
+    """The product has no CPU fallback: without a device ppmx_gpu_init must fail, not emulate."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import imageprocessingtools_b200 as ip
+    with pytest.raises(ip.PpmxError):
+        ip.Ppmx(0)
+
+
+def test_div3_multiplier_exact():
+    s = np.arange(0, 766, dtype=np.uint64)
+    assert np.array_equal((s * 43691) >> 17, s // 3)          # used by the kernels
+    assert not np.array_equal((s * 171) >> 9, s // 3)          # the shorter constant is NOT exact
+
+
+def test_mono_nibble_multiplier():
+    for m in range(16):
+        b = [(m >> (3 - i)) & 1 for i in range(4)]
+        word = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24)
+        assert ((word * 0x08040201) & 0xFFFFFFFF) >> 24 & 0xF == m
+
+
+def test_contributions_match_oracle(pp, orc):
+    for n_in, n_out in [(37, 74), (37, 55), (37, 37), (37, 18), (37, 7), (37, 3), (64, 96), (64, 13), (5, 64), (3, 2),
+                        (2, 1), (1, 3), (4096, 6144), (4096, 2048), (1920, 960), (1080, 540), (1000, 999)]:
+        s = float(n_out) / n_in
+        w0, i0 = orc.calc_contributions(n_in, n_out, s)
+        w1, i1 = pp.calc_contributions(n_in, n_out, s)
+        assert w0.shape == w1.shape and np.array_equal(i0, i1), (n_in, n_out)
+        assert np.array_equal(w0.view(np.uint64), w1.view(np.uint64)), (n_in, n_out)
+
+
+def test_rotation_sizes_and_cubic(pp, orc):
+    H = pp.host_lib()
+    for (w, h) in [(1, 1), (37, 23), (512, 512), (1920, 1080), (4096, 4096)]:
+        for a in range(360):
+            assert pp.rotate_size(a, w, h) == orc.rotate_size(a, w, h), (w, h, a)
+    for x in np.linspace(-3, 3, 601):
+        assert H.ppmx_cubic(float(x)) == orc.cubic(float(x))
+    for a in range(-20, 20):
+        for b in (0, 1, 2, 7):
+            assert H.ppmx_mod(a, b) == orc.lib.orc_mod(a, b)
+
+
+def test_header_parse_and_format(pp, orc):
+    raster = bytes(range(24))
+    assert pp.parse_header(b"P6\n4 2\n255\n" + raster) == (4, 2, 255, 11)
+    assert pp.parse_header(b"P6\n# a comment\n4 2\n# another\n255\n" + raster)[:3] == (4, 2, 255)
+    assert pp.parse_header(b"P6 4 2 255 " + raster)[3] == 11
+    for bad in (b"P3\n4 2\n255\n" + raster, b"P6\n4 2\n255\n" + raster + b"x", b"P6\n4 2\n255\n" + raster[:-4],
+                b"P6\n4 x\n255\n" + raster, b"\n", b"P6\n4 2\n65535\n" + raster * 2):
+        with pytest.raises(pp.PpmxError):
+            pp.parse_header(bad)
+    for ft in (0, 1, 2):
+        assert pp.format_header(ft, 37, 23, 255) == orc.header(ft, 37, 23, 255)
+
+
+def test_plan_chain_follows_reference_order(pp):
+    """ref:1084-1155: resize(2 passes) -> rotate -> gray|mono -> flipv|fliph; renew iff -w or -r."""
+    ph = pp._PlanHolder(resize_w=55, angle=90, gray=True, flipv=True, w=37, h=23)
+    ops = [ph.plan.ops[i] for i in range(ph.plan.nops)]
+    assert [o.kind for o in ops] == [pp.OP_IMRESIZE, pp.OP_IMRESIZE, pp.OP_ROTATE, pp.OP_GRAY, pp.OP_FLIP]
+    assert [o.renew_before for o in ops] == [0, 1, 1, 1, 1]
+    # scale[0] < scale[1] here, so the height pass runs first (ref:1102)
+    assert ops[0].dim == 0 and ops[1].dim == 1 and ops[1].out_size == 55 and ops[0].out_size == int(23 * (55 / 37))
+    ph.close()
+    ph = pp._PlanHolder(gray=True, fliph=True, w=8, h=8)  # the leaked-gray quirk: no renew without -w/-r
+    assert [ph.plan.ops[i].renew_before for i in range(ph.plan.nops)] == [0, 0]
+    ph.close()
+    ph = pp._PlanHolder(resize_w=74, w=37, h=23)  # exact scale: width pass first
+    assert ph.plan.ops[0].dim == 1 and ph.plan.ops[1].dim == 0
+    ph.close()
+    ph = pp._PlanHolder(w=8, h=8)
+    assert ph.plan.nops == 0
+    ph.close()
+
+
+def test_cli_flag_errors_match_reference(pp, tmp_path):
+    """Flag parsing happens before any device work, so these run without a GPU (ref:125-187)."""
+    import oracle
+    img = str(tmp_path / "x.ppm")
+    oracle.write_p6(img, P.lcg(4, 4, 1))
+    cases = [["-gray", "-mono", img], ["-fv", "-fh", img], ["-gray", "-gray", img], ["-r360", img], ["-r", img],
+             ["-wabc", img], ["-q", img], ["-fx", img], [img, img], []]
+    for args in cases:
+        ours = subprocess.run([pp.CLI] + args, capture_output=True, text=True)
+        assert ours.returncode == 255, args
+        if os.path.exists(oracle.REF_CLI):
+            ref = subprocess.run([oracle.REF_CLI] + args, capture_output=True, text=True)
+            assert ref.returncode == 255 and ref.stdout == ours.stdout, (args, ref.stdout, ours.stdout)
