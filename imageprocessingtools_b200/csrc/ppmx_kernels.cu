@@ -88,16 +88,26 @@ static inline unsigned wave_grid(size_t work_items, unsigned block, unsigned cta
 
 // s / 3 for 0 <= s <= 765, exact (checked exhaustively in tests/test_host_logic.py)
 __device__ __forceinline__ uint32_t div3(uint32_t s) { return (s * 43691u) >> 17; }
+// (one multiply-high, __umulhi(s, 0x55555556), is also exact but measured 10% slower: IMAD.HI
+// is not a full-rate instruction)
 
-// grey of 4 consecutive pixels held in 3 little-endian words (12 bytes r0 g0 b0 r1 ...),
-// ref:1000 -- one byte per pixel, pixel 0 in the low byte.
+// greys of 4 consecutive pixels held in 3 little-endian words (12 bytes r0 g0 b0 r1 ...), ref:1000
+__device__ __forceinline__ void gray4_split(uint32_t a, uint32_t b, uint32_t c, uint32_t (&q)[4])
+{
+    q[0] = div3(__dp4a(a, 0x00010101u, 0u));
+    q[1] = div3(__dp4a(a, 0x01000000u, __dp4a(b, 0x00000101u, 0u)));
+    q[2] = div3(__dp4a(b, 0x01010000u, __dp4a(c, 0x00000001u, 0u)));
+    q[3] = div3(__dp4a(c, 0x01010100u, 0u));
+}
+__device__ __forceinline__ uint32_t pack4(const uint32_t (&q)[4])
+{  // one byte per pixel, pixel 0 in the low byte
+    return __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+}
 __device__ __forceinline__ uint32_t gray4(uint32_t a, uint32_t b, uint32_t c)
 {
-    uint32_t s0 = __dp4a(a, 0x00010101u, 0u);
-    uint32_t s1 = __dp4a(a, 0x01000000u, __dp4a(b, 0x00000101u, 0u));
-    uint32_t s2 = __dp4a(b, 0x01010000u, __dp4a(c, 0x00000001u, 0u));
-    uint32_t s3 = __dp4a(c, 0x01010100u, 0u);
-    return div3(s0) | (div3(s1) << 8) | (div3(s2) << 16) | (div3(s3) << 24);
+    uint32_t q[4];
+    gray4_split(a, b, c, q);
+    return pack4(q);
 }
 
 // 16 pixels = 48 bytes = three 16-byte vectors -> 16 grey bytes
@@ -322,6 +332,80 @@ __global__ void __launch_bounds__(HP_THREADS, 3) gray_hist_private_kernel(const 
     if (total[tid]) atomicAdd(&d_hist[tid], (unsigned long long)total[tid]);
 }
 
+// ---- histogram with one shared-memory column per LANE: bins[256][32] u32.  Lane l of every warp
+// only ever touches bank l, so a warp's 32 updates never conflict (a constant image costs the same
+// as noise); warps share columns, hence RED.shared adds.  One fold + one global atomic pass per CTA.
+constexpr size_t HL_SMEM = 256 * 32 * sizeof(uint32_t);
+
+__device__ __forceinline__ uint32_t hl_gray4(uint32_t *col, uint32_t a, uint32_t b, uint32_t c)
+{  // grey of 4 pixels, each counted in this lane's column before the bytes are packed
+    uint32_t q[4];
+    gray4_split(a, b, c, q);
+#pragma unroll
+    for (int i = 0; i < 4; i++) atomicAdd(col + q[i] * 32u, 1u);
+    return pack4(q);
+}
+
+constexpr int HL_THREADS = 1024;
+template <bool STORE>
+__global__ void __launch_bounds__(HL_THREADS, 1) gray_hist_lanes_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
+                                                              size_t ngroups, size_t npix,
+                                                              unsigned long long *d_hist)
+{
+    PDL_PROLOGUE();
+    extern __shared__ __align__(16) uint32_t hl_bins[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < 256 * 32 / 4; i += HL_THREADS) reinterpret_cast<uint4 *>(hl_bins)[i] = zero4;
+    __syncthreads();
+    uint32_t *col = hl_bins + lane;
+    // few, fat CTAs (one per SM): the final 256 global atomics per CTA hit only 16 cache lines, and
+    // every CTA adds to all of them, so the number of CTAs is what that last pass costs
+    const size_t stride = (size_t)gridDim.x * HL_THREADS;
+    size_t g = (size_t)blockIdx.x * HL_THREADS + tid;
+    for (; g + stride < ngroups; g += 2 * stride) {  // two groups (96 B) in flight per thread
+        const uint4 *p = src + 3 * g, *p2 = src + 3 * (g + stride);
+        const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        const uint4 a2 = __ldg(p2), b2 = __ldg(p2 + 1), c2 = __ldg(p2 + 2);
+        uint4 o, o2;
+        o.x = hl_gray4(col, a.x, a.y, a.z);
+        o.y = hl_gray4(col, a.w, b.x, b.y);
+        o.z = hl_gray4(col, b.z, b.w, c.x);
+        o.w = hl_gray4(col, c.y, c.z, c.w);
+        if (STORE) dst[g] = o;
+        o2.x = hl_gray4(col, a2.x, a2.y, a2.z);
+        o2.y = hl_gray4(col, a2.w, b2.x, b2.y);
+        o2.z = hl_gray4(col, b2.z, b2.w, c2.x);
+        o2.w = hl_gray4(col, c2.y, c2.z, c2.w);
+        if (STORE) dst[g + stride] = o2;
+    }
+    if (g < ngroups) {
+        const uint4 *p = src + 3 * g;
+        const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        uint4 o;
+        o.x = hl_gray4(col, a.x, a.y, a.z);
+        o.y = hl_gray4(col, a.w, b.x, b.y);
+        o.z = hl_gray4(col, b.z, b.w, c.x);
+        o.w = hl_gray4(col, c.y, c.z, c.w);
+        if (STORE) dst[g] = o;
+    }
+    if (blockIdx.x == 0 && tid < (npix - ngroups * 16)) {
+        const size_t i = ngroups * 16 + tid;
+        const uint8_t *s8 = reinterpret_cast<const uint8_t *>(src) + 3 * i;
+        const uint32_t g = div3((uint32_t)s8[0] + s8[1] + s8[2]);
+        if (STORE) reinterpret_cast<uint8_t *>(dst)[i] = (uint8_t)g;
+        atomicAdd(col + (g << 5), 1u);
+    }
+    __syncthreads();
+    if (tid < 256) {  // fold bin `tid` over its 32 columns, starting at a different bank per lane
+        const uint32_t *row = hl_bins + tid * 32u;
+        uint32_t t = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 32; k++) t += row[(k + lane) & 31u];
+        if (t) atomicAdd(&d_hist[tid], (unsigned long long)t);
+    }
+}
+
 // variant: one 16-pixel group per thread, one CTA per 256 groups (no grid-stride loop)
 __global__ void __launch_bounds__(256) gray_flat_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
                                                         size_t ngroups, size_t npix)
@@ -431,7 +515,17 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
     if (npix == 0) return cudaSuccess;
     if (aligned16(src) && (!STORE || aligned16(dst))) {
         size_t ngroups = npix / 16;
-        if (HIST && g_variant != 2) {
+        if (HIST && g_variant != 2 && g_variant != 5) {
+            // lane-private columns, RED.shared; one 1024-thread CTA per SM
+            static bool ok[64] = {};
+            allow_smem(gray_hist_lanes_kernel<STORE>, HL_SMEM, ok);
+            size_t want = (ngroups + HL_THREADS - 1) / HL_THREADS, wave = (size_t)sm_count();
+            unsigned grid = (unsigned)(want < 1 ? 1 : want < wave ? want : wave);
+            launch(gray_hist_lanes_kernel<STORE>, dim3(grid), dim3(HL_THREADS), HL_SMEM, s, reinterpret_cast<const uint4 *>(src),
+                   reinterpret_cast<uint4 *>(dst), ngroups, npix, d_hist);
+            return PPMX_LAUNCHED();
+        }
+        if (HIST && g_variant == 5) {
             // thread-private byte counters: <= 15 groups per thread between folds, 3 CTAs per SM
             static bool ok[64] = {};
             allow_smem(gray_hist_private_kernel<STORE>, HP_SMEM, ok);
@@ -764,15 +858,16 @@ __global__ void __launch_bounds__(256) rotate_transpose_kernel(const uint8_t *__
 // Fast path (w % 16 == 0, h % 16 == 0, 16-byte aligned rasters): 64 x 64 pixel tiles.
 //   phase 1: a thread loads 16 pixels of one source row (3 x 16 B), widens them to one word per
 //            pixel (r g b x) and stores 4 x 16 B into a swizzled shared tile (no bank conflicts);
-//   phase 2: a warp reads 32 neighbouring source columns, 16 source rows each, one word per
-//            lane and row (conflict free), repacks the 16 pixels to 48 B and writes them as
-//            three 16-byte stores into the destination row that column became.
+//   phase 2: a lane reads one source column over 16 source rows, one word per row (conflict
+//            free), repacks the 16 pixels to 48 B and writes them as three 16-byte stores into
+//            the destination row that column became; 4 lanes complete 192 contiguous bytes.
 constexpr int XT = 64;
 
 __device__ __forceinline__ uint32_t xt_slot(uint32_t row, uint32_t chunk)
 {
-    // 16-byte chunk index inside a 256-byte tile row, swizzled so that both phases spread over all banks
-    return row * 64u + ((chunk ^ (((chunk >> 3) & 1u) << 1) ^ (row & 1u)) << 2);
+    // 16-byte chunk index inside a 256-byte tile row, swizzled so that both phases spread over all
+    // banks: phase 1 stores rows (r, r+1) x 4 quarter rows at once, phase 2 reads rows 16 apart
+    return row * 64u + ((chunk ^ (((chunk >> 3) & 1u) << 1) ^ (row & 1u) ^ (((row >> 4) & 3u) << 1)) << 2);
 }
 
 template <bool CW>
@@ -803,8 +898,10 @@ __global__ void __launch_bounds__(256) rotate_transpose64_kernel(const uint8_t *
     }
     __syncthreads();
     {
+        // four neighbouring lanes take the four 16-row units of one source column, so together they
+        // write one contiguous 192-byte piece of a destination row
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-        const uint32_t col = 32u * (warp & 1u) + lane, j = warp >> 1;  // source column, 16-row unit
+        const uint32_t col = 8u * warp + (lane >> 2), j = lane & 3u;  // source column, 16-row unit
         const uint32_t x = tx0 + col, y0 = ty0 + 16u * j;
         if (x < w && y0 < h) {
             uint32_t px[16];
