@@ -34,9 +34,10 @@ UNIT = "Mpix/s"
 
 # workload -> (w, h, batch, algorithmic bytes per input pixel, description)
 WORKLOADS = {
-    "gray": (4096, 4096, 16, 4.0, "4096x4096 P6 RGB->greyscale (config 2), 16 distinct rasters per step"),
-    "gray_hist": (4096, 4096, 16, 4.0, "4096x4096 P6 RGB->greyscale + histogram fused (config 2), 16 rasters per step"),
-    "mono": (4096, 4096, 16, 3.125, "4096x4096 P6 -> Bayer bilevel P4 bits, 16 rasters per step"),
+    "gray": (4096, 4096, 32, 4.0, "4096x4096 P6 RGB->greyscale, 32 distinct rasters per step"),
+    "gray_hist": (4096, 4096, 32, 4.0,
+                  "4096x4096 P6 RGB->greyscale + histogram in one pass (config 2), 32 distinct rasters per step"),
+    "mono": (4096, 4096, 32, 3.125, "4096x4096 P6 -> Bayer bilevel P4 bits, 32 rasters per step"),
     "fliph": (4096, 4096, 8, 6.0, "4096x4096 horizontal flip, 8 rasters per step"),
     "flipv": (4096, 4096, 8, 6.0, "4096x4096 vertical flip, 8 rasters per step"),
     "rot90": (4096, 4096, 8, 6.0, "4096x4096 rotate 90, 8 rasters per step"),
@@ -47,7 +48,7 @@ WORKLOADS = {
     "resize_down": (4096, 4096, 2, None, "4096x4096 -w2048 bicubic resize (FP64), 2 rasters per step"),
     "rot30": (4096, 4096, 2, None, "4096x4096 -r30 bicubic rotate (FP64), 2 rasters per step"),
 }
-DEFAULT_WORKLOAD = "gray"
+DEFAULT_WORKLOAD = "gray_hist"
 PER_OP = ["gray", "gray_hist", "mono", "fliph", "flipv", "rot90", "rot180", "conv3", "conv7", "resize_up",
           "resize_down", "rot30"]
 
@@ -61,10 +62,16 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples SM clock and throttle reasons during the timed region (pynvml, else nvidia-smi)."""
+    """Samples SM clock and throttle reasons while the GPU works (pynvml).  Samples taken between
+    mark_timed(True) and mark_timed(False) belong to the timed region; if that region is too short to
+    catch three samples the summary falls back to every sample taken under load and says so."""
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+             0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.max_mhz = index, [], None
+        self.timed = False
         self._stop = threading.Event()
         self._t = None
 
@@ -74,20 +81,19 @@ class ClockSampler:
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
-                     0x80: "hw_power_brake_slowdown"}
             while not self._stop.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, n in names.items():
-                    if r & bit:
-                        self.reasons.add(n)
-                time.sleep(0.02)
+                self.samples.append((self.timed, mhz, r))
+                time.sleep(0.002)
         except Exception:
             pass
+
+    def mark_timed(self, on: bool):
+        self.timed = on
 
     def __enter__(self):
         self._t = threading.Thread(target=self._loop, daemon=True)
@@ -99,9 +105,16 @@ class ClockSampler:
         self._t.join(timeout=2)
 
     def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        timed = [x for x in self.samples if x[0]]
+        use, window = (timed, "timed region") if len(timed) >= 3 else (self.samples, "whole run under load")
+        mhz = sorted(x[1] for x in use)
+        reasons = set()
+        for _, _, r in use:
+            for bit, n in self.NAMES.items():
+                if r & bit:
+                    reasons.add(n)
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(use), "window": window}
 
 
 # --------------------------------------------------------------------------------------------
@@ -180,7 +193,7 @@ class Runner:
             k.close()
 
 
-def time_steps(torch, runner, steps, warmup, dist=None, after_step=None):
+def time_steps(torch, runner, steps, warmup, dist=None, after_step=None, clk=None):
     stream = torch.cuda.current_stream().cuda_stream
     for _ in range(warmup):
         runner.step(stream)
@@ -191,6 +204,8 @@ def time_steps(torch, runner, steps, warmup, dist=None, after_step=None):
         dist.barrier()
         torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if clk is not None:
+        clk.mark_timed(True)
     e0.record()
     for _ in range(steps):
         runner.step(stream)
@@ -198,6 +213,8 @@ def time_steps(torch, runner, steps, warmup, dist=None, after_step=None):
             after_step()
     e1.record()
     torch.cuda.synchronize()
+    if clk is not None:
+        clk.mark_timed(False)
     if dist is not None:
         dist.barrier()
         torch.cuda.synchronize()
@@ -218,8 +235,10 @@ def e2e_run(torch, g, name, steps, warmup, device, dist=None):
     if name == "gray":
         ops = (pp.PpmxOp * 1)(pp.PpmxOp(kind=pp.OP_GRAY))
         out_each = w * h
-    elif name == "gray_hist":  # the chain API has no histogram output: gray through the chain
-        ops = (pp.PpmxOp * 1)(pp.PpmxOp(kind=pp.OP_GRAY))
+    elif name == "gray_hist":
+        hist_host = torch.zeros((batch, 256), dtype=torch.int64).pin_memory()
+        ops = (pp.PpmxOp * 1)(pp.PpmxOp(kind=pp.OP_GRAY_HIST,
+                                        hist_out=C.cast(C.c_void_p(hist_host.data_ptr()), C.POINTER(C.c_uint64))))
         out_each = w * h
     elif name == "mono":
         ops = (pp.PpmxOp * 1)(pp.PpmxOp(kind=pp.OP_MONO))
@@ -337,7 +356,7 @@ def run_ours(args):
 
     n0 = g.launch_count()
     with ClockSampler(local) as clk:
-        ms = time_steps(torch, runner, args.steps, args.warmup, dist, after)
+        ms = time_steps(torch, runner, args.steps, args.warmup, dist, after, clk)
     launches = (g.launch_count() - n0) - args.warmup * runner.launches_per_step
     px = world * args.steps * runner.pixels_per_step
     value = px / (ms / 1e3) / 1e6
@@ -432,7 +451,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))

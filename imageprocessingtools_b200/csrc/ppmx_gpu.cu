@@ -356,7 +356,7 @@ static int launch_op(const ppmx_op *op, const uint8_t *d_src, uint32_t w, uint32
 }
 
 static int op_on(ppmx_gpu_ctx *c, int lane, const ppmx_op *op, const ppmx_gpu_image *src, ppmx_gpu_image **dst,
-                 const DeviceTables *shared_tables, bool want_hist)
+                 const DeviceTables *shared_tables, unsigned long long *d_hist)
 {
     uint32_t ow, oh;
     int ol;
@@ -375,9 +375,9 @@ static int op_on(ppmx_gpu_ctx *c, int lane, const ppmx_op *op, const ppmx_gpu_im
         }
         tables = &local;
     }
-    if (want_hist) CK(cudaMemsetAsync(c->d_hist, 0, 256 * sizeof(unsigned long long), s), "clear hist");
+    if (d_hist) CK(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), s), "clear hist");
     // rotate's uncovered pixels are written as 0 by the kernel itself (ref:727); no memset needed
-    int rc = launch_op(op, src->d, src->w, src->h, src->layout, out ? out->d : nullptr, Band(), c->d_hist, tables, s);
+    int rc = launch_op(op, src->d, src->w, src->h, src->layout, out ? out->d : nullptr, Band(), d_hist, tables, s);
     if (local.base) cudaFreeAsync(local.base, s);
     if (rc != PPMX_OK) {
         image_free_on(c, out);
@@ -395,7 +395,7 @@ extern "C" int ppmx_gpu_op(ppmx_gpu_ctx *c, const ppmx_op *op, const ppmx_gpu_im
     *dst = nullptr;
     const bool hist = (op->kind == PPMX_OP_HIST_GRAY || op->kind == PPMX_OP_GRAY_HIST);
     if (hist && !hist_out) return fail("histogram operator needs hist_out");
-    int rc = op_on(c, src->lane, op, src, dst, nullptr, hist);
+    int rc = op_on(c, src->lane, op, src, dst, nullptr, hist ? c->d_hist : nullptr);
     if (rc != PPMX_OK) return rc;
     if (hist) {
         cudaStream_t s = c->lane[src->lane];
@@ -426,7 +426,7 @@ static int download_on(ppmx_gpu_ctx *c, int lane, const ppmx_gpu_image *img, int
         cv.kind = -1;
     }
     if (cv.kind >= 0) {
-        if (op_on(c, lane, &cv, img, tmp, nullptr, false) != PPMX_OK) return PPMX_ERROR;
+        if (op_on(c, lane, &cv, img, tmp, nullptr, nullptr) != PPMX_OK) return PPMX_ERROR;
         from = *tmp;
     }
     if (from->bytes > cap) return fail("destination buffer too small");
@@ -457,6 +457,7 @@ struct Chain {
     int lane;
     ppmx_gpu_image *buff = nullptr, *newb = nullptr;  // newb may alias buff (flip, rotate 0)
     int file_type = PPMX_FILETYPE_PPM;
+    int index = 0;  // position of this raster in a batch
 
     void drop_new()
     {  // the reference leaks a superseded new_buff; here it goes back to the pool
@@ -492,14 +493,30 @@ static int run_chain(Chain &ch, const ppmx_op *ops, int nops, const std::vector<
             if (i == nops - 1) op.kind = PPMX_OP_MONO_BITS;
             /* fall through */
         case PPMX_OP_GRAY:
-            if (op_on(c, ch.lane, &op, ch.buff, &out, nullptr, false) != PPMX_OK) return PPMX_ERROR;
+            if (op_on(c, ch.lane, &op, ch.buff, &out, nullptr, nullptr) != PPMX_OK) return PPMX_ERROR;
             ch.drop_new();
             ch.newb = out;
             ch.file_type = (op.kind == PPMX_OP_GRAY) ? PPMX_FILETYPE_PGM : PPMX_FILETYPE_PBM;  // ref:991, 956
             break;
+        case PPMX_OP_GRAY_HIST: {  // extension: gray (ref:998-1000) + its 256-bin histogram in one pass
+            if (!op.hist_out) return fail("gray+hist in a chain needs op.hist_out");
+            unsigned long long *dh = nullptr;
+            cudaStream_t s = c->lane[ch.lane];
+            CK(cudaMallocAsync((void **)&dh, 256 * sizeof(unsigned long long), s), "cudaMallocAsync hist");
+            int rc = op_on(c, ch.lane, &op, ch.buff, &out, nullptr, dh);
+            if (rc == PPMX_OK)
+                rc = cudaMemcpyAsync(op.hist_out + 256 * (size_t)ch.index, dh, 256 * sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost, s) == cudaSuccess ? PPMX_OK : fail("hist D2H");
+            cudaFreeAsync(dh, s);
+            if (rc != PPMX_OK) return rc;
+            ch.drop_new();
+            ch.newb = out;
+            ch.file_type = PPMX_FILETYPE_PGM;
+            break;
+        }
         case PPMX_OP_FLIP:
             // ref:896: works on buff itself and aliases new_buff to it
-            if (op_on(c, ch.lane, &op, ch.buff, &out, nullptr, false) != PPMX_OK) return PPMX_ERROR;
+            if (op_on(c, ch.lane, &op, ch.buff, &out, nullptr, nullptr) != PPMX_OK) return PPMX_ERROR;
             ch.drop_new();
             image_free_on(c, ch.buff);
             ch.buff = ch.newb = out;
@@ -513,7 +530,7 @@ static int run_chain(Chain &ch, const ppmx_op *ops, int nops, const std::vector<
             /* fall through */
         case PPMX_OP_IMRESIZE:
         case PPMX_OP_CONV:
-            if (op_on(c, ch.lane, &op, ch.buff, &out, t, false) != PPMX_OK) return PPMX_ERROR;
+            if (op_on(c, ch.lane, &op, ch.buff, &out, t, nullptr) != PPMX_OK) return PPMX_ERROR;
             ch.drop_new();
             ch.newb = out;
             break;
@@ -567,6 +584,7 @@ extern "C" int ppmx_gpu_apply_batch(ppmx_gpu_ctx *c, const ppmx_op *ops, int nop
         Chain ch;
         ch.c = c;
         ch.lane = i % kLanes;
+        ch.index = i;
         rc = upload_on(c, ch.lane, src + (size_t)i * in_bytes, w, h, PPMX_LAYOUT_RGB8, &ch.buff);
         if (rc == PPMX_OK) rc = run_chain(ch, ops, nops, tables);
         if (rc == PPMX_OK) {

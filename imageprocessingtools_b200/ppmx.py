@@ -39,7 +39,8 @@ class PpmxOp(C.Structure):
                 ("new_width", C.c_uint32), ("new_height", C.c_uint32),
                 ("dim", C.c_int32), ("out_size", C.c_int32), ("weights_sz", C.c_int32),
                 ("weights", _dblp), ("indices", _i32p),
-                ("conv_k", C.c_int32), ("conv_div", C.c_int32), ("conv_bias", C.c_int32), ("conv_coef", _i32p)]
+                ("conv_k", C.c_int32), ("conv_div", C.c_int32), ("conv_bias", C.c_int32), ("conv_coef", _i32p),
+                ("hist_out", C.POINTER(C.c_uint64))]
 
 
 class PpmxBand(C.Structure):
@@ -366,6 +367,23 @@ class Ppmx:
             return out[:n.value].copy(), rw.value, rh.value, ft.value
         finally:
             ph.close()
+
+    def apply_ops(self, imgs, ops, out_bytes_each: Optional[int] = None):
+        """ppmx_gpu_apply_batch on a stack of equally sized rasters (n, h, w, 3) with an explicit op list.
+        Returns (outputs (n, bytes_each) uint8, out_w, out_h, file_type)."""
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        if imgs.ndim == 3:
+            imgs = imgs[None]
+        n, h, w, _ = imgs.shape
+        arr = (PpmxOp * len(ops))(*ops)
+        cap = out_bytes_each or (max(w, h) ** 2 * 6 + 64)
+        out = np.empty((n, cap), np.uint8)
+        each, rw, rh, ft = C.c_size_t(), C.c_uint32(), C.c_uint32(), C.c_int()
+        rc = self.L.ppmx_gpu_apply_batch(self.ctx, arr, len(ops), _vp(imgs), w, h, n, _vp(out), cap, C.byref(each),
+                                         C.byref(rw), C.byref(rh), C.byref(ft))
+        if rc != 0:
+            raise PpmxError("ppmx_gpu_apply_batch failed")
+        return out[:, :each.value].copy(), rw.value, rh.value, ft.value
 
     @staticmethod
     def header(file_type: int, w: int, h: int, maxval: int = 255) -> bytes:

@@ -75,6 +75,9 @@ typedef struct ppmx_op {
     int32_t conv_div;        /* > 0                                                         */
     int32_t conv_bias;
     const int32_t *conv_coef; /* k*k, row major                                             */
+    /* extension: histogram.  GRAY_HIST inside a chain writes 256 bins per raster here (host
+     * memory, raster i of a batch at hist_out + 256*i); ppmx_gpu_op takes its own argument.   */
+    uint64_t *hist_out;
 } ppmx_op;
 
 typedef struct ppmx_gpu_ctx ppmx_gpu_ctx;     /* one CUDA device, one stream, buffer pool   */

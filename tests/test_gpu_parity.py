@@ -216,6 +216,31 @@ def test_extension_conv(gpu, orc):
                 assert np.array_equal(gpu.conv(img, coef, div, bias), orc.conv(img, coef, div, bias)), (w, h, pname, kname)
 
 
+def test_batch_and_gray_hist_chain(gpu, orc):
+    """ppmx_gpu_apply_batch: rasters go round-robin over the context's streams; results stay per raster."""
+    import ctypes as C
+    import imageprocessingtools_b200.ppmx as pp
+    imgs = np.stack([P.lcg(96, 40, 100 + i) for i in range(7)])
+    out, w, h, ft = gpu.apply_ops(imgs, [pp.PpmxOp(kind=pp.OP_FLIP, flip_direction=0, renew_before=0)])
+    assert (w, h, ft) == (96, 40, 0)
+    for i in range(7):
+        assert np.array_equal(out[i].reshape(40, 96, 3), orc.flip(imgs[i], 0))
+    ph = pp._PlanHolder(resize_w=60, angle=90, mono=True, w=96, h=40)
+    ops = [ph.plan.ops[i] for i in range(ph.plan.nops)]
+    out, w, h, ft = gpu.apply_ops(imgs, ops)
+    for i in range(7):
+        exp, ew, eh, eft = orc.process(imgs[i], resize_w=60, angle=90, mono=True)
+        assert (w, h, ft) == (ew, eh, eft) and np.array_equal(out[i], exp), i
+    ph.close()
+    bins = np.zeros((7, 256), np.uint64)
+    op = pp.PpmxOp(kind=pp.OP_GRAY_HIST, hist_out=bins.ctypes.data_as(C.POINTER(C.c_uint64)))
+    out, w, h, ft = gpu.apply_ops(imgs, [op])
+    assert ft == 1
+    for i in range(7):
+        assert np.array_equal(out[i].reshape(40, 96), orc.gray(imgs[i]))
+        assert np.array_equal(bins[i], orc.hist_gray(imgs[i]))
+
+
 def test_extension_histogram(gpu, orc):
     for (w, h) in [(1, 1), (13, 7), (64, 64), (301, 211), (1024, 1024)]:
         for pname in ("lcg", "c200", "bayer"):
