@@ -53,6 +53,16 @@ PER_OP = ["gray", "gray_hist", "mono", "fliph", "flipv", "rot90", "rot180", "con
           "resize_down", "rot30"]
 
 
+def traffic_for(name):
+    """DRAM bytes per launch from the committed ncu --set full capture of this kernel, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p)).get(name)
+        return int(t["dram_read"] + t["dram_write"]) if t else None
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -324,9 +334,11 @@ def cpu_baseline_sample(name, threads, seconds_budget=12.0):
     for t in ts:
         t.join()
     total_px = sum(count) * w * h
+    fn = {"gray_hist": "gray", "fliph": "flip", "flipv": "flip", "rot90": "rotate", "rot180": "rotate",
+          "rot30": "rotate"}.get(name, name)
     return {"value": round(total_px / max(op_time) / 1e6, 1), "unit": UNIT, "cores": threads, "kind": kind,
             "sample": "%d calls of the reference's %s() on %dx%d rasters over %d thread(s); time inside the "
-                      "reference function only (its own image_buff_alloc included)" % (sum(count), name, w, h, threads)}
+                      "reference function only (its own image_buff_alloc included)" % (sum(count), fn, w, h, threads)}
 
 
 def run_ours(args):
@@ -376,7 +388,8 @@ def run_ours(args):
         per_launch_ms = ms / (args.steps * runner.launches_per_step)
         achieved = bpp * w * h / (per_launch_ms / 1e3) / 1e9
         line["roofline"] = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                            "frac": round(achieved / peak, 4), "traffic": traffic_for(name), "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": int(bpp * w * h),
                             "kernel": name, "algorithmic_bytes_per_pixel": bpp,
                             "avg_launch_us": round(per_launch_ms * 1e3, 2)}
     else:
