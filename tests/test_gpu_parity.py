@@ -208,12 +208,65 @@ KERNELS = {
 }
 
 
+KERNELS["big5"] = (np.array([[300, -200, 0, 5, 1]] * 5), 7, -3)  # coefficients beyond int8: generic kernel
+
+
 def test_extension_conv(gpu, orc):
-    for (w, h) in [(1, 1), (2, 3), (5, 4), (37, 23), (64, 48), (130, 70), (301, 211)]:
+    for (w, h) in [(1, 1), (2, 3), (5, 4), (37, 23), (64, 48), (130, 70), (301, 211), (16, 1), (16, 40), (128, 32),
+                   (144, 37), (256, 64), (400, 33)]:
         for pname in ("lcg", "checker", "mixed"):
             img = P.all_patterns(w, h)[pname]
             for kname, (coef, div, bias) in KERNELS.items():
                 assert np.array_equal(gpu.conv(img, coef, div, bias), orc.conv(img, coef, div, bias)), (w, h, pname, kname)
+
+
+def test_extension_conv_row_bands(gpu, orc):
+    """A raster cut into row bands, each convolved separately with halo rows read through the band
+    pointers (here: the neighbour band in the same HBM), equals the whole-raster result."""
+    import torch
+    import imageprocessingtools_b200.ppmx as pp
+    for (w, h, k, cuts) in [(128, 96, 3, [0, 32, 64, 96]), (128, 96, 7, [0, 24, 48, 72, 96]), (64, 50, 5, [0, 7, 13, 50]),
+                            (37, 23, 3, [0, 10, 23]), (256, 40, 7, [0, 3, 6, 40])]:
+        coef, div, bias = (np.ones((k, k), np.int64), k * k, 0) if k != 5 else KERNELS["emboss5"]
+        img = P.lcg(w, h, 77)
+        exp = orc.conv(img, coef, div, bias)
+        r = k // 2
+        dev = torch.device("cuda", 0)
+        bands = [torch.from_numpy(img[a:b].copy()).to(dev) for a, b in zip(cuts[:-1], cuts[1:])]
+        outs = [torch.zeros_like(b) for b in bands]
+        op = gpu.conv_op(coef, div, bias)
+        for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+            band = pp.PpmxBand(full_h=h, y0=a, halo=r)
+            # halo rows: the last r rows of the band above, the first r rows of the band below
+            if i > 0:
+                prev = bands[i - 1]
+                assert prev.shape[0] >= r
+                band.d_top = prev.data_ptr() + (prev.shape[0] - r) * w * 3
+            if i < len(bands) - 1:
+                assert bands[i + 1].shape[0] >= r
+                band.d_bottom = bands[i + 1].data_ptr()
+            gpu.launch(op, bands[i].data_ptr(), w, b - a, pp.LAYOUT_RGB8, outs[i].data_ptr(), band)
+        torch.cuda.synchronize()
+        got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+        assert np.array_equal(got, exp), (w, h, k)
+
+
+def test_mono_row_bands_keep_bayer_phase(gpu, orc):
+    import torch
+    import imageprocessingtools_b200.ppmx as pp
+    w, h = 64, 23
+    img = P.bayer_edges(w, h)
+    exp = orc.pack_pbm(orc.mono(img))
+    dev = torch.device("cuda", 0)
+    got = []
+    for a, b in [(0, 5), (5, 6), (6, 23)]:  # cuts that are not multiples of 4
+        src = torch.from_numpy(img[a:b].copy()).to(dev)
+        dst = torch.zeros(((b - a) * (w // 8),), dtype=torch.uint8, device=dev)
+        gpu.launch(pp.PpmxOp(kind=pp.OP_MONO_BITS), src.data_ptr(), w, b - a, pp.LAYOUT_RGB8, dst.data_ptr(),
+                   pp.PpmxBand(full_h=h, y0=a))
+        torch.cuda.synchronize()
+        got.append(dst.cpu().numpy())
+    assert np.array_equal(np.concatenate(got), exp)
 
 
 def test_batch_and_gray_hist_chain(gpu, orc):

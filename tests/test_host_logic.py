@@ -141,3 +141,26 @@ def test_cli_flag_errors_match_reference(pp, tmp_path):
         if os.path.exists(oracle.REF_CLI):
             ref = subprocess.run([oracle.REF_CLI] + args, capture_output=True, text=True)
             assert ref.returncode == 255 and ref.stdout == ours.stdout, (args, ref.stdout, ours.stdout)
+
+
+def test_conv_rounding_magic():
+    """The convolution's exact floor((2*acc+div)/(2*div)) via one multiply-high (ppmx_kernels.cu
+    make_conv_round / ConvRound): n/d == (n*M) >> (31+l) for all 0 <= n < 2^31."""
+    rng = np.random.default_rng(0)
+    for div in [1, 2, 3, 7, 9, 16, 25, 49, 81, 100, 255, 256, 1000, 4096, 65535, 12345678]:
+        d = 2 * div
+        l = 0
+        while (1 << l) < d:
+            l += 1
+        M = ((1 << (31 + l)) + d - 1) // d
+        assert M < (1 << 32)
+        ns = np.concatenate([np.arange(0, 70000, dtype=np.uint64), rng.integers(0, 1 << 31, 200000).astype(np.uint64),
+                             np.array([(1 << 31) - 1 - i for i in range(1000)], np.uint64),
+                             (np.arange(1, 5000, dtype=np.uint64) * np.uint64(d)) - np.uint64(1),
+                             np.arange(1, 5000, dtype=np.uint64) * np.uint64(d)])
+        ns = ns[ns < (1 << 31)]
+        hi = (ns.astype(object) * M) >> 32
+        q = np.array([int(v) >> (l - 1) for v in hi], dtype=object)
+        assert all(int(a) == int(b) // d for a, b in zip(q[::37], ns[::37]))
+        exp = (ns // np.uint64(d)).astype(object)
+        assert (q == exp).all(), div
