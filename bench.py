@@ -341,6 +341,83 @@ def cpu_baseline_sample(name, threads, seconds_budget=12.0):
                       "reference function only (its own image_buff_alloc included)" % (sum(count), fn, w, h, threads)}
 
 
+def band_split_run(torch, g, dist, rank, world, device, k=3, full=16384, iters=10):
+    """BASELINE config 4: ONE full x full raster cut into row bands (ppmx_band_plan), one band per rank, k x k
+    convolution (extension op) with the r = k/2 halo rows read straight from the neighbours' HBM over NVLink
+    (CUDA IPC peer pointers, no copy, no collective).  Total work is fixed: strong scaling."""
+    import numpy as np
+    from imageprocessingtools_b200 import ppmx as pp
+    w = full
+    r = k // 2
+    y0, rows = pp.band_plan(full, world, rank, 1)
+    nbytes = rows * w * 3
+    gen = torch.Generator(device=device)
+    gen.manual_seed(0xBA2D ^ rank)
+    srcs, handles = [], []
+    for i in range(2):  # two distinct rasters alternate so that a band never stays resident in the 126 MB L2
+        p = g.device_alloc(nbytes)
+        t = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=device, generator=gen)
+        g.copy(p, t.data_ptr(), nbytes, 2)
+        del t
+        srcs.append(p)
+        handles.append(g.ipc_export(p))
+    dst = g.device_alloc(nbytes)
+    peers = {}
+    bands = []
+    if world > 1:
+        info = [None] * world
+        dist.all_gather_object(info, (rows, handles))
+        for nb in (rank - 1, rank + 1):
+            if 0 <= nb < world:
+                peers[nb] = [g.ipc_open(hd) for hd in info[nb][1]]
+        for i in range(2):
+            b = pp.PpmxBand(full_h=full, y0=y0, halo=r)
+            if rank > 0:
+                b.d_top = peers[rank - 1][i] + (info[rank - 1][0] - r) * w * 3
+            if rank < world - 1:
+                b.d_bottom = peers[rank + 1][i]
+            bands.append(b)
+        dist.barrier()
+    else:
+        bands = [pp.PpmxBand(full_h=full, y0=0, halo=r)] * 2
+    coef = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], np.int32) if k == 3 else np.ones((k, k), np.int32)
+    op = g.conv_op(coef, 16 if k == 3 else k * k, 0)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i):
+        g.launch(op, srcs[i & 1], w, rows, pp.LAYOUT_RGB8, dst, bands[i & 1], 0, 0, stream)
+
+    for i in range(4):
+        step(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        dist.barrier()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    for lst in peers.values():
+        for p in lst:
+            g.ipc_close(p)
+    if dist is not None:
+        dist.barrier()  # nobody frees a band a neighbour may still have mapped
+    for p in srcs + [dst]:
+        g.device_free(p)
+    mp = iters * full * full / (ms / 1e3) / 1e6
+    return {"workload": "%dx%d raster, %dx%d convolution (extension), row bands over %d GPU(s), halo rows read from "
+                        "peer HBM over NVLink" % (full, full, k, k, world),
+            "scaling": "strong", "mpix_s": round(mp, 1), "ms_per_raster": round(ms / iters, 4),
+            "gbs_total": round(6.0 * mp / 1e3, 1), "rows_per_gpu": rows, "halo_rows": r}
+
+
 def run_ours(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -426,6 +503,11 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample(name, 1)
     runner.close()
+    del runner
+    torch.cuda.empty_cache()
+    if not args.no_band:
+        line["band_split"] = [band_split_run(torch, g, dist, rank, world, device, k=3),
+                              band_split_run(torch, g, dist, rank, world, device, k=7)]
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -470,6 +552,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-per-op", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-band", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

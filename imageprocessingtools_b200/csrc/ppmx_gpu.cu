@@ -679,6 +679,16 @@ extern "C" void ppmx_gpu_device_free(ppmx_gpu_ctx *c, void *device_ptr)
     if (device_ptr) cudaFree(device_ptr);
 }
 
+extern "C" int ppmx_gpu_copy(ppmx_gpu_ctx *c, void *dst, const void *src, size_t bytes, int kind)
+{
+    if (!c || (bytes && (!dst || !src))) return fail("ppmx_gpu_copy: null argument");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, k, c->lane[0]), "cudaMemcpyAsync");
+    CK(cudaStreamSynchronize(c->lane[0]), "sync");
+    return PPMX_OK;
+}
+
 extern "C" int ppmx_gpu_ipc_export(ppmx_gpu_ctx *c, const void *device_ptr, uint8_t handle[64])
 {
     if (!c || !device_ptr || !handle) return fail("ppmx_gpu_ipc_export: null argument");

@@ -314,6 +314,26 @@ void ppmx_plan_free(ppmx_plan *plan)
     plan->nops = 0;
 }
 
+/* ------------------------------------------------------------------ row bands over GPUs */
+
+int ppmx_band_plan(unsigned int full_h, int nranks, int rank, unsigned int align, unsigned int *y0,
+                   unsigned int *rows)
+{
+    unsigned int units, base, extra, u0, u1, a, b;
+    if (nranks < 1 || rank < 0 || rank >= nranks || align < 1 || !y0 || !rows) return PPMX_ERROR;
+    units = (full_h + align - 1) / align;          /* the last unit may be short */
+    base = units / (unsigned int)nranks;
+    extra = units % (unsigned int)nranks;          /* the first `extra` ranks get one unit more */
+    u0 = (unsigned int)rank * base + ((unsigned int)rank < extra ? (unsigned int)rank : extra);
+    u1 = u0 + base + ((unsigned int)rank < extra ? 1u : 0u);
+    a = u0 * align; b = u1 * align;
+    if (a > full_h) a = full_h;
+    if (b > full_h) b = full_h;
+    *y0 = a;
+    *rows = b - a;
+    return PPMX_OK;
+}
+
 /* ------------------------------------------------------------------ P6 in, P6/P5/P4 out */
 
 /* cursor over the in-memory file with the reference's lookahead rules (ref:333-347) */

@@ -105,6 +105,7 @@ def gpu_lib() -> C.CDLL:
         L.ppmx_gpu_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
         L.ppmx_gpu_device_free.argtypes = [vp, vp]
         L.ppmx_gpu_device_free.restype = None
+        L.ppmx_gpu_copy.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
         L.ppmx_gpu_ipc_export.argtypes = [vp, vp, _u8p]
         L.ppmx_gpu_ipc_open.argtypes = [vp, _u8p, C.POINTER(vp)]
         L.ppmx_gpu_ipc_close.argtypes = [vp, vp]
@@ -134,6 +135,7 @@ def host_lib() -> C.CDLL:
         H.ppmx_plan_chain.argtypes = [C.POINTER(_ArgsFlag), C.c_uint, C.c_double, C.c_uint, C.c_uint, C.POINTER(_Plan)]
         H.ppmx_plan_free.argtypes = [C.POINTER(_Plan)]
         H.ppmx_plan_free.restype = None
+        H.ppmx_band_plan.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, _u32p, _u32p]
         H.ppmx_parse_header.argtypes = [C.c_char_p, C.c_size_t, _u32p, _u32p, _u32p, C.POINTER(C.c_size_t)]
         H.ppmx_format_header.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_uint]
         _host = H
@@ -178,6 +180,14 @@ def rotate_size(angle: float, w: int, h: int) -> Tuple[int, int]:
     nw, nh = C.c_uint32(), C.c_uint32()
     host_lib().ppmx_calc_rot_size(a, w, h, C.byref(nw), C.byref(nh))
     return nw.value, nh.value
+
+
+def band_plan(full_h: int, nranks: int, rank: int, align: int = 1) -> Tuple[int, int]:
+    """ppmx_band_plan (host C): rows [y0, y0+rows) of a full_h-row raster owned by `rank`."""
+    y0, rows = C.c_uint32(), C.c_uint32()
+    if host_lib().ppmx_band_plan(full_h, nranks, rank, align, C.byref(y0), C.byref(rows)) != 0:
+        raise PpmxError("ppmx_band_plan failed")
+    return y0.value, rows.value
 
 
 def parse_header(data: bytes):
@@ -418,6 +428,36 @@ class Ppmx:
                                     C.c_void_p(d_tables), C.c_void_p(stream))
         if rc != 0:
             raise PpmxError("ppmx_gpu_launch failed (kind %d)" % op.kind)
+
+    # -- exportable HBM + CUDA IPC (one process per GPU reads its neighbours' bands over NVLink) --
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        if self.L.ppmx_gpu_device_alloc(self.ctx, nbytes, C.byref(p)) != 0:
+            raise PpmxError("ppmx_gpu_device_alloc failed")
+        return p.value
+
+    def device_free(self, p: int) -> None:
+        self.L.ppmx_gpu_device_free(self.ctx, C.c_void_p(p))
+
+    def copy(self, dst: int, src: int, nbytes: int, kind: int) -> None:
+        if self.L.ppmx_gpu_copy(self.ctx, C.c_void_p(dst), C.c_void_p(src), nbytes, kind) != 0:
+            raise PpmxError("ppmx_gpu_copy failed")
+
+    def ipc_export(self, p: int) -> bytes:
+        h = (C.c_uint8 * 64)()
+        if self.L.ppmx_gpu_ipc_export(self.ctx, C.c_void_p(p), h) != 0:
+            raise PpmxError("ppmx_gpu_ipc_export failed")
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        if self.L.ppmx_gpu_ipc_open(self.ctx, h, C.byref(p)) != 0:
+            raise PpmxError("ppmx_gpu_ipc_open failed")
+        return p.value
+
+    def ipc_close(self, p: int) -> None:
+        self.L.ppmx_gpu_ipc_close(self.ctx, C.c_void_p(p))
 
     def tables_upload(self, op: PpmxOp) -> int:
         p = C.c_void_p()

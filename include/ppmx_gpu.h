@@ -175,6 +175,9 @@ int ppmx_gpu_op_output(const ppmx_op *op, uint32_t w, uint32_t h, int layout,
  * into this process; halo rows are then read over NVLink by the kernels themselves. */
 int ppmx_gpu_device_alloc(ppmx_gpu_ctx *ctx, size_t bytes, void **device_ptr); /* exportable HBM */
 void ppmx_gpu_device_free(ppmx_gpu_ctx *ctx, void *device_ptr);
+/* plain copies on the context's first stream, blocking: kind 0 = host->device, 1 = device->host,
+ * 2 = device->device (also between a local and a peer-mapped pointer) */
+int ppmx_gpu_copy(ppmx_gpu_ctx *ctx, void *dst, const void *src, size_t bytes, int kind);
 int ppmx_gpu_ipc_export(ppmx_gpu_ctx *ctx, const void *device_ptr, uint8_t handle[64]);
 int ppmx_gpu_ipc_open(ppmx_gpu_ctx *ctx, const uint8_t handle[64], void **device_ptr);
 int ppmx_gpu_ipc_close(ppmx_gpu_ctx *ctx, void *device_ptr);

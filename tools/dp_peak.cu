@@ -1,0 +1,73 @@
+// tools/dp_peak.cu -- measures the non-fused FP64 issue rate of this GPU: independent chains of
+// DMUL + DADD (never contracted to DFMA), the instruction mix of the bicubic operators.
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -fmad=false -o tools/dp_peak tools/dp_peak.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int CHAINS>
+__global__ void __launch_bounds__(256) dp_kernel(double *out, double a, double b, int iters)
+{
+    double v[CHAINS];
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) v[i] = a + i + threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < CHAINS; i++) v[i] = __dadd_rn(__dmul_rn(v[i], b), a);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) s += v[i];
+    if (s == 12345.678) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) dfma_kernel(double *out, double a, double b, int iters)
+{
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = a + i + threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = fma(v[i], b, a);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += v[i];
+    if (s == 12345.678) out[0] = s;
+}
+
+int main()
+{
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int clk_khz = 0;
+    cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+    double *d;
+    cudaMalloc(&d, 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4096, grid = sms * 8;
+    for (int rep = 0; rep < 3; rep++) {
+        dp_kernel<8><<<grid, 256>>>(d, 1.0000001, 0.9999999, iters);
+        cudaEventRecord(e0);
+        dp_kernel<8><<<grid, 256>>>(d, 1.0000001, 0.9999999, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double ops = (double)grid * 256 * iters * 8 * 2;  // DMUL + DADD
+        printf("{\"kind\": \"dmul+dadd\", \"dp_inst_per_s\": %.4g, \"per_sm_per_clk_at_max\": %.2f, \"ms\": %.3f}\n", ops / (ms * 1e-3),
+               ops / (ms * 1e-3) / sms / (clk_khz * 1e3), ms);
+        dfma_kernel<<<grid, 256>>>(d, 1.0000001, 0.9999999, iters);
+        cudaEventRecord(e0);
+        dfma_kernel<<<grid, 256>>>(d, 1.0000001, 0.9999999, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        ops = (double)grid * 256 * iters * 8;
+        printf("{\"kind\": \"dfma\", \"dp_inst_per_s\": %.4g, \"per_sm_per_clk_at_max\": %.2f, \"ms\": %.3f}\n", ops / (ms * 1e-3),
+               ops / (ms * 1e-3) / sms / (clk_khz * 1e3), ms);
+    }
+    printf("{\"sms\": %d, \"max_clock_mhz\": %d}\n", sms, clk_khz / 1000);
+    return 0;
+}
