@@ -976,6 +976,23 @@ __device__ __forceinline__ double u8_to_double(uint32_t v)
     return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
 }
 
+// four u8 -> double conversions from one word.  CONV 0: I2F.F64.U8 with byte selectors (ptxas
+// emits them for uchar4 members; XU pipe).  CONV 1: the exact 2^52 trick (one DADD each; FP64 pipe).
+template <int CONV>
+__device__ __forceinline__ void word_to_double4(uint32_t w, double (&d)[4])
+{
+    if (CONV == 0) {
+        const uchar4 b = *reinterpret_cast<const uchar4 *>(&w);
+        d[0] = (double)b.x;
+        d[1] = (double)b.y;
+        d[2] = (double)b.z;
+        d[3] = (double)b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) d[i] = u8_to_double((w >> (8 * i)) & 0xFFu);
+    }
+}
+
 // Keys cubic convolution kernel, a = -0.5 (ref:477-489), same association as the source
 __device__ __forceinline__ double cubic(double x)
 {
@@ -996,6 +1013,8 @@ __device__ __forceinline__ double round_half_up(double v) { return floor(dadd(v,
 // rotate, arbitrary angle  (ref:726-786): inverse map + 4x4 bicubic, nearest on a 2-pixel ring
 // ------------------------------------------------------------------------------------------
 
+// WORDS: w % 4 == 0 and an aligned raster -- the 12 bytes of a tap row come in as aligned words.
+template <bool WORDS, int CONV>
 __global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__restrict__ src,
                                                              uint8_t *__restrict__ dst, uint32_t w, uint32_t h,
                                                              uint32_t nw, uint32_t nh, double cs, double sn,
@@ -1028,13 +1047,30 @@ __global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__re
             double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint8_t *row = src + ((size_t)(v0 + j) * w + u0) * 3;
                 double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+                if (WORDS) {
+                    const uint32_t b0 = 3u * (uint32_t)u0, sh = (b0 & 3u) * 8u;
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(src + (size_t)(v0 + j) * w * 3) + (b0 >> 2);
+                    const uint32_t q0w = __ldg(rw), q1w = __ldg(rw + 1), q2w = __ldg(rw + 2);
+                    const uint32_t q3w = (b0 & 3u) ? __ldg(rw + 3) : 0u;  // only needed when the run is unaligned
+                    double d[3][4];
+                    word_to_double4<CONV>(__funnelshift_r(q0w, q1w, sh), d[0]);
+                    word_to_double4<CONV>(__funnelshift_r(q1w, q2w, sh), d[1]);
+                    word_to_double4<CONV>(__funnelshift_r(q2w, q3w, sh), d[2]);
 #pragma unroll
-                for (int i = 0; i < 4; i++) {  // ref:762-764
-                    p0 = dadd(p0, dmul(u8_to_double(row[3 * i]), wx[i]));
-                    p1 = dadd(p1, dmul(u8_to_double(row[3 * i + 1]), wx[i]));
-                    p2 = dadd(p2, dmul(u8_to_double(row[3 * i + 2]), wx[i]));
+                    for (int i = 0; i < 4; i++) {  // ref:762-764
+                        p0 = dadd(p0, dmul(d[(3 * i) >> 2][(3 * i) & 3], wx[i]));
+                        p1 = dadd(p1, dmul(d[(3 * i + 1) >> 2][(3 * i + 1) & 3], wx[i]));
+                        p2 = dadd(p2, dmul(d[(3 * i + 2) >> 2][(3 * i + 2) & 3], wx[i]));
+                    }
+                } else {
+                    const uint8_t *row = src + ((size_t)(v0 + j) * w + u0) * 3;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {  // ref:762-764
+                        p0 = dadd(p0, dmul(u8_to_double(row[3 * i]), wx[i]));
+                        p1 = dadd(p1, dmul(u8_to_double(row[3 * i + 1]), wx[i]));
+                        p2 = dadd(p2, dmul(u8_to_double(row[3 * i + 2]), wx[i]));
+                    }
                 }
                 q0 = dadd(q0, dmul(p0, wy[j]));  // ref:766-768
                 q1 = dadd(q1, dmul(p1, wy[j]));
@@ -1046,9 +1082,10 @@ __global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__re
             if (q0 >= 256.0) q0 = 255.0;
             if (q1 >= 256.0) q1 = 255.0;
             if (q2 >= 256.0) q2 = 255.0;
-            r = (uint32_t)__double2int_rz(q0);  // truncation, ref:779-781
-            g = (uint32_t)__double2int_rz(q1);
-            b = (uint32_t)__double2int_rz(q2);
+            // truncation (ref:779-781) of a value in [0, 256): floor, as the low word of q + 1.5*2^52
+            r = (uint32_t)__double2loint(__dadd_rd(q0, 6755399441055744.0));
+            g = (uint32_t)__double2loint(__dadd_rd(q1, 6755399441055744.0));
+            b = (uint32_t)__double2loint(__dadd_rd(q2, 6755399441055744.0));
         } else {  // nearest, ref:783
             const uint8_t *p = src + ((size_t)(int)ry * w + (size_t)(int)rx) * 3;
             r = p[0];
@@ -1070,7 +1107,14 @@ cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_
     int xo = (int)(nw / 2u) - (int)(w / 2u), yo = (int)(nh / 2u) - (int)(h / 2u);
     dim3 block(32, 8), grid((nw + 31) / 32, (nh + 7) / 8);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
-    launch(rotate_bicubic_kernel, dim3(grid), dim3(block), 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+    if ((w % 4u) == 0 && aligned4(src) && g_variant != 1) {
+        if (g_variant == 2)
+            launch(rotate_bicubic_kernel<true, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+        else
+            launch(rotate_bicubic_kernel<true, 0>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+    } else {
+        launch(rotate_bicubic_kernel<false, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+    }
     return PPMX_LAUNCHED();
 }
 
@@ -1083,6 +1127,129 @@ __device__ __forceinline__ uint32_t quantise(double s)
 {
     s = round_half_up(s);                                           // ref:831
     return (s < 0.0) ? 0u : (s >= 256.0) ? 255u : (uint32_t)__double2int_rz(s);  // ref:835
+}
+
+// The same result with one DP add instead of FRND + compares + F2I: for |v| < 2^31,
+// v + 1.5*2^52 rounded toward -inf is floor(v) + 1.5*2^52 exactly and its low word is floor(v) as
+// an int32; "< 0 -> 0" and ">= 256 -> 255" on floor(v) (ref:835) become an integer clamp.
+__device__ __forceinline__ uint32_t quantise_fast(double s)
+{
+    const double v = dadd(s, 0.5);                                                // ref:27, 831
+    const int n = __double2loint(__dadd_rd(v, 6755399441055744.0));
+    return (uint32_t)min(max(n, 0), 255);
+}
+
+// height pass, fast path (row pitch % 16 == 0, aligned): one thread = 16 bytes of an output row
+template <int CONV>
+__global__ void __launch_bounds__(256) imresize_rows16_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                              uint32_t row_vecs, int taps,
+                                                              const double *__restrict__ wts, const int *__restrict__ idx)
+{
+    PDL_PROLOGUE();
+    const uint32_t xv = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    if (xv >= row_vecs) return;
+    const double *wy = wts + (size_t)y * taps;
+    const int *iy = idx + (size_t)y * taps;
+    const size_t row_bytes = (size_t)row_vecs * 16;
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = 0.0;
+    for (int z = 0; z < taps; z++) {  // tap order is the reference's summation order (ref:826-830)
+        const double wz = __ldg(wy + z);
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)__ldg(iy + z) * row_bytes) + xv);
+        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double d[4];
+            word_to_double4<CONV>(wd[q], d);
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[4 * q + b] = dadd(acc[4 * q + b], dmul(d[b], wz));
+        }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        o[q] = quantise_fast(acc[4 * q]) | (quantise_fast(acc[4 * q + 1]) << 8) | (quantise_fast(acc[4 * q + 2]) << 16) |
+               (quantise_fast(acc[4 * q + 3]) << 24);
+    reinterpret_cast<uint4 *>(dst + (size_t)y * row_bytes)[xv] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// width pass, fast path (w % 4 == 0, aligned, 4 <= K <= 8): one thread = one output column for a
+// run of rows; its K weights and indices live in registers.  When the K taps are consecutive source
+// pixels (always, except where the table mirrors at the raster's edge) their 3K bytes are fetched as
+// aligned words and funnel-shifted into place; otherwise tap by tap.
+template <int K, int CONV>
+__global__ void __launch_bounds__(128) imresize_colsK_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                             uint32_t w, uint32_t h, int out_w, int rows_per_cta,
+                                                             const double *__restrict__ wts, const int *__restrict__ idx)
+{
+    PDL_PROLOGUE();
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    if (x >= out_w) return;
+    double wk[K];
+    int ik[K];
+#pragma unroll
+    for (int z = 0; z < K; z++) {
+        wk[z] = __ldg(wts + (size_t)x * K + z);
+        ik[z] = __ldg(idx + (size_t)x * K + z);
+    }
+    bool consecutive = true;
+#pragma unroll
+    for (int z = 1; z < K; z++) consecutive = consecutive && (ik[z] == ik[0] + z);
+    constexpr int NS = (3 * K + 3) / 4;  // words of the aligned 3K-byte stream
+    const uint32_t b0 = 3u * (uint32_t)ik[0], w0 = b0 >> 2, sh = (b0 & 3u) * 8u;
+    const uint32_t y0 = blockIdx.y * (uint32_t)rows_per_cta, y1 = min(h, y0 + (uint32_t)rows_per_cta);
+    const size_t in_pitch = (size_t)w * 3, out_pitch = (size_t)out_w * 3;
+    for (uint32_t y = y0; y < y1; y++) {
+        const uint8_t *row = src + (size_t)y * in_pitch;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        if (consecutive) {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(row) + w0;
+            uint32_t q[NS + 1];
+#pragma unroll
+            for (int j = 0; j <= NS; j++)  // word j is needed iff it starts before the last tap byte
+                q[j] = (4u * j < (b0 & 3u) + 3u * K) ? __ldg(rw + j) : 0u;
+            double d[NS][4];
+#pragma unroll
+            for (int j = 0; j < NS; j++) word_to_double4<CONV>(__funnelshift_r(q[j], q[j + 1], sh), d[j]);
+#pragma unroll
+            for (int z = 0; z < K; z++) {  // ref:852-858, tap order
+                s0 = dadd(s0, dmul(d[(3 * z) >> 2][(3 * z) & 3], wk[z]));
+                s1 = dadd(s1, dmul(d[(3 * z + 1) >> 2][(3 * z + 1) & 3], wk[z]));
+                s2 = dadd(s2, dmul(d[(3 * z + 2) >> 2][(3 * z + 2) & 3], wk[z]));
+            }
+        } else {
+#pragma unroll
+            for (int z = 0; z < K; z++) {
+                const uint8_t *p = row + (size_t)ik[z] * 3;
+                s0 = dadd(s0, dmul(u8_to_double(p[0]), wk[z]));
+                s1 = dadd(s1, dmul(u8_to_double(p[1]), wk[z]));
+                s2 = dadd(s2, dmul(u8_to_double(p[2]), wk[z]));
+            }
+        }
+        uint8_t *o = dst + (size_t)y * out_pitch + (size_t)x * 3;
+        o[0] = (uint8_t)quantise_fast(s0);
+        o[1] = (uint8_t)quantise_fast(s1);
+        o[2] = (uint8_t)quantise_fast(s2);
+    }
+}
+
+template <int K>
+static void launch_colsK(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int out_w, const double *wts,
+                         const int *idx, cudaStream_t s)
+{
+    const int rows_per_cta = 16;
+    for (uint32_t y0 = 0; y0 < h; y0 += 65535u * rows_per_cta) {
+        uint32_t rows = min(65535u * rows_per_cta, h - y0);
+        dim3 grid((out_w + 127) / 128, (rows + rows_per_cta - 1) / rows_per_cta);
+        if (g_variant == 2)
+            launch(imresize_colsK_kernel<K, 1>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
+                   dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
+        else
+            launch(imresize_colsK_kernel<K, 0>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
+                   dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
+    }
 }
 
 // height pass: every byte of an output row uses the same K source rows and weights, so the
@@ -1153,6 +1320,20 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
     if (out_size <= 0 || !w || !h) return cudaSuccess;
     if (dim == 0) {
         uint32_t row_bytes = w * 3u;
+        if (row_bytes % 16 == 0 && aligned16(src) && aligned16(dst) && g_variant != 1) {
+            dim3 grid((row_bytes / 16 + 255) / 256, 1);
+            for (int y0 = 0; y0 < out_size; y0 += 65535) {
+                int rows = min(65535, out_size - y0);
+                grid.y = rows;
+                if (g_variant == 2)
+                    launch(imresize_rows16_kernel<1>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
+                           taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+                else
+                    launch(imresize_rows16_kernel<0>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
+                           taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+            }
+            return cudaGetLastError();
+        }
         if (row_bytes % 4 == 0 && aligned4(src) && aligned4(dst)) {
             dim3 grid((row_bytes / 4 + 255) / 256, 1);
             // rows go on grid.y in slabs of <= 65535
@@ -1170,6 +1351,16 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
                 launch(imresize_rows_kernel<1>, dim3(grid), dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes, rows, taps,
                                                              d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
                             }
+        }
+        return cudaGetLastError();
+    }
+    if ((w % 4u) == 0 && aligned4(src) && taps >= 4 && taps <= 8 && g_variant != 1) {
+        switch (taps) {
+        case 4: launch_colsK<4>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
+        case 5: launch_colsK<5>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
+        case 6: launch_colsK<6>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
+        case 7: launch_colsK<7>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
+        default: launch_colsK<8>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
         }
         return cudaGetLastError();
     }
