@@ -976,20 +976,29 @@ __device__ __forceinline__ double u8_to_double(uint32_t v)
     return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
 }
 
-// four u8 -> double conversions from one word.  CONV 0: I2F.F64.U8 with byte selectors (ptxas
-// emits them for uchar4 members; XU pipe).  CONV 1: the exact 2^52 trick (one DADD each; FP64 pipe).
+// four u8 -> double conversions from one word.
+//   CONV 0: I2F.F64.U8 with a byte selector (cvt.rn.f64.u8 of the shifted word folds into it);
+//           XU pipe, measured 15.2 conversions/clk/SM (tools/dp_peak).
+//   CONV 1: the exact 2^52 trick: PRMT + one DADD on the FP64 pipe (64 inst/clk/SM).
+//   CONV 2: bytes 0 and 2 on the XU pipe, bytes 1 and 3 on the FP64 pipe, so neither pipe alone
+//           limits the K-tap loops (XU 16/clk vs FP64 64/clk at 2-3 DP instructions per tap byte).
+__device__ __forceinline__ double cvt_byte_xu(uint32_t shifted)
+{
+    double d;
+    asm("cvt.rn.f64.u8 %0, %1;" : "=d"(d) : "r"(shifted));
+    return d;
+}
+__device__ __forceinline__ double cvt_byte_dp(uint32_t w, int i)
+{
+    return __hiloint2double(0x43300000, (int)__byte_perm(w, 0, 0x4440 | i)) - 4503599627370496.0;
+}
 template <int CONV>
 __device__ __forceinline__ void word_to_double4(uint32_t w, double (&d)[4])
 {
-    if (CONV == 0) {
-        const uchar4 b = *reinterpret_cast<const uchar4 *>(&w);
-        d[0] = (double)b.x;
-        d[1] = (double)b.y;
-        d[2] = (double)b.z;
-        d[3] = (double)b.w;
-    } else {
 #pragma unroll
-        for (int i = 0; i < 4; i++) d[i] = u8_to_double((w >> (8 * i)) & 0xFFu);
+    for (int i = 0; i < 4; i++) {
+        const bool xu = (CONV == 0) || (CONV == 2 && (i & 1) == 0);
+        d[i] = xu ? cvt_byte_xu(w >> (8 * i)) : cvt_byte_dp(w, i);
     }
 }
 
@@ -1110,8 +1119,10 @@ cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_
     if ((w % 4u) == 0 && aligned4(src) && g_variant != 1) {
         if (g_variant == 2)
             launch(rotate_bicubic_kernel<true, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
-        else
+        else if (g_variant == 3)
             launch(rotate_bicubic_kernel<true, 0>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+        else
+            launch(rotate_bicubic_kernel<true, 2>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
     } else {
         launch(rotate_bicubic_kernel<false, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
     }
@@ -1139,32 +1150,48 @@ __device__ __forceinline__ uint32_t quantise_fast(double s)
     return (uint32_t)min(max(n, 0), 255);
 }
 
-// height pass, fast path (row pitch % 16 == 0, aligned): one thread = 16 bytes of an output row
+// height pass, fast path (row pitch % 16 == 0, aligned, K <= 64): one thread = 16 bytes of an
+// output row.  The row's K weights and source-row numbers are staged once per CTA in shared memory
+// so the K source loads of a thread are independent of each other and fly four at a time.
+constexpr int ROWS16_MAXK = 64;
 template <int CONV>
 __global__ void __launch_bounds__(256) imresize_rows16_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                               uint32_t row_vecs, int taps,
                                                               const double *__restrict__ wts, const int *__restrict__ idx)
 {
     PDL_PROLOGUE();
-    const uint32_t xv = blockIdx.x * 256 + threadIdx.x;
+    __shared__ double s_w[ROWS16_MAXK];
+    __shared__ int s_i[ROWS16_MAXK];
     const int y = blockIdx.y;
+    if ((int)threadIdx.x < taps) {
+        s_w[threadIdx.x] = __ldg(wts + (size_t)y * taps + threadIdx.x);
+        s_i[threadIdx.x] = __ldg(idx + (size_t)y * taps + threadIdx.x);
+    }
+    __syncthreads();
+    const uint32_t xv = blockIdx.x * 256 + threadIdx.x;
     if (xv >= row_vecs) return;
-    const double *wy = wts + (size_t)y * taps;
-    const int *iy = idx + (size_t)y * taps;
     const size_t row_bytes = (size_t)row_vecs * 16;
+    const uint4 *col = reinterpret_cast<const uint4 *>(src) + xv;
     double acc[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) acc[i] = 0.0;
-    for (int z = 0; z < taps; z++) {  // tap order is the reference's summation order (ref:826-830)
-        const double wz = __ldg(wy + z);
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)__ldg(iy + z) * row_bytes) + xv);
-        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+    for (int z0 = 0; z0 < taps; z0 += 4) {
+        uint4 v[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            double d[4];
-            word_to_double4<CONV>(wd[q], d);
+        for (int u = 0; u < 4; u++)
+            if (z0 + u < taps) v[u] = __ldg(col + (size_t)s_i[z0 + u] * row_vecs);
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[4 * q + b] = dadd(acc[4 * q + b], dmul(d[b], wz));
+        for (int u = 0; u < 4; u++) {  // tap order is the reference's summation order (ref:826-830)
+            if (z0 + u >= taps) break;
+            const double wz = s_w[z0 + u];
+            const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double d[4];
+                word_to_double4<CONV>(wd[q], d);
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[4 * q + b] = dadd(acc[4 * q + b], dmul(d[b], wz));
+            }
         }
     }
     uint32_t o[4];
@@ -1201,25 +1228,39 @@ __global__ void __launch_bounds__(128) imresize_colsK_kernel(const uint8_t *__re
     const uint32_t b0 = 3u * (uint32_t)ik[0], w0 = b0 >> 2, sh = (b0 & 3u) * 8u;
     const uint32_t y0 = blockIdx.y * (uint32_t)rows_per_cta, y1 = min(h, y0 + (uint32_t)rows_per_cta);
     const size_t in_pitch = (size_t)w * 3, out_pitch = (size_t)out_w * 3;
-    for (uint32_t y = y0; y < y1; y++) {
-        const uint8_t *row = src + (size_t)y * in_pitch;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        if (consecutive) {
-            const uint32_t *rw = reinterpret_cast<const uint32_t *>(row) + w0;
-            uint32_t q[NS + 1];
+    if (consecutive) {
+        // the words of row y+1 are requested before row y is evaluated
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(src + (size_t)y0 * in_pitch) + w0;
+        const size_t pitch_words = in_pitch / 4;
+        uint32_t q[NS + 1], qn[NS + 1];
 #pragma unroll
-            for (int j = 0; j <= NS; j++)  // word j is needed iff it starts before the last tap byte
-                q[j] = (4u * j < (b0 & 3u) + 3u * K) ? __ldg(rw + j) : 0u;
+        for (int j = 0; j <= NS; j++)  // word j is needed iff it starts before the last tap byte
+            q[j] = (y0 < y1 && 4u * j < (b0 & 3u) + 3u * K) ? __ldg(rw + j) : 0u;
+        for (uint32_t y = y0; y < y1; y++) {
+            rw += pitch_words;
+#pragma unroll
+            for (int j = 0; j <= NS; j++) qn[j] = (y + 1 < y1 && 4u * j < (b0 & 3u) + 3u * K) ? __ldg(rw + j) : 0u;
             double d[NS][4];
 #pragma unroll
             for (int j = 0; j < NS; j++) word_to_double4<CONV>(__funnelshift_r(q[j], q[j + 1], sh), d[j]);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int z = 0; z < K; z++) {  // ref:852-858, tap order
                 s0 = dadd(s0, dmul(d[(3 * z) >> 2][(3 * z) & 3], wk[z]));
                 s1 = dadd(s1, dmul(d[(3 * z + 1) >> 2][(3 * z + 1) & 3], wk[z]));
                 s2 = dadd(s2, dmul(d[(3 * z + 2) >> 2][(3 * z + 2) & 3], wk[z]));
             }
-        } else {
+            uint8_t *o = dst + (size_t)y * out_pitch + (size_t)x * 3;
+            o[0] = (uint8_t)quantise_fast(s0);
+            o[1] = (uint8_t)quantise_fast(s1);
+            o[2] = (uint8_t)quantise_fast(s2);
+#pragma unroll
+            for (int j = 0; j <= NS; j++) q[j] = qn[j];
+        }
+    } else {
+        for (uint32_t y = y0; y < y1; y++) {
+            const uint8_t *row = src + (size_t)y * in_pitch;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int z = 0; z < K; z++) {
                 const uint8_t *p = row + (size_t)ik[z] * 3;
@@ -1227,11 +1268,11 @@ __global__ void __launch_bounds__(128) imresize_colsK_kernel(const uint8_t *__re
                 s1 = dadd(s1, dmul(u8_to_double(p[1]), wk[z]));
                 s2 = dadd(s2, dmul(u8_to_double(p[2]), wk[z]));
             }
+            uint8_t *o = dst + (size_t)y * out_pitch + (size_t)x * 3;
+            o[0] = (uint8_t)quantise_fast(s0);
+            o[1] = (uint8_t)quantise_fast(s1);
+            o[2] = (uint8_t)quantise_fast(s2);
         }
-        uint8_t *o = dst + (size_t)y * out_pitch + (size_t)x * 3;
-        o[0] = (uint8_t)quantise_fast(s0);
-        o[1] = (uint8_t)quantise_fast(s1);
-        o[2] = (uint8_t)quantise_fast(s2);
     }
 }
 
@@ -1246,8 +1287,11 @@ static void launch_colsK(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t 
         if (g_variant == 2)
             launch(imresize_colsK_kernel<K, 1>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
                    dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
-        else
+        else if (g_variant == 3)
             launch(imresize_colsK_kernel<K, 0>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
+                   dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
+        else
+            launch(imresize_colsK_kernel<K, 2>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
                    dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
     }
 }
@@ -1320,7 +1364,7 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
     if (out_size <= 0 || !w || !h) return cudaSuccess;
     if (dim == 0) {
         uint32_t row_bytes = w * 3u;
-        if (row_bytes % 16 == 0 && aligned16(src) && aligned16(dst) && g_variant != 1) {
+        if (row_bytes % 16 == 0 && aligned16(src) && aligned16(dst) && taps <= ROWS16_MAXK && g_variant != 1) {
             dim3 grid((row_bytes / 16 + 255) / 256, 1);
             for (int y0 = 0; y0 < out_size; y0 += 65535) {
                 int rows = min(65535, out_size - y0);
@@ -1328,8 +1372,11 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
                 if (g_variant == 2)
                     launch(imresize_rows16_kernel<1>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
                            taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
-                else
+                else if (g_variant == 3)
                     launch(imresize_rows16_kernel<0>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
+                           taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+                else
+                    launch(imresize_rows16_kernel<2>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
                            taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
             }
             return cudaGetLastError();
