@@ -203,7 +203,7 @@ class Runner:
             k.close()
 
 
-def time_steps(torch, runner, steps, warmup, dist=None, after_step=None, clk=None):
+def time_steps(torch, runner, steps, warmup, dist=None, after_step=None, clk=None, before_end=None):
     stream = torch.cuda.current_stream().cuda_stream
     for _ in range(warmup):
         runner.step(stream)
@@ -221,6 +221,8 @@ def time_steps(torch, runner, steps, warmup, dist=None, after_step=None, clk=Non
         runner.step(stream)
         if after_step:
             after_step()
+    if before_end:
+        before_end()  # e.g. make the stream wait for collectives still in flight: they belong to the region
     e1.record()
     torch.cuda.synchronize()
     if clk is not None:
@@ -440,12 +442,31 @@ def run_ours(args):
 
     after = None
     if name == "gray_hist" and dist is not None:
-        def after():  # the one real exchange of this path: sum the 256 bins over ranks (NCCL)
-            dist.all_reduce(runner.hist, op=dist.ReduceOp.SUM)
+        # the one real exchange of this path: sum the 256 bins over ranks (NCCL).  Two bin buffers
+        # alternate, so the all-reduce of step i runs beside the kernels of step i+1.
+        bins = [runner.hist, torch.zeros_like(runner.hist)]
+        pending = [None, None]
+        state = {"i": 0}
+
+        def after():
+            i = state["i"]
+            pending[i & 1] = dist.all_reduce(bins[i & 1], op=dist.ReduceOp.SUM, async_op=True)
+            state["i"] = i + 1
+            nxt = (i + 1) & 1
+            if pending[nxt] is not None:
+                pending[nxt].wait()  # stream-level: the buffer about to be reused has been reduced
+                pending[nxt] = None
+            runner.hist = bins[nxt]
+
+        def drain():
+            for k in range(2):
+                if pending[k] is not None:
+                    pending[k].wait()
+                    pending[k] = None
 
     n0 = g.launch_count()
     with ClockSampler(local) as clk:
-        ms = time_steps(torch, runner, args.steps, args.warmup, dist, after, clk)
+        ms = time_steps(torch, runner, args.steps, args.warmup, dist, after, clk, drain if after else None)
     launches = (g.launch_count() - n0) - args.warmup * runner.launches_per_step
     px = world * args.steps * runner.pixels_per_step
     value = px / (ms / 1e3) / 1e6
