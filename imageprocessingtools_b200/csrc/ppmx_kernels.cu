@@ -352,12 +352,13 @@ __global__ void __launch_bounds__(HL_THREADS, 1) gray_hist_lanes_kernel(const ui
                                                               size_t ngroups, size_t npix,
                                                               unsigned long long *d_hist)
 {
-    PDL_PROLOGUE();
+    pdl_trigger();
     extern __shared__ __align__(16) uint32_t hl_bins[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
     for (uint32_t i = tid; i < 256 * 32 / 4; i += HL_THREADS) reinterpret_cast<uint4 *>(hl_bins)[i] = zero4;
     __syncthreads();
+    pdl_wait();  // everything above is index arithmetic; global memory is touched only below
     uint32_t *col = hl_bins + lane;
     // few, fat CTAs (one per SM): the final 256 global atomics per CTA hit only 16 cache lines, and
     // every CTA adds to all of them, so the number of CTAs is what that last pass costs
@@ -410,8 +411,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) gray_hist_lanes_kernel(const ui
 __global__ void __launch_bounds__(256) gray_flat_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
                                                         size_t ngroups, size_t npix)
 {
-    PDL_PROLOGUE();
+    pdl_trigger();
     const size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
+    pdl_wait();  // everything above is index arithmetic; global memory is touched only below
     if (g < ngroups) {
         const uint4 *p = src + 3 * g;
         const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -592,21 +594,42 @@ __global__ void __launch_bounds__(256) mono_plane_kernel(const uint8_t *__restri
 
 // w % 16 == 0 and 16-byte aligned rasters: one thread = 16 pixels of one row (48 B in) = two
 // output bytes; one CTA per 256 such groups, no loop (same access pattern as gray)
+// grey < thr  <=>  (r+g+b)/3 < thr  <=>  r+g+b < 3*thr (integers), so neither the division nor the
+// grey byte is needed: each dp4a starts from -3*thr and the pixel's bit is the SIGN of the sum, which
+// one funnel shift appends to the output (pixel 0 ends up in the most significant bit, ref:273).
+__device__ __forceinline__ uint32_t mono_bits4(uint32_t bits, uint32_t a, uint32_t b, uint32_t c, const int (&t)[4])
+{
+    const int s0 = (int)__dp4a(a, 0x00010101u, (uint32_t)t[0]);
+    const int s1 = (int)__dp4a(a, 0x01000000u, __dp4a(b, 0x00000101u, (uint32_t)t[1]));
+    const int s2 = (int)__dp4a(b, 0x01010000u, __dp4a(c, 0x00000001u, (uint32_t)t[2]));
+    const int s3 = (int)__dp4a(c, 0x01010100u, (uint32_t)t[3]);
+    bits = __funnelshift_l((uint32_t)s0, bits, 1);
+    bits = __funnelshift_l((uint32_t)s1, bits, 1);
+    bits = __funnelshift_l((uint32_t)s2, bits, 1);
+    bits = __funnelshift_l((uint32_t)s3, bits, 1);
+    return bits;
+}
+
 __global__ void __launch_bounds__(256) mono_bits_vec_kernel(const uint4 *__restrict__ src, uint16_t *__restrict__ dst,
                                                             uint32_t groups_per_row, size_t ngroups, uint32_t y0)
 {
-    PDL_PROLOGUE();
+    pdl_trigger();
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= ngroups) return;
     const uint32_t y = (ngroups <= 0xFFFFFFFFull ? (uint32_t)i / groups_per_row : (uint32_t)(i / groups_per_row)) + y0;
-    const uint32_t t4 = bayer_row4(y);
+    const uint32_t yy = y & 3u;
+    const int t[4] = {-3 * (int)c_bayer[yy], -3 * (int)c_bayer[4 + yy], -3 * (int)c_bayer[8 + yy],
+                      -3 * (int)c_bayer[12 + yy]};  // x % 4 = 0..3 on this row (a group starts at x % 16 == 0)
+    pdl_wait();  // everything above is index arithmetic; global memory is touched only below
     const uint4 *p = src + 3 * i;
     const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    const uint32_t n0 = mono_nibble(gray4(a.x, a.y, a.z), t4);
-    const uint32_t n1 = mono_nibble(gray4(a.w, b.x, b.y), t4);
-    const uint32_t n2 = mono_nibble(gray4(b.z, b.w, c.x), t4);
-    const uint32_t n3 = mono_nibble(gray4(c.y, c.z, c.w), t4);
-    dst[i] = (uint16_t)(((n0 << 4) | n1) | (((n2 << 4) | n3) << 8));  // little endian: pixels 0-7 first
+    uint32_t bits = 0;
+    bits = mono_bits4(bits, a.x, a.y, a.z, t);
+    bits = mono_bits4(bits, a.w, b.x, b.y, t);
+    bits = mono_bits4(bits, b.z, b.w, c.x, t);
+    bits = mono_bits4(bits, c.y, c.z, c.w, t);
+    // pixels 0-7 sit in bits 15..8: they are the FIRST byte in memory
+    dst[i] = (uint16_t)__byte_perm(bits, 0, 0x4401);
 }
 
 // any width / alignment: one thread = one output byte (up to 8 pixels of one row)
@@ -701,7 +724,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) flipv_kernel(const T *__restrict__ src, T *__restrict__ dst,
                                                     uint32_t row_elems, uint32_t h, size_t n)
 {
-    PDL_PROLOGUE();
+    pdl_trigger();
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     uint32_t y, e;
@@ -712,6 +735,7 @@ __global__ void __launch_bounds__(256) flipv_kernel(const T *__restrict__ src, T
         y = (uint32_t)(i / row_elems);
         e = (uint32_t)(i - (size_t)y * row_elems);
     }
+    pdl_wait();  // everything above is index arithmetic; global memory is touched only below
     dst[i] = src[(size_t)(h - 1 - y) * row_elems + e];
 }
 
@@ -750,7 +774,7 @@ __device__ __forceinline__ void reverse16px(const uint32_t (&in)[12], uint32_t (
 __global__ void __launch_bounds__(256) fliph_rgb16_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
                                                           uint32_t groups_per_row, size_t ngroups)
 {
-    PDL_PROLOGUE();
+    pdl_trigger();
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= ngroups) return;
     size_t y;
@@ -762,6 +786,7 @@ __global__ void __launch_bounds__(256) fliph_rgb16_kernel(const uint4 *__restric
         y = i / groups_per_row;
         g = (uint32_t)(i - y * groups_per_row);
     }
+    pdl_wait();  // everything above is index arithmetic; global memory is touched only below
     const uint4 *p = src + 3 * (y * groups_per_row + (groups_per_row - 1 - g));
     const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     const uint32_t in[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
@@ -874,10 +899,11 @@ template <bool CW>
 __global__ void __launch_bounds__(256) rotate_transpose64_kernel(const uint8_t *__restrict__ src,
                                                                  uint8_t *__restrict__ dst, uint32_t w, uint32_t h)
 {
-    PDL_PROLOGUE();
+    pdl_trigger();
     __shared__ __align__(16) uint32_t tile[XT * 64];
     const uint32_t tx0 = blockIdx.x * XT, ty0 = blockIdx.y * XT;
     const size_t in_pitch = (size_t)w * 3, out_pitch = (size_t)h * 3;
+    pdl_wait();  // everything above is index arithmetic; global memory is touched only below
     {
         const uint32_t row = threadIdx.x >> 2, q = threadIdx.x & 3u;
         const uint32_t y = ty0 + row, x0 = tx0 + 16u * q;
@@ -947,6 +973,8 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
     }
     if (angle != 90 && angle != 270) return cudaErrorInvalidValue;
     if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && g_variant != 1) {
+        // (numbering the CTAs down bands of 2..16 tile rows, for DRAM page locality on the write side,
+        // measured 1-5 % SLOWER than this plain 2-D grid: the index arithmetic costs more than it gains)
         dim3 g64((w + XT - 1) / XT, (h + XT - 1) / XT);
         if (g64.y > 65535u) return cudaErrorInvalidValue;
         if (angle == 90) launch(rotate_transpose64_kernel<true>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
