@@ -895,22 +895,45 @@ __device__ __forceinline__ uint32_t xt_slot(uint32_t row, uint32_t chunk)
     return row * 64u + ((chunk ^ (((chunk >> 3) & 1u) << 1) ^ (row & 1u) ^ (((row >> 4) & 3u) << 1)) << 2);
 }
 
+// XT_NT horizontally adjacent tiles per CTA (vertical pairs, i.e. longer contiguous WRITES, measured
+// 8 % slower: long contiguous reads matter more): the loads of ALL of them are issued up front, so
+// the second tile's DRAM latency hides behind the first tile's shared-memory phase and stores.
+constexpr int XT_NT = 2;  // 1 and 2 measure the same (73.7 % of the HBM roofline), 4 loses 6 %
+
 template <bool CW>
 __global__ void __launch_bounds__(256) rotate_transpose64_kernel(const uint8_t *__restrict__ src,
                                                                  uint8_t *__restrict__ dst, uint32_t w, uint32_t h)
 {
     pdl_trigger();
     __shared__ __align__(16) uint32_t tile[XT * 64];
-    const uint32_t tx0 = blockIdx.x * XT, ty0 = blockIdx.y * XT;
+    const uint32_t ty0 = blockIdx.y * XT;
     const size_t in_pitch = (size_t)w * 3, out_pitch = (size_t)h * 3;
+    const uint32_t row = threadIdx.x >> 2, q = threadIdx.x & 3u;               // phase 1 role
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t col = 8u * warp + (lane >> 2), j = lane & 3u;              // phase 2 role
     pdl_wait();  // everything above is index arithmetic; global memory is touched only below
-    {
-        const uint32_t row = threadIdx.x >> 2, q = threadIdx.x & 3u;
-        const uint32_t y = ty0 + row, x0 = tx0 + 16u * q;
-        if (y < h && x0 < w) {
+
+    uint4 ld[XT_NT][3];
+    bool have[XT_NT];
+#pragma unroll
+    for (int t = 0; t < XT_NT; t++) {
+        const uint32_t y = ty0 + row, x0 = (blockIdx.x * XT_NT + t) * XT + 16u * q;
+        have[t] = (y < h && x0 < w);
+        if (have[t]) {
             const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)y * in_pitch + (size_t)x0 * 3);
-            const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-            const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+            ld[t][0] = __ldg(p);
+            ld[t][1] = __ldg(p + 1);
+            ld[t][2] = __ldg(p + 2);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < XT_NT; t++) {
+        const uint32_t tx0 = (blockIdx.x * XT_NT + t) * XT;
+        if (tx0 >= w) break;
+        if (t > 0) __syncthreads();  // the previous tile has been read out of shared memory
+        if (have[t]) {
+            const uint32_t wd[12] = {ld[t][0].x, ld[t][0].y, ld[t][0].z, ld[t][0].w, ld[t][1].x, ld[t][1].y,
+                                     ld[t][1].z, ld[t][1].w, ld[t][2].x, ld[t][2].y, ld[t][2].z, ld[t][2].w};
 #pragma unroll
             for (int i = 0; i < 4; i++) {  // 4 pixels = 3 words -> 4 words (byte 3 of each is don't-care)
                 uint4 o;
@@ -921,13 +944,9 @@ __global__ void __launch_bounds__(256) rotate_transpose64_kernel(const uint8_t *
                 *reinterpret_cast<uint4 *>(&tile[xt_slot(row, 4u * q + i)]) = o;
             }
         }
-    }
-    __syncthreads();
-    {
+        __syncthreads();
         // four neighbouring lanes take the four 16-row units of one source column, so together they
         // write one contiguous 192-byte piece of a destination row
-        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-        const uint32_t col = 8u * warp + (lane >> 2), j = lane & 3u;  // source column, 16-row unit
         const uint32_t x = tx0 + col, y0 = ty0 + 16u * j;
         if (x < w && y0 < h) {
             uint32_t px[16];
@@ -948,10 +967,10 @@ __global__ void __launch_bounds__(256) rotate_transpose64_kernel(const uint8_t *
             size_t off;
             if (CW) off = (size_t)x * out_pitch + (size_t)(h - y0 - 16u) * 3;        // out[x][h-1-y], ref:717
             else off = (size_t)(w - 1u - x) * out_pitch + (size_t)y0 * 3;             // out[w-1-x][y], ref:725
-            uint4 *q = reinterpret_cast<uint4 *>(dst + off);
-            q[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            q[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            q[2] = make_uint4(o[8], o[9], o[10], o[11]);
+            uint4 *qo = reinterpret_cast<uint4 *>(dst + off);
+            qo[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            qo[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            qo[2] = make_uint4(o[8], o[9], o[10], o[11]);
         }
     }
 }
@@ -975,7 +994,7 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
     if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && g_variant != 1) {
         // (numbering the CTAs down bands of 2..16 tile rows, for DRAM page locality on the write side,
         // measured 1-5 % SLOWER than this plain 2-D grid: the index arithmetic costs more than it gains)
-        dim3 g64((w + XT - 1) / XT, (h + XT - 1) / XT);
+        dim3 g64((w + XT * XT_NT - 1) / (XT * XT_NT), (h + XT - 1) / XT);
         if (g64.y > 65535u) return cudaErrorInvalidValue;
         if (angle == 90) launch(rotate_transpose64_kernel<true>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
         else launch(rotate_transpose64_kernel<false>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
@@ -1489,12 +1508,20 @@ struct ConvRound {
     uint32_t M, shift;  // shift = l - 1, applied to the high word of n * M
     int32_t add, K, bias;  // n = 2*acc + add, add = div + d*K
     int32_t pow2;          // d is a power of two: a plain shift by l replaces the multiply-high
-    __device__ __forceinline__ uint32_t operator()(int32_t acc) const
+    __device__ __forceinline__ int32_t quotient(int32_t acc) const  // before the 0..255 clamp
     {
         uint32_t n = (uint32_t)(2 * acc + add);
         uint32_t qn = pow2 ? (n >> (shift + 1)) : (__umulhi(n, M) >> shift);
-        int32_t q = (int32_t)qn - K + bias;
-        return (uint32_t)min(max(q, 0), 255);
+        return (int32_t)qn - K + bias;
+    }
+    __device__ __forceinline__ uint32_t operator()(int32_t acc) const { return (uint32_t)min(max(quotient(acc), 0), 255); }
+    // four results clamped to 0..255 and packed, result 0 in the low byte: two I2IP instructions
+    __device__ __forceinline__ uint32_t pack4(int32_t a0, int32_t a1, int32_t a2, int32_t a3) const
+    {
+        uint32_t hi, out;
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(quotient(a3)), "r"(quotient(a2)), "r"(0));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(quotient(a1)), "r"(quotient(a0)), "r"(hi));
+        return out;
     }
 };
 
@@ -1666,7 +1693,7 @@ __global__ void __launch_bounds__(256) conv_dp4a_kernel(RowSource rs, uint8_t *_
         }
 #pragma unroll
         for (int a = 0; a < FC_RV; a++)
-            outw[a][ch] = rnd(acc[a][0]) | (rnd(acc[a][1]) << 8) | (rnd(acc[a][2]) << 16) | (rnd(acc[a][3]) << 24);
+            outw[a][ch] = rnd.pack4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
     }
 #pragma unroll
     for (int a = 0; a < FC_RV; a++) {
