@@ -63,6 +63,14 @@ def traffic_for(name):
         return None
 
 
+def dp_peak():
+    """Measured non-fused FP64 instruction rate (tools/dp_peak.cu), the roofline of the bicubic operators."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "dp_peak.json")))["dmul_dadd_inst_per_s"])
+    except Exception:
+        return 1.84e13
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -515,6 +523,15 @@ def run_ours(args):
                 ent.update({"gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
             else:
                 ent["out_mpix_s"] = round(3 * r.batch * r.out_w * r.out_h / (t / 1e3) / 1e6, 1)
+                # algorithmic FP64 instructions: imresize 6*K per output pixel per pass;
+                # bicubic rotate ~190 per output pixel that maps inside the source (~ w*h of them)
+                if op_name.startswith("resize"):
+                    dp = sum(6.0 * o[0].weights_sz * o[1] * o[2] for o in r.ops)
+                else:
+                    dp = 190.0 * ow * oh
+                rate = 3 * r.batch * dp / (t / 1e3)
+                ent.update({"bound": "fp64 issue", "dp_inst_per_s": float("%.4g" % rate),
+                            "frac_of_dp_peak": round(rate / dp_peak(), 4)})
             per[op_name] = ent
             r.close()
             del r

@@ -303,3 +303,47 @@ def test_extension_histogram(gpu, orc):
             g, bins = gpu.gray_hist(img)
             assert np.array_equal(bins, exp) and np.array_equal(g, orc.gray(img)), (w, h, pname)
             assert int(bins.sum()) == w * h
+
+
+def test_no_out_of_bounds_writes(gpu, orc):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds WRITES are checked by hand: every
+    operator writes into the middle of a canary-filled device buffer (raw launch on caller-owned memory)
+    and the canaries on both sides must survive.  Outputs are compared with the oracle as well."""
+    import torch
+    import imageprocessingtools_b200.ppmx as pp
+    dev = torch.device("cuda", 0)
+    PAD = 4096
+
+    def run(op, img, out_bytes, layout=pp.LAYOUT_RGB8, tables=0):
+        h, w = img.shape[0], img.shape[1]
+        src = torch.from_numpy(np.ascontiguousarray(img)).to(dev)
+        buf = torch.full((PAD + out_bytes + PAD,), 0xA5, dtype=torch.uint8, device=dev)
+        gpu.launch(op, src.data_ptr(), w, h, layout, buf.data_ptr() + PAD, None, 0, tables)
+        torch.cuda.synchronize()
+        host = buf.cpu().numpy()
+        assert (host[:PAD] == 0xA5).all() and (host[PAD + out_bytes:] == 0xA5).all(), "canary overwritten"
+        return host[PAD:PAD + out_bytes]
+
+    for (w, h) in [(1, 1), (5, 3), (17, 9), (33, 7), (48, 16), (64, 64), (100, 37), (128, 80), (256, 16)]:
+        img = P.lcg(w, h, 9)
+        assert np.array_equal(run(pp.PpmxOp(kind=pp.OP_GRAY), img, w * h), orc.gray(img).reshape(-1))
+        assert np.array_equal(run(pp.PpmxOp(kind=pp.OP_MONO_BITS), img, ((w + 7) // 8) * h), orc.pack_pbm(orc.mono(img)))
+        assert np.array_equal(run(pp.PpmxOp(kind=pp.OP_MONO), img, w * h), orc.mono(img).reshape(-1))
+        for d in (0, 1):
+            assert np.array_equal(run(pp.PpmxOp(kind=pp.OP_FLIP, flip_direction=d), img, w * h * 3),
+                                  orc.flip(img, d).reshape(-1))
+        for a in (90, 180, 270, 31):
+            op = gpu.rotate_op(a, w, h)
+            exp = orc.rotate(img, a)
+            assert np.array_equal(run(op, img, exp.size), exp.reshape(-1)), (w, h, a)
+        for new in (max(1, w // 2), w + 3):
+            for dim, n_in in ((1, w), (0, h)):
+                wt, ix = gpu.calc_contributions(n_in, new, float(new) / n_in)
+                op = gpu.imresize_op(new, dim, wt, ix)
+                t = gpu.tables_upload(op)
+                exp = orc.imresize(img, new, dim, wt, ix)
+                assert np.array_equal(run(op, img, exp.size, tables=t), exp.reshape(-1)), (w, h, new, dim)
+                gpu.tables_free(t)
+        for k in (3, 7):
+            coef = np.ones((k, k), np.int64)
+            assert np.array_equal(run(gpu.conv_op(coef, k * k, 0), img, w * h * 3), orc.conv(img, coef, k * k, 0).reshape(-1))
