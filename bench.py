@@ -42,6 +42,10 @@ WORKLOADS = {
     "flipv": (4096, 4096, 8, 6.0, "4096x4096 vertical flip, 8 rasters per step"),
     "rot90": (4096, 4096, 8, 6.0, "4096x4096 rotate 90, 8 rasters per step"),
     "rot180": (4096, 4096, 8, 6.0, "4096x4096 rotate 180, 8 rasters per step"),
+    "gray_16k": (16384, 16384, 2, 4.0, "16384x16384 RGB->greyscale, two rasters (805 MB each) per step"),
+    "mono_16k": (16384, 16384, 2, 3.125, "16384x16384 -> Bayer bilevel P4 bits, two rasters per step"),
+    "fliph_16k": (16384, 16384, 2, 6.0, "16384x16384 horizontal flip, two rasters per step"),
+    "rot90_16k": (16384, 16384, 2, 6.0, "16384x16384 rotate 90, two rasters per step"),
     "conv3": (8192, 8192, 2, 6.0, "8192x8192 3x3 blur (extension, config 3), 2 rasters per step"),
     "conv7": (8192, 8192, 2, 6.0, "8192x8192 7x7 box (extension, config 3), 2 rasters per step"),
     "resize_up": (4096, 4096, 2, None, "4096x4096 -w6144 bicubic resize (FP64), 2 rasters per step"),
@@ -49,8 +53,8 @@ WORKLOADS = {
     "rot30": (4096, 4096, 2, None, "4096x4096 -r30 bicubic rotate (FP64), 2 rasters per step"),
 }
 DEFAULT_WORKLOAD = "gray_hist"
-PER_OP = ["gray", "gray_hist", "mono", "fliph", "flipv", "rot90", "rot180", "conv3", "conv7", "resize_up",
-          "resize_down", "rot30"]
+PER_OP = ["gray", "gray_hist", "mono", "fliph", "flipv", "rot90", "rot180", "gray_16k", "mono_16k", "fliph_16k",
+          "rot90_16k", "conv3", "conv7", "resize_up", "resize_down", "rot30"]
 
 
 def traffic_for(name):
@@ -157,6 +161,9 @@ class Runner:
         self.ops = []  # (op, out_w, out_h, out_bytes_per_raster, src_layout)
         self.keep = []
         L = pp
+        base = name.split("_16k")[0]
+        if name.endswith("_16k"):
+            name = base
         if name in ("gray", "gray_hist"):
             kind = L.OP_GRAY if name == "gray" else L.OP_GRAY_HIST
             self.ops = [(L.PpmxOp(kind=kind), w, h, w * h)]
@@ -428,6 +435,48 @@ def band_split_run(torch, g, dist, rank, world, device, k=3, full=16384, iters=1
             "gbs_total": round(6.0 * mp / 1e3, 1), "rows_per_gpu": rows, "halo_rows": r}
 
 
+def batch_chain_run(torch, g, dist, world, images=128):
+    """BASELINE config 5: a batch of 1920x1080 PPM rasters through full op chains, image-parallel (every rank
+    takes `images` rasters), end to end through ppmx_gpu_apply_batch with pinned host buffers."""
+    import ctypes as C
+    from imageprocessingtools_b200 import ppmx as pp
+    w, h = 1920, 1080
+    src = torch.randint(0, 256, (images, h, w, 3), dtype=torch.uint8).pin_memory()
+    out = []
+    for label, kw in (("-w960 -r90 -gray -fv", dict(resize_w=960, angle=90, gray=True, flipv=True)),
+                      ("-r90 -mono -fh", dict(angle=90, mono=True, fliph=True))):
+        ph = pp._PlanHolder(w=w, h=h, **kw)
+        cap = w * h * 3 + 64
+        dst = torch.empty((images, cap), dtype=torch.uint8).pin_memory()
+        each, ow, oh, ft = C.c_size_t(), C.c_uint32(), C.c_uint32(), C.c_int()
+
+        def one():
+            rc = g.L.ppmx_gpu_apply_batch(g.ctx, ph.plan.ops, ph.plan.nops, C.c_void_p(src.data_ptr()), w, h, images,
+                                          C.c_void_p(dst.data_ptr()), cap, C.byref(each), C.byref(ow), C.byref(oh),
+                                          C.byref(ft))
+            if rc != 0:
+                raise SystemExit("ppmx_gpu_apply_batch failed")
+
+        one()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        one()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        out.append({"chain": label, "images": images * world, "frame": "%dx%d" % (w, h),
+                    "out": "%dx%d type %d" % (ow.value, oh.value, ft.value),
+                    "e2e_mpix_s": round(world * images * w * h / dt / 1e6, 1),
+                    "images_per_s": round(world * images / dt, 1)})
+        ph.close()
+        del dst
+    return out
+
+
 def run_ours(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -546,6 +595,7 @@ def run_ours(args):
     if not args.no_band:
         line["band_split"] = [band_split_run(torch, g, dist, rank, world, device, k=3),
                               band_split_run(torch, g, dist, rank, world, device, k=7)]
+        line["batch_chain"] = batch_chain_run(torch, g, dist, world)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
