@@ -347,3 +347,41 @@ def test_no_out_of_bounds_writes(gpu, orc):
         for k in (3, 7):
             coef = np.ones((k, k), np.int64)
             assert np.array_equal(run(gpu.conv_op(coef, k * k, 0), img, w * h * 3), orc.conv(img, coef, k * k, 0).reshape(-1))
+
+
+def test_full_size_bicubic_4096(gpu, orc):
+    """The reference's real stencil work at BASELINE size: -w6144 / -w2048 and -r30 on a 4096x4096 raster,
+    compared directly (the oracle needs a few seconds each), plus a flat image for the truncation speckle."""
+    img = P.lcg(4096, 4096, 0xC0FFEE ^ 3)
+    for new_w in (6144, 2048):
+        exp = orc.process(img, resize_w=new_w)
+        got = gpu.process(img, resize_w=new_w)
+        assert got[1:] == exp[1:] and np.array_equal(got[0], exp[0]), new_w
+    exp = orc.rotate(img, 30)
+    assert np.array_equal(gpu.rotate(img, 30), exp)
+    flat = P.const(2048, 2048, 200)
+    assert np.array_equal(gpu.rotate(flat, 77), orc.rotate(flat, 77))
+
+
+def test_tuning_variants_are_bit_identical(gpu, orc):
+    """Every alternative kernel kept for benchmarking must give the default's bytes."""
+    img = P.lcg(256, 192, 31)
+    wt, ix = gpu.calc_contributions(192, 288, 1.5)
+    wt2, ix2 = gpu.calc_contributions(256, 128, 0.5)
+    coef = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]])
+    try:
+        for v in (0, 1, 2, 3, 4, 5):
+            for pdl in (1, 0):
+                gpu.set_tuning("variant", v)
+                gpu.set_tuning("pdl", pdl)
+                assert np.array_equal(gpu.gray(img), orc.gray(img)), (v, pdl)
+                g, bins = gpu.gray_hist(img)
+                assert np.array_equal(g, orc.gray(img)) and np.array_equal(bins, orc.hist_gray(img)), (v, pdl)
+                assert np.array_equal(gpu.rotate(img, 90), orc.rotate(img, 90)), (v, pdl)
+                assert np.array_equal(gpu.rotate(img, 33), orc.rotate(img, 33)), (v, pdl)
+                assert np.array_equal(gpu.imresize(img, 288, 0, wt, ix), orc.imresize(img, 288, 0, wt, ix)), (v, pdl)
+                assert np.array_equal(gpu.imresize(img, 128, 1, wt2, ix2), orc.imresize(img, 128, 1, wt2, ix2)), (v, pdl)
+                assert np.array_equal(gpu.conv(img, coef, 16, 0), orc.conv(img, coef, 16, 0)), (v, pdl)
+    finally:
+        gpu.set_tuning("variant", 0)
+        gpu.set_tuning("pdl", 1)
