@@ -358,6 +358,91 @@ def cpu_baseline_sample(name, threads, seconds_budget=12.0):
                       "reference function only (its own image_buff_alloc included)" % (sum(count), fn, w, h, threads)}
 
 
+def band_split_ref_ops(torch, g, dist, rank, world, device, full=16384, iters=10):
+    """The same 16384 x 16384 raster cut into row bands for three REFERENCE operators (bit-exact ones):
+    gray and mono need no exchange (mono takes the band's y0 for the Bayer phase); the resize height pass
+    (x1.5, K = 4) reads the few source rows beyond its band from the neighbours' HBM over NVLink."""
+    import numpy as np
+    from imageprocessingtools_b200 import ppmx as pp
+    w = full
+    y0, rows = pp.band_plan(full, world, rank, 4)
+    nbytes = rows * w * 3
+    gen = torch.Generator(device=device)
+    gen.manual_seed(0x5EED ^ rank)
+    srcs, handles = [], []
+    for i in range(2):
+        p = g.device_alloc(nbytes)
+        t = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=device, generator=gen)
+        g.copy(p, t.data_ptr(), nbytes, 2)
+        del t
+        srcs.append(p)
+        handles.append(g.ipc_export(p))
+    new_h = full * 3 // 2
+    wt, ix = pp.calc_contributions(full, new_h, 1.5)
+    oy0, orows = pp.band_plan(new_h, world, rank, 1)
+    need = ix[oy0:oy0 + orows]
+    halo = int(max(0, y0 - need.min(), need.max() - (y0 + rows - 1)))
+    rop = g.imresize_op(new_h, 0, wt, ix)
+    tables = g.tables_upload(rop)
+    dst = g.device_alloc(max(orows * w * 3, nbytes))
+    peers = {}
+    bands = [pp.PpmxBand(full_h=full, y0=y0, halo=halo, out_y0=oy0, out_rows=orows) for _ in range(2)]
+    if world > 1:
+        info = [None] * world
+        dist.all_gather_object(info, (rows, handles))
+        for nb in (rank - 1, rank + 1):
+            if 0 <= nb < world:
+                peers[nb] = [g.ipc_open(hd) for hd in info[nb][1]]
+        for i in range(2):
+            if rank > 0:
+                bands[i].d_top = peers[rank - 1][i] + (info[rank - 1][0] - halo) * w * 3
+            if rank < world - 1:
+                bands[i].d_bottom = peers[rank + 1][i]
+        dist.barrier()
+    stream = torch.cuda.current_stream().cuda_stream
+    plain = pp.PpmxBand(full_h=full, y0=y0)
+    results = []
+    for label, op, bnd, tab, bpp in (("gray", pp.PpmxOp(kind=pp.OP_GRAY), [plain, plain], 0, 4.0),
+                                     ("mono", pp.PpmxOp(kind=pp.OP_MONO_BITS), [plain, plain], 0, 3.125),
+                                     ("imresize height pass x1.5", rop, bands, tables, None)):
+        def step(i):
+            g.launch(op, srcs[i & 1], w, rows, pp.LAYOUT_RGB8, dst, bnd[i & 1], 0, tab, stream)
+        for i in range(4):
+            step(i)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            dist.barrier()
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        mp = iters * full * full / (ms / 1e3) / 1e6
+        ent = {"workload": "%dx%d raster, %s (reference operator), row bands over %d GPU(s)" % (full, full, label, world),
+               "scaling": "strong", "mpix_s": round(mp, 1), "ms_per_raster": round(ms / iters, 4), "rows_per_gpu": rows}
+        if bpp:
+            ent["gbs_total"] = round(bpp * mp / 1e3, 1)
+        else:
+            ent.update({"halo_rows": halo, "out_mpix_s": round(mp * 1.5, 1)})
+        results.append(ent)
+    for lst in peers.values():
+        for p in lst:
+            g.ipc_close(p)
+    if dist is not None:
+        dist.barrier()
+    g.tables_free(tables)
+    for p in srcs + [dst]:
+        g.device_free(p)
+    return results
+
+
 def band_split_run(torch, g, dist, rank, world, device, k=3, full=16384, iters=10):
     """BASELINE config 4: ONE full x full raster cut into row bands (ppmx_band_plan), one band per rank, k x k
     convolution (extension op) with the r = k/2 halo rows read straight from the neighbours' HBM over NVLink
@@ -498,32 +583,18 @@ def run_ours(args):
     runner = Runner(torch, g, name, device, seed=0xC0FFEE ^ (rank + 2))
 
     after = None
+    drain = None
     if name == "gray_hist" and dist is not None:
-        # the one real exchange of this path: sum the 256 bins over ranks (NCCL).  Two bin buffers
-        # alternate, so the all-reduce of step i runs beside the kernels of step i+1.
-        bins = [runner.hist, torch.zeros_like(runner.hist)]
-        pending = [None, None]
-        state = {"i": 0}
-
+        # the one real exchange of this path: sum the 256 bins over ranks (NCCL), in stream order after the
+        # step's kernels.  (Issuing it asynchronously on alternating bin buffers so that it overlaps the
+        # next step measured SLOWER at N=2: 0.495 vs 0.399 ms per step -- the NCCL kernel then competes
+        # with the PDL-chained launches -- so it stays in order.)
         def after():
-            i = state["i"]
-            pending[i & 1] = dist.all_reduce(bins[i & 1], op=dist.ReduceOp.SUM, async_op=True)
-            state["i"] = i + 1
-            nxt = (i + 1) & 1
-            if pending[nxt] is not None:
-                pending[nxt].wait()  # stream-level: the buffer about to be reused has been reduced
-                pending[nxt] = None
-            runner.hist = bins[nxt]
-
-        def drain():
-            for k in range(2):
-                if pending[k] is not None:
-                    pending[k].wait()
-                    pending[k] = None
+            dist.all_reduce(runner.hist, op=dist.ReduceOp.SUM)
 
     n0 = g.launch_count()
     with ClockSampler(local) as clk:
-        ms = time_steps(torch, runner, args.steps, args.warmup, dist, after, clk, drain if after else None)
+        ms = time_steps(torch, runner, args.steps, args.warmup, dist, after, clk, drain)
     launches = (g.launch_count() - n0) - args.warmup * runner.launches_per_step
     px = world * args.steps * runner.pixels_per_step
     value = px / (ms / 1e3) / 1e6
@@ -593,8 +664,9 @@ def run_ours(args):
     del runner
     torch.cuda.empty_cache()
     if not args.no_band:
-        line["band_split"] = [band_split_run(torch, g, dist, rank, world, device, k=3),
-                              band_split_run(torch, g, dist, rank, world, device, k=7)]
+        line["band_split"] = band_split_ref_ops(torch, g, dist, rank, world, device) + [
+            band_split_run(torch, g, dist, rank, world, device, k=3),
+            band_split_run(torch, g, dist, rank, world, device, k=7)]
         line["batch_chain"] = batch_chain_run(torch, g, dist, world)
     if dist is not None:
         dist.barrier()

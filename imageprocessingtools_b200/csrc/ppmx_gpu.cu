@@ -343,7 +343,7 @@ static int launch_op(const ppmx_op *op, const uint8_t *d_src, uint32_t w, uint32
         return PPMX_OK;
     case PPMX_OP_IMRESIZE:
         if (!tables || !tables->weights) return fail("imresize: tables are not on the device");
-        CK(ppmx::imresize(d_src, d_dst, w, h, op->out_size, op->dim, op->weights_sz, tables->weights, tables->indices, s),
+        CK(ppmx::imresize(d_src, d_dst, w, h, op->out_size, op->dim, op->weights_sz, tables->weights, tables->indices, band, s),
            "imresize");
         return PPMX_OK;
     case PPMX_OP_CONV:
@@ -648,6 +648,8 @@ extern "C" int ppmx_gpu_launch(const ppmx_op *op, const void *d_src, uint32_t w,
         b.top = (const uint8_t *)band->d_top;
         b.bottom = (const uint8_t *)band->d_bottom;
         b.halo = band->halo;
+        b.out_y0 = band->out_y0;
+        b.out_rows = band->out_rows;
     }
     DeviceTables t;
     if (op->kind == PPMX_OP_IMRESIZE) {

@@ -1176,6 +1176,49 @@ cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_
     return PPMX_LAUNCHED();
 }
 
+// ---- rows of a raster that may be spread over a band and its neighbours' halos ----------------
+__host__ __device__ __forceinline__ int mirror_index(int i, int n)
+{
+    int m = i % (2 * n);
+    if (m < 0) m += 2 * n;
+    return m < n ? m : 2 * n - 1 - m;
+}
+
+// resolves a row of the WHOLE raster to memory: own band, halo above, halo below (maybe peer HBM)
+struct RowSource {
+    const uint8_t *own, *top, *bottom;
+    int y0, h, halo, full_h;
+    __device__ __forceinline__ const uint8_t *row(int gy, size_t pitch) const
+    {
+        gy = mirror_index(gy, full_h);
+        if (gy >= y0 && gy < y0 + h) return own + (size_t)(gy - y0) * pitch;
+        if (gy < y0) return top + (size_t)(gy - (y0 - halo)) * pitch;
+        return bottom + (size_t)(gy - (y0 + h)) * pitch;
+    }
+    // the same without the mirror step, for row numbers that are already inside the raster
+    __device__ __forceinline__ const uint8_t *row_plain(int gy, size_t pitch) const
+    {
+        if (gy >= y0 && gy < y0 + h) return own + (size_t)(gy - y0) * pitch;
+        if (gy < y0) return top + (size_t)(gy - (y0 - halo)) * pitch;
+        return bottom + (size_t)(gy - (y0 + h)) * pitch;
+    }
+};
+
+static RowSource make_row_source(const uint8_t *src, uint32_t h, const Band &band)
+{
+    RowSource rs;
+    rs.own = src;
+    rs.top = band.top;
+    rs.bottom = band.bottom;
+    rs.y0 = band.full_h ? (int)band.y0 : 0;
+    rs.h = (int)h;
+    rs.halo = (int)band.halo;
+    rs.full_h = band.full_h ? (int)band.full_h : (int)h;
+    return rs;
+}
+
+
+
 // ------------------------------------------------------------------------------------------
 // imresize  (ref:820-838 height pass, ref:846-868 width pass): K-tap gather, FP64 accumulate
 // in tap order, floor(s + 0.5), clamp, u8 store.
@@ -1202,7 +1245,7 @@ __device__ __forceinline__ uint32_t quantise_fast(double s)
 // so the K source loads of a thread are independent of each other and fly four at a time.
 constexpr int ROWS16_MAXK = 64;
 template <int CONV>
-__global__ void __launch_bounds__(256) imresize_rows16_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+__global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource src, uint8_t *__restrict__ dst,
                                                               uint32_t row_vecs, int taps,
                                                               const double *__restrict__ wts, const int *__restrict__ idx)
 {
@@ -1218,7 +1261,7 @@ __global__ void __launch_bounds__(256) imresize_rows16_kernel(const uint8_t *__r
     const uint32_t xv = blockIdx.x * 256 + threadIdx.x;
     if (xv >= row_vecs) return;
     const size_t row_bytes = (size_t)row_vecs * 16;
-    const uint4 *col = reinterpret_cast<const uint4 *>(src) + xv;
+
     double acc[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) acc[i] = 0.0;
@@ -1226,7 +1269,7 @@ __global__ void __launch_bounds__(256) imresize_rows16_kernel(const uint8_t *__r
         uint4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; u++)
-            if (z0 + u < taps) v[u] = __ldg(col + (size_t)s_i[z0 + u] * row_vecs);
+            if (z0 + u < taps) v[u] = __ldg(reinterpret_cast<const uint4 *>(src.row_plain(s_i[z0 + u], row_bytes)) + xv);
 #pragma unroll
         for (int u = 0; u < 4; u++) {  // tap order is the reference's summation order (ref:826-830)
             if (z0 + u >= taps) break;
@@ -1346,7 +1389,7 @@ static void launch_colsK(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t 
 // height pass: every byte of an output row uses the same K source rows and weights, so the
 // raster is treated as rows of 3*w independent bytes; VEC bytes per thread.
 template <int VEC>
-__global__ void __launch_bounds__(256) imresize_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+__global__ void __launch_bounds__(256) imresize_rows_kernel(const RowSource src, uint8_t *__restrict__ dst,
                                                             uint32_t row_bytes, int out_h, int taps,
                                                             const double *__restrict__ wts, const int *__restrict__ idx)
 {
@@ -1361,7 +1404,7 @@ __global__ void __launch_bounds__(256) imresize_rows_kernel(const uint8_t *__res
     for (int v = 0; v < VEC; v++) acc[v] = 0.0;
     for (int z = 0; z < taps; z++) {
         const double wz = __ldg(wy + z);
-        const uint8_t *p = src + (size_t)__ldg(iy + z) * row_bytes + xb;
+        const uint8_t *p = src.row_plain(__ldg(iy + z), row_bytes) + xb;
         if (VEC == 4) {
             uint32_t v4 = __ldg(reinterpret_cast<const uint32_t *>(p));
 #pragma unroll
@@ -1405,13 +1448,23 @@ __global__ void __launch_bounds__(256) imresize_cols_kernel(const uint8_t *__res
     o[2] = (uint8_t)quantise(s2);
 }
 
-cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int out_size, int dim, int taps,
-                     const double *d_weights, const int *d_indices, cudaStream_t s)
+cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t h, int out_size, int dim, int taps,
+                     const double *d_weights, const int *d_indices, const Band &band, cudaStream_t s)
 {
     if (out_size <= 0 || !w || !h) return cudaSuccess;
     if (dim == 0) {
+        // a band computes output rows [out_y0, out_y0 + out_rows) from its own source rows plus halos
+        const RowSource src = make_row_source(src_ptr, h, band);
+        if (band.full_h) {
+            if (band.out_y0 + band.out_rows > (uint32_t)out_size) return cudaErrorInvalidValue;
+            d_weights += (size_t)band.out_y0 * taps;
+            d_indices += (size_t)band.out_y0 * taps;
+            out_size = (int)band.out_rows;
+            if (out_size <= 0) return cudaSuccess;
+        }
+        const bool halo_ok = (!band.top || aligned16(band.top)) && (!band.bottom || aligned16(band.bottom));
         uint32_t row_bytes = w * 3u;
-        if (row_bytes % 16 == 0 && aligned16(src) && aligned16(dst) && taps <= ROWS16_MAXK && g_variant != 1) {
+        if (row_bytes % 16 == 0 && aligned16(src_ptr) && aligned16(dst) && halo_ok && taps <= ROWS16_MAXK && g_variant != 1) {
             dim3 grid((row_bytes / 16 + 255) / 256, 1);
             for (int y0 = 0; y0 < out_size; y0 += 65535) {
                 int rows = min(65535, out_size - y0);
@@ -1428,7 +1481,7 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
             }
             return cudaGetLastError();
         }
-        if (row_bytes % 4 == 0 && aligned4(src) && aligned4(dst)) {
+        if (row_bytes % 4 == 0 && aligned4(src_ptr) && aligned4(dst) && halo_ok) {
             dim3 grid((row_bytes / 4 + 255) / 256, 1);
             // rows go on grid.y in slabs of <= 65535
             for (int y0 = 0; y0 < out_size; y0 += 65535) {
@@ -1448,6 +1501,7 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
         }
         return cudaGetLastError();
     }
+    const uint8_t *src = src_ptr;
     if ((w % 4u) == 0 && aligned4(src) && taps >= 4 && taps <= 8 && g_variant != 1) {
         switch (taps) {
         case 4: launch_colsK<4>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
@@ -1480,26 +1534,6 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
 // ------------------------------------------------------------------------------------------
 
 constexpr int CONV_MAXK = 15;
-
-__host__ __device__ __forceinline__ int mirror_index(int i, int n)
-{
-    int m = i % (2 * n);
-    if (m < 0) m += 2 * n;
-    return m < n ? m : 2 * n - 1 - m;
-}
-
-// resolves a row of the WHOLE raster to memory: own band, halo above, halo below (maybe peer HBM)
-struct RowSource {
-    const uint8_t *own, *top, *bottom;
-    int y0, h, halo, full_h;
-    __device__ __forceinline__ const uint8_t *row(int gy, size_t pitch) const
-    {
-        gy = mirror_index(gy, full_h);
-        if (gy >= y0 && gy < y0 + h) return own + (size_t)(gy - y0) * pitch;
-        if (gy < y0) return top + (size_t)(gy - (y0 - halo)) * pitch;
-        return bottom + (size_t)(gy - (y0 + h)) * pitch;
-    }
-};
 
 // exact floor((2*acc + div) / (2*div)) + bias with one multiply-high: the numerator is shifted to
 // be non-negative by a multiple K of the divisor d = 2*div, then n/d = (n * M) >> (31 + l) for all
@@ -1738,14 +1772,7 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
 {
     if (k < 1 || k > CONV_MAXK || !(k & 1) || div < 1) return cudaErrorInvalidValue;
     if (!w || !h) return cudaSuccess;
-    RowSource rs;
-    rs.own = src;
-    rs.top = band.top;
-    rs.bottom = band.bottom;
-    rs.y0 = band.full_h ? (int)band.y0 : 0;
-    rs.h = (int)h;
-    rs.halo = (int)band.halo;
-    rs.full_h = band.full_h ? (int)band.full_h : (int)h;
+    const RowSource rs = make_row_source(src, h, band);
 
     bool s8 = true;
     int64_t sum_abs = 0;

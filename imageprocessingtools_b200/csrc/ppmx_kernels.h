@@ -16,6 +16,7 @@ struct Band {
     const uint8_t *top = nullptr;  // `halo` rows directly above the band (may be peer memory)
     const uint8_t *bottom = nullptr;
     uint32_t halo = 0;
+    uint32_t out_y0 = 0, out_rows = 0;  // imresize height pass: the slice of output rows this band produces
 };
 
 // which implementation of an operator to launch; 0 = the default (best measured)
@@ -34,7 +35,7 @@ cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_
                            double cos_t, double sin_t, cudaStream_t s);
 // one separable pass; d_weights/d_indices are [out_size][taps] in device memory
 cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int out_size, int dim, int taps,
-                     const double *d_weights, const int *d_indices, cudaStream_t s);
+                     const double *d_weights, const int *d_indices, const Band &band, cudaStream_t s);
 // extension operators (no reference counterpart)
 cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef /*host*/,
                  int32_t div, int32_t bias, const Band &band, cudaStream_t s);

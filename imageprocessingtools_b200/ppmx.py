@@ -46,7 +46,7 @@ class PpmxOp(C.Structure):
 class PpmxBand(C.Structure):
     """struct ppmx_band of include/ppmx_gpu.h"""
     _fields_ = [("full_h", C.c_uint32), ("y0", C.c_uint32), ("d_top", C.c_void_p), ("d_bottom", C.c_void_p),
-                ("halo", C.c_uint32)]
+                ("halo", C.c_uint32), ("out_y0", C.c_uint32), ("out_rows", C.c_uint32)]
 
 
 class _ArgsFlag(C.Structure):

@@ -153,6 +153,8 @@ typedef struct ppmx_band {
     const void *d_top; /* rows [y0-halo, y0) as a packed raster, or NULL at the image top    */
     const void *d_bottom; /* rows [y0+h, y0+h+halo), or NULL at the image bottom             */
     uint32_t halo;     /* rows available behind d_top / d_bottom                             */
+    uint32_t out_y0;   /* imresize height pass only: this band produces output rows          */
+    uint32_t out_rows; /*   [out_y0, out_y0 + out_rows) of the op's out_size rows            */
 } ppmx_band;
 
 int ppmx_gpu_launch(const ppmx_op *op, const void *d_src, uint32_t w, uint32_t h, int src_layout,

@@ -251,6 +251,41 @@ def test_extension_conv_row_bands(gpu, orc):
         assert np.array_equal(got, exp), (w, h, k)
 
 
+def test_imresize_height_pass_row_bands(gpu, orc):
+    """ref:820-838 cut into row bands: every band owns a slice of the SOURCE rows and produces a slice of
+    the OUTPUT rows; taps that fall into a neighbour's rows are read through the halo pointers."""
+    import torch
+    import imageprocessingtools_b200.ppmx as pp
+    dev = torch.device("cuda", 0)
+    for (w, h, new_h, n) in [(64, 96, 144, 3), (64, 96, 40, 2), (48, 50, 75, 4), (37, 60, 90, 2), (128, 64, 64, 2)]:
+        img = P.lcg(w, h, 123)
+        wt, ix = gpu.calc_contributions(h, new_h, float(new_h) / h)
+        exp = orc.imresize(img, new_h, 0, wt, ix)
+        op = gpu.imresize_op(new_h, 0, wt, ix)
+        tables = gpu.tables_upload(op)
+        in_bands = [pp.band_plan(h, n, r, 1) for r in range(n)]
+        out_bands = [pp.band_plan(new_h, n, r, 1) for r in range(n)]
+        srcs = [torch.from_numpy(img[a:a + c].copy()).to(dev) for a, c in in_bands]
+        got = []
+        for r in range(n):
+            (y0, rows), (oy0, orows) = in_bands[r], out_bands[r]
+            need = ix[oy0:oy0 + orows]
+            halo = int(max(0, y0 - need.min(), need.max() - (y0 + rows - 1))) if orows else 0
+            band = pp.PpmxBand(full_h=h, y0=y0, halo=halo, out_y0=oy0, out_rows=orows)
+            if r > 0 and halo:
+                assert in_bands[r - 1][1] >= halo
+                band.d_top = srcs[r - 1].data_ptr() + (in_bands[r - 1][1] - halo) * w * 3
+            if r < n - 1 and halo:
+                assert in_bands[r + 1][1] >= halo
+                band.d_bottom = srcs[r + 1].data_ptr()
+            dst = torch.zeros((max(orows, 1), w, 3), dtype=torch.uint8, device=dev)
+            gpu.launch(op, srcs[r].data_ptr(), w, rows, pp.LAYOUT_RGB8, dst.data_ptr(), band, 0, tables)
+            torch.cuda.synchronize()
+            got.append(dst.cpu().numpy()[:orows])
+        gpu.tables_free(tables)
+        assert np.array_equal(np.concatenate(got, axis=0), exp), (w, h, new_h, n)
+
+
 def test_mono_row_bands_keep_bayer_phase(gpu, orc):
     import torch
     import imageprocessingtools_b200.ppmx as pp
