@@ -562,6 +562,41 @@ def batch_chain_run(torch, g, dist, world, images=128):
     return out
 
 
+def cpu_reference_per_op(names):
+    """One bounded, single-threaded call (two for the cheap ones) of the compiled reference per operator,
+    on a 4096x4096 raster of the same kind; time inside the reference function only."""
+    import numpy as np
+    import oracle
+    ref = oracle.ref()
+    if ref is None:
+        return {}
+    img = np.random.default_rng(2).integers(0, 256, (4096, 4096, 3), dtype=np.uint8)
+    out = {}
+    for name in names:
+        base = name.split("_16k")[0]
+        try:
+            if base in ("gray", "gray_hist"):
+                ref.gray(img); t = ref.last_seconds
+            elif base == "mono":
+                ref.mono(img); t = ref.last_seconds
+            elif base in ("fliph", "flipv"):
+                ref.flip(img, int(base == "flipv")); t = ref.last_seconds
+            elif base in ("rot90", "rot180", "rot30"):
+                ref.rotate(img, int(base[3:])); t = ref.last_seconds
+            elif base in ("resize_up", "resize_down"):
+                new_w = 6144 if base == "resize_up" else 2048
+                # both passes in the reference's order (ref:1098-1120): width then height for exact scales
+                wt1, ix1 = ref.calc_contributions(4096, new_w, new_w / 4096.0)
+                mid = ref.imresize(img, new_w, 1, wt1, ix1); t = ref.last_seconds
+                mid = ref.imresize(mid, new_w, 0, wt1, ix1); t += ref.last_seconds
+            else:
+                continue  # extension operators have no reference implementation
+            out[name] = round(4096 * 4096 / t / 1e6, 1)
+        except Exception:
+            pass
+    return out
+
+
 def run_ours(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -660,6 +695,9 @@ def run_ours(args):
 
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample(name, 1)
+        if "per_op" in line:  # the reference's own function, 1 thread, 4096x4096, beside every operator
+            for k, v in cpu_reference_per_op(list(line["per_op"])).items():
+                line["per_op"][k]["cpu_reference_mpix_s_1thread"] = v
     runner.close()
     del runner
     torch.cuda.empty_cache()

@@ -580,27 +580,36 @@ extern "C" int ppmx_gpu_apply_batch(ppmx_gpu_ctx *c, const ppmx_op *ops, int nop
     size_t each = 0;
     uint32_t ow = 0, oh = 0;
     int ft = PPMX_FILETYPE_PPM;
+    // at most kInFlight rasters per lane are enqueued ahead of the GPU, so the stream-ordered pool
+    // holds a bounded number of rasters however long the batch is
+    constexpr int kInFlight = 4;
+    cudaEvent_t done[kLanes][kInFlight] = {};
     for (int i = 0; i < count && rc == PPMX_OK; i++) {
         Chain ch;
         ch.c = c;
         ch.lane = i % kLanes;
         ch.index = i;
+        const int slot = (i / kLanes) % kInFlight;
+        if (done[ch.lane][slot]) CK(cudaEventSynchronize(done[ch.lane][slot]), "event sync");
+        else CK(cudaEventCreateWithFlags(&done[ch.lane][slot], cudaEventDisableTiming), "event create");
         rc = upload_on(c, ch.lane, src + (size_t)i * in_bytes, w, h, PPMX_LAYOUT_RGB8, &ch.buff);
         if (rc == PPMX_OK) rc = run_chain(ch, ops, nops, tables);
         if (rc == PPMX_OK) {
             ppmx_gpu_image *tmp = nullptr;
-            size_t cap = (count == 1) ? dst_stride : dst_stride;
-            rc = download_on(c, ch.lane, ch.newb, ch.file_type, dst + (size_t)i * dst_stride, cap, &each, &tmp);
+            rc = download_on(c, ch.lane, ch.newb, ch.file_type, dst + (size_t)i * dst_stride, dst_stride, &each, &tmp);
             image_free_on(c, tmp);
             ow = ch.newb->w;
             oh = ch.newb->h;
             ft = ch.file_type;
         }
         ch.release();
+        cudaEventRecord(done[ch.lane][slot], c->lane[ch.lane]);
     }
     for (int l = 0; l < kLanes; l++) {
         cudaError_t e = cudaStreamSynchronize(c->lane[l]);
         if (e != cudaSuccess && rc == PPMX_OK) rc = fail("stream sync", e);
+        for (int k = 0; k < kInFlight; k++)
+            if (done[l][k]) cudaEventDestroy(done[l][k]);
     }
     release_tables(c, tables);
     if (rc != PPMX_OK) return rc;

@@ -241,11 +241,25 @@ void ppmx_renewBuffer(ppmx_image_handler *h)
 
 /* ------------------------------------------------------------------ the op chain as data */
 
+/* extension presets (no reference counterpart) */
+static const int32_t k_blur3[9] = {1, 2, 1, 2, 4, 2, 1, 2, 1};
+static const int32_t k_sharpen[9] = {0, -1, 0, -1, 5, -1, 0, -1, 0};
+static const int32_t k_edge[9] = {-1, -1, -1, -1, 8, -1, -1, -1, -1};
+static const int32_t k_box7[49] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                                   1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+
 int ppmx_plan_chain(const ppmx_args_flag *f, unsigned int output_width_size, double angle, unsigned int width,
                     unsigned int height, ppmx_plan *plan)
 {
+    return ppmx_plan_chain_ext(f, output_width_size, angle, width, height, PPMX_CONV_NONE, plan);
+}
+
+int ppmx_plan_chain_ext(const ppmx_args_flag *f, unsigned int output_width_size, double angle, unsigned int width,
+                        unsigned int height, int conv_preset, ppmx_plan *plan)
+{
     unsigned int w = width, h = height;
-    const int renew = f->resize_enable || f->rotate_enable; /* the condition of ref:1138,1143,1148,1153 */
+    /* the condition of ref:1138,1143,1148,1153; an extension stage counts like -w / -r */
+    int renew = f->resize_enable || f->rotate_enable;
     int n = 0;
     memset(plan, 0, sizeof(*plan));
 
@@ -280,6 +294,20 @@ int ppmx_plan_chain(const ppmx_args_flag *f, unsigned int output_width_size, dou
         fill_rotate_op(op, angle, w, h);
         op->renew_before = f->resize_enable ? 1 : 0;
         if (angle != 0) { w = op->new_width; h = op->new_height; }
+    }
+    if (conv_preset != PPMX_CONV_NONE) { /* extension stage, handed over like the reference's own stages */
+        ppmx_op *op = &plan->ops[n++];
+        op->kind = PPMX_OP_CONV;
+        op->renew_before = renew;
+        op->conv_bias = 0;
+        switch (conv_preset) {
+        case PPMX_CONV_BLUR3: op->conv_k = 3; op->conv_div = 16; op->conv_coef = k_blur3; break;
+        case PPMX_CONV_BLUR7: op->conv_k = 7; op->conv_div = 49; op->conv_coef = k_box7; break;
+        case PPMX_CONV_SHARPEN: op->conv_k = 3; op->conv_div = 1; op->conv_coef = k_sharpen; break;
+        case PPMX_CONV_EDGE: op->conv_k = 3; op->conv_div = 1; op->conv_coef = k_edge; break;
+        default: printf("Error: unknown convolution preset\n"); goto bad;
+        }
+        renew = 1;
     }
     if (f->gray_enable) { /* ref:1137-1140 */
         plan->ops[n].kind = PPMX_OP_GRAY;
@@ -519,7 +547,7 @@ int ppmx_doProcessPPM(ppmx_image_handler *h)
     if (ppmx_parse_header(h->file_buffer, h->filesize, &w, &hh, &mx, &off) != PPMX_OK) goto done;
     h->imginfo.width = w; h->imginfo.height = hh; h->imginfo.max_color = mx; h->index_buffer = off;
 
-    if (ppmx_plan_chain(&h->arg_flag, h->output_width_size, h->angle, w, hh, &plan) != PPMX_OK) goto done;
+    if (ppmx_plan_chain_ext(&h->arg_flag, h->output_width_size, h->angle, w, hh, h->conv_preset, &plan) != PPMX_OK) goto done;
     if (plan.nops == 0) { printf("Error: no data to write\n"); goto done; } /* ref:235 */
 
     /* the largest raster any stage can hand to the writer is RGB at the final size */
@@ -603,6 +631,11 @@ int ppmx_main(int argc, char *argv[])
             if (!all_digits(a + 2)) BAIL("Error: invalid option for rotate.\n");
             hd.angle = (double)atoi(a + 2);
             if (hd.angle < 0 || hd.angle >= 360) BAIL("Error: invalid option for rotate.\n");
+        } else if (strcmp(a + 1, "blur") == 0 || strcmp(a + 1, "blur7") == 0 || strcmp(a + 1, "sharpen") == 0 ||
+                   strcmp(a + 1, "edge") == 0) { /* EXTENSION flags: the reference rejects them (ref:175) */
+            if (hd.conv_preset) BAIL("Error: Duplicate options not allowed\n");
+            hd.conv_preset = a[1] == 's' ? PPMX_CONV_SHARPEN : a[1] == 'e' ? PPMX_CONV_EDGE
+                             : a[5] == '7' ? PPMX_CONV_BLUR7 : PPMX_CONV_BLUR3;
         } else if (strcmp(a + 1, "gray") == 0) {
             if (hd.arg_flag.gray_enable) BAIL("Error: Duplicate options not allowed\n");
             if (hd.arg_flag.mono_enable) BAIL("Error: Conflicting options not allowed\n");

@@ -133,6 +133,8 @@ def host_lib() -> C.CDLL:
         H.ppmx_calc_rot_size.argtypes = [C.c_double, C.c_uint, C.c_uint, _u32p, _u32p]
         H.ppmx_calc_rot_size.restype = None
         H.ppmx_plan_chain.argtypes = [C.POINTER(_ArgsFlag), C.c_uint, C.c_double, C.c_uint, C.c_uint, C.POINTER(_Plan)]
+        H.ppmx_plan_chain_ext.argtypes = [C.POINTER(_ArgsFlag), C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_int,
+                                          C.POINTER(_Plan)]
         H.ppmx_plan_free.argtypes = [C.POINTER(_Plan)]
         H.ppmx_plan_free.restype = None
         H.ppmx_band_plan.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, _u32p, _u32p]
@@ -206,11 +208,13 @@ def format_header(file_type: int, w: int, h: int, maxval: int = 255) -> bytes:
 
 
 class _PlanHolder:
-    def __init__(self, resize_w=None, angle=None, gray=False, mono=False, flipv=False, fliph=False, w=0, h=0):
+    def __init__(self, resize_w=None, angle=None, gray=False, mono=False, flipv=False, fliph=False, w=0, h=0,
+                 conv_preset=0):
         self.plan = _Plan()
         f = _ArgsFlag(bytes([int(resize_w is not None)]), bytes([int(angle is not None)]), bytes([int(flipv)]),
                       bytes([int(fliph)]), bytes([int(gray)]), bytes([int(mono)]))
-        rc = host_lib().ppmx_plan_chain(C.byref(f), int(resize_w or 0), float(angle or 0), w, h, C.byref(self.plan))
+        rc = host_lib().ppmx_plan_chain_ext(C.byref(f), int(resize_w or 0), float(angle or 0), w, h, int(conv_preset),
+                                            C.byref(self.plan))
         if rc != 0:
             raise PpmxError("ppmx_plan_chain failed")
 
@@ -352,11 +356,11 @@ class Ppmx:
         return data.reshape(h, w, 3)
 
     def process(self, img, resize_w: Optional[int] = None, angle: Optional[int] = None, gray=False, mono=False,
-                flipv=False, fliph=False):
+                flipv=False, fliph=False, conv_preset: int = 0):
         """The whole chain through ppmx_plan_chain + ppmx_gpu_apply (host raster in, writer bytes out)."""
         img = _img(img)
         h, w, _ = img.shape
-        ph = _PlanHolder(resize_w, angle, gray, mono, flipv, fliph, w, h)
+        ph = _PlanHolder(resize_w, angle, gray, mono, flipv, fliph, w, h, conv_preset)
         try:
             if ph.plan.nops == 0:
                 raise PpmxError("Error: no data to write")

@@ -49,6 +49,7 @@ typedef struct ppmx_image_handler {
     unsigned int output_width_size;
     double angle;
     char norotate;
+    int conv_preset;            /* extension flags -blur/-blur7/-sharpen/-edge (0 = none); not in the reference */
 } ppmx_image_handler;
 
 /* ref:92-96, flat: weights[out_size][weights_sz], indices likewise */
@@ -88,6 +89,16 @@ typedef struct ppmx_plan {
 } ppmx_plan;
 int ppmx_plan_chain(const ppmx_args_flag *flags, unsigned int output_width_size, double angle,
                     unsigned int width, unsigned int height, ppmx_plan *plan);
+/* The same with one EXTENSION stage (no reference counterpart): a preset k x k convolution inserted after
+ * resize/rotate and before gray/mono/flip.  Presets: 1 blur 3x3 (1 2 1; 2 4 2; 1 2 1)/16, 2 box blur 7x7 /49,
+ * 3 sharpen (0 -1 0; -1 5 -1; 0 -1 0), 4 edge (-1 ... 8 ... -1).  0 = none = ppmx_plan_chain. */
+#define PPMX_CONV_NONE 0
+#define PPMX_CONV_BLUR3 1
+#define PPMX_CONV_BLUR7 2
+#define PPMX_CONV_SHARPEN 3
+#define PPMX_CONV_EDGE 4
+int ppmx_plan_chain_ext(const ppmx_args_flag *flags, unsigned int output_width_size, double angle,
+                        unsigned int width, unsigned int height, int conv_preset, ppmx_plan *plan);
 void ppmx_plan_free(ppmx_plan *plan);
 
 /* Header tokenizer of ref:333-456 on an in-memory file: width, height, maxval and the offset

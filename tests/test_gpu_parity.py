@@ -420,3 +420,25 @@ def test_tuning_variants_are_bit_identical(gpu, orc):
     finally:
         gpu.set_tuning("variant", 0)
         gpu.set_tuning("pdl", 1)
+
+
+def test_extension_cli_conv_presets(gpu, orc, tmp_path):
+    """EXTENSION flags of ppmx-b200 (-blur, -blur7, -sharpen, -edge; the reference rejects them): the stage
+    sits after resize/rotate and before gray/mono/flip.  Self-oracle only (parity unpinned)."""
+    import imageprocessingtools_b200.ppmx as pp
+    img = P.lcg(64, 40, 5)
+    presets = {"-blur": KERNELS["blur3"], "-blur7": (np.ones((7, 7), np.int64), 49, 0), "-sharpen": KERNELS["sharpen3"],
+               "-edge": KERNELS["edge3"]}
+    path = str(tmp_path / "x.ppm")
+    for flag, (coef, div, bias) in presets.items():
+        oracle.write_p6(path, img)
+        p = subprocess.run([pp.CLI, flag, "-gray", path], capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout
+        exp = orc.header(oracle.FT_PGM, 64, 40) + orc.gray(orc.conv(img, coef, div, bias)).tobytes()
+        assert open(path + ".out", "rb").read() == exp, flag
+        p = subprocess.run([pp.CLI, "-r90", flag, "-fh", path], capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout
+        exp = orc.flip(orc.conv(orc.rotate(img, 90), coef, div, bias), 0)
+        assert open(path + ".out", "rb").read() == orc.header(oracle.FT_PPM, 40, 64) + exp.tobytes(), flag
+    p = subprocess.run([pp.CLI, "-blur", "-edge", path], capture_output=True, text=True)
+    assert p.returncode == 255 and "Duplicate" in p.stdout
