@@ -898,10 +898,8 @@ __device__ __forceinline__ uint32_t xt_slot(uint32_t row, uint32_t chunk)
 // XT_NT horizontally adjacent tiles per CTA (vertical pairs, i.e. longer contiguous WRITES, measured
 // 8 % slower: long contiguous reads matter more): the loads of ALL of them are issued up front, so
 // the second tile's DRAM latency hides behind the first tile's shared-memory phase and stores.
-constexpr int XT_NT = 2;  // 1 and 2 measure the same (73.7 % of the HBM roofline), 4 loses 6 %
-
-template <bool CW>
-__global__ void __launch_bounds__(256) rotate_transpose64_kernel(const uint8_t *__restrict__ src,
+template <bool CW, int XT_NT, int MINB>
+__global__ void __launch_bounds__(256, MINB) rotate_transpose64_kernel(const uint8_t *__restrict__ src,
                                                                  uint8_t *__restrict__ dst, uint32_t w, uint32_t h)
 {
     pdl_trigger();
@@ -994,10 +992,18 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
     if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && g_variant != 1) {
         // (numbering the CTAs down bands of 2..16 tile rows, for DRAM page locality on the write side,
         // measured 1-5 % SLOWER than this plain 2-D grid: the index arithmetic costs more than it gains)
-        dim3 g64((w + XT * XT_NT - 1) / (XT * XT_NT), (h + XT - 1) / XT);
+        // two tiles per CTA at <= 40 registers (6 CTAs per SM) measured best: 0.725 / 0.828 of the HBM
+        // roofline at 4096^2 / 16384^2; one tile per CTA (variant 6): 0.723 / 0.753
+        const int nt = (g_variant == 6) ? 1 : 2;
+        dim3 g64((w + XT * nt - 1) / (XT * nt), (h + XT - 1) / XT);
         if (g64.y > 65535u) return cudaErrorInvalidValue;
-        if (angle == 90) launch(rotate_transpose64_kernel<true>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
-        else launch(rotate_transpose64_kernel<false>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+        if (g_variant == 6) {
+            if (angle == 90) launch(rotate_transpose64_kernel<true, 1, 1>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+            else launch(rotate_transpose64_kernel<false, 1, 1>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+        } else {
+            if (angle == 90) launch(rotate_transpose64_kernel<true, 2, 6>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+            else launch(rotate_transpose64_kernel<false, 2, 6>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+        }
         return PPMX_LAUNCHED();
     }
     dim3 grid((w + RT - 1) / RT, (h + RT - 1) / RT);
