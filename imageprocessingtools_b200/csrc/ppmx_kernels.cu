@@ -408,11 +408,12 @@ __global__ void __launch_bounds__(HL_THREADS, 1) gray_hist_lanes_kernel(const ui
 }
 
 // variant: one 16-pixel group per thread, one CTA per 256 groups (no grid-stride loop)
-__global__ void __launch_bounds__(256) gray_flat_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
-                                                        size_t ngroups, size_t npix)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) gray_flat_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
+                                                          size_t ngroups, size_t npix)
 {
     pdl_trigger();
-    const size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t g = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     pdl_wait();  // everything above is index arithmetic; global memory is touched only below
     if (g < ngroups) {
         const uint4 *p = src + 3 * g;
@@ -543,8 +544,17 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
             return PPMX_LAUNCHED();
         }
         if (!HIST && g_variant != 1 && g_variant != 4) {  // default: one group per thread, no loop
+            if (g_variant == 6 || g_variant == 7) {  // smaller CTAs: shorter tail, more CTA launches
+                const unsigned blk = g_variant == 6 ? 128u : 64u;
+                unsigned grid = (unsigned)((ngroups + blk - 1) / blk);
+                if (blk == 128) launch(gray_flat_kernel<128>, dim3(grid ? grid : 1), dim3(128), 0, s,
+                                       reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), ngroups, npix);
+                else launch(gray_flat_kernel<64>, dim3(grid ? grid : 1), dim3(64), 0, s,
+                            reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), ngroups, npix);
+                return PPMX_LAUNCHED();
+            }
             unsigned grid = (unsigned)((ngroups + 255) / 256);
-            launch(gray_flat_kernel, dim3(grid ? grid : 1), dim3(256), 0, s, reinterpret_cast<const uint4 *>(src),
+            launch(gray_flat_kernel<256>, dim3(grid ? grid : 1), dim3(256), 0, s, reinterpret_cast<const uint4 *>(src),
                    reinterpret_cast<uint4 *>(dst), ngroups, npix);
             return PPMX_LAUNCHED();
         }
@@ -898,13 +908,19 @@ __device__ __forceinline__ uint32_t xt_slot(uint32_t row, uint32_t chunk)
 // XT_NT horizontally adjacent tiles per CTA (vertical pairs, i.e. longer contiguous WRITES, measured
 // 8 % slower: long contiguous reads matter more): the loads of ALL of them are issued up front, so
 // the second tile's DRAM latency hides behind the first tile's shared-memory phase and stores.
-template <bool CW, int XT_NT, int MINB>
+// BAND > 0: blockIdx.x = tile_x * BAND + (tile row inside a band of BAND tile rows), blockIdx.y = band; CTAs
+// then walk BAND tiles down before stepping right, which lengthens the contiguous run written per
+// destination row while it is "hot" (shift arithmetic only).  BAND = 0: plain 2-D grid.
+template <bool CW, int XT_NT, int MINB, int BAND>
 __global__ void __launch_bounds__(256, MINB) rotate_transpose64_kernel(const uint8_t *__restrict__ src,
                                                                  uint8_t *__restrict__ dst, uint32_t w, uint32_t h)
 {
     pdl_trigger();
     __shared__ __align__(16) uint32_t tile[XT * 64];
-    const uint32_t ty0 = blockIdx.y * XT;
+    const uint32_t bx = BAND ? blockIdx.x / BAND : blockIdx.x;
+    const uint32_t by = BAND ? blockIdx.y * BAND + blockIdx.x % BAND : blockIdx.y;
+    const uint32_t ty0 = by * XT;
+    if (ty0 >= h) return;
     const size_t in_pitch = (size_t)w * 3, out_pitch = (size_t)h * 3;
     const uint32_t row = threadIdx.x >> 2, q = threadIdx.x & 3u;               // phase 1 role
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -915,7 +931,7 @@ __global__ void __launch_bounds__(256, MINB) rotate_transpose64_kernel(const uin
     bool have[XT_NT];
 #pragma unroll
     for (int t = 0; t < XT_NT; t++) {
-        const uint32_t y = ty0 + row, x0 = (blockIdx.x * XT_NT + t) * XT + 16u * q;
+        const uint32_t y = ty0 + row, x0 = (bx * XT_NT + t) * XT + 16u * q;
         have[t] = (y < h && x0 < w);
         if (have[t]) {
             const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)y * in_pitch + (size_t)x0 * 3);
@@ -926,7 +942,7 @@ __global__ void __launch_bounds__(256, MINB) rotate_transpose64_kernel(const uin
     }
 #pragma unroll
     for (int t = 0; t < XT_NT; t++) {
-        const uint32_t tx0 = (blockIdx.x * XT_NT + t) * XT;
+        const uint32_t tx0 = (bx * XT_NT + t) * XT;
         if (tx0 >= w) break;
         if (t > 0) __syncthreads();  // the previous tile has been read out of shared memory
         if (have[t]) {
@@ -998,11 +1014,21 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
         dim3 g64((w + XT * nt - 1) / (XT * nt), (h + XT - 1) / XT);
         if (g64.y > 65535u) return cudaErrorInvalidValue;
         if (g_variant == 6) {
-            if (angle == 90) launch(rotate_transpose64_kernel<true, 1, 1>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
-            else launch(rotate_transpose64_kernel<false, 1, 1>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+            if (angle == 90) launch(rotate_transpose64_kernel<true, 1, 1, 0>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+            else launch(rotate_transpose64_kernel<false, 1, 1, 0>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+        } else if (g_variant == 7 || g_variant == 8) {
+            const unsigned band = g_variant == 7 ? 8u : 4u;
+            dim3 gb(g64.x * band, (g64.y + band - 1) / band);
+            if (g_variant == 7) {
+                if (angle == 90) launch(rotate_transpose64_kernel<true, 2, 6, 8>, gb, dim3(256), 0, s, src, dst, w, h);
+                else launch(rotate_transpose64_kernel<false, 2, 6, 8>, gb, dim3(256), 0, s, src, dst, w, h);
+            } else {
+                if (angle == 90) launch(rotate_transpose64_kernel<true, 2, 6, 4>, gb, dim3(256), 0, s, src, dst, w, h);
+                else launch(rotate_transpose64_kernel<false, 2, 6, 4>, gb, dim3(256), 0, s, src, dst, w, h);
+            }
         } else {
-            if (angle == 90) launch(rotate_transpose64_kernel<true, 2, 6>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
-            else launch(rotate_transpose64_kernel<false, 2, 6>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+            if (angle == 90) launch(rotate_transpose64_kernel<true, 2, 6, 0>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
+            else launch(rotate_transpose64_kernel<false, 2, 6, 0>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
         }
         return PPMX_LAUNCHED();
     }
