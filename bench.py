@@ -432,6 +432,49 @@ def band_split_ref_ops(torch, g, dist, rank, world, device, full=16384, iters=10
         else:
             ent.update({"halo_rows": halo, "out_mpix_s": round(mp * 1.5, 1)})
         results.append(ent)
+    # flipv / rot180: output band r is input band N-1-r upside down -- read it straight
+    # from that rank's HBM over NVLink (one launch, no copy); with one rank it is a local flip
+    mirror = world - 1 - rank
+    m_rows = rows
+    m_ptr = None
+    if world > 1:
+        m_rows = info[mirror][0]
+        if mirror == rank:
+            m_ptr = srcs
+        elif mirror in peers:
+            m_ptr = peers[mirror]
+        else:
+            m_ptr = [g.ipc_open(hd) for hd in info[mirror][1]]
+            peers[mirror] = m_ptr
+    else:
+        m_ptr = srcs
+    for label, op in (("flipv", pp.PpmxOp(kind=pp.OP_FLIP, flip_direction=1)), ("rot180", g.rotate_op(180, w, m_rows))):
+        def step(i):
+            g.launch(op, m_ptr[i & 1], w, m_rows, pp.LAYOUT_RGB8, dst, None, 0, 0, stream)
+        if m_rows * w * 3 > max(orows * w * 3, nbytes):
+            continue
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            dist.barrier()
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        mp = iters * full * full / (ms / 1e3) / 1e6
+        results.append({"workload": "%dx%d raster, %s (reference operator), row bands over %d GPU(s); a rank reads the "
+                                    "mirrored band from its owner's HBM over NVLink" % (full, full, label, world),
+                        "scaling": "strong", "mpix_s": round(mp, 1), "ms_per_raster": round(ms / iters, 4),
+                        "peer_read_gbs_per_gpu": round(3.0 * mp / 1e3 / world, 1) if world > 1 else None})
     for lst in peers.values():
         for p in lst:
             g.ipc_close(p)
