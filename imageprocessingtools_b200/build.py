@@ -48,10 +48,28 @@ def _run(cmd, verbose):
 
 def build_all(force: bool = False, verbose: bool = False) -> None:
     hdrs = [os.path.join(PKG, "..", "include", "ppmx_gpu.h"), os.path.join(PKG, "..", "include", "ppmx_host.h"),
-            os.path.join(CSRC, "ppmx_kernels.h")]
-    cu = [os.path.join(CSRC, "ppmx_kernels.cu"), os.path.join(CSRC, "ppmx_gpu.cu")]
+            os.path.join(CSRC, "ppmx_kernels.h"), os.path.join(CSRC, "ppmx_common.cuh")]
+    cu = [os.path.join(CSRC, f) for f in ("ppmx_color.cu", "ppmx_geometry.cu", "ppmx_bicubic.cu", "ppmx_conv.cu",
+                                          "ppmx_gpu.cu")]
     if force or _newer(GPU_SO, cu + hdrs):
-        _run([_nvcc()] + NVCC_FLAGS + ["-o", GPU_SO] + cu, verbose)
+        # one nvcc per translation unit, in parallel, then one link step
+        objdir = os.path.join(PKG, "build")
+        os.makedirs(objdir, exist_ok=True)
+        compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared", "-cudart", "static")]
+        procs = []
+        for src in cu:
+            obj = os.path.join(objdir, os.path.basename(src) + ".o")
+            cmd = [_nvcc()] + compile_flags + ["-c", "-o", obj, src]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            procs.append((subprocess.Popen(cmd), obj))
+        objs = []
+        for proc, obj in procs:
+            if proc.wait() != 0:
+                raise RuntimeError("nvcc failed for " + obj)
+            objs.append(obj)
+        _run([_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", GPU_SO] + objs,
+             verbose)
     host_c = os.path.join(CSRC, "ppmx_host.c")
     if force or _newer(HOST_SO, [host_c, GPU_SO] + hdrs):
         _run(["gcc"] + GCC_FLAGS + ["-shared", "-o", HOST_SO, host_c, "-L" + PKG, "-lppmx_gpu", "-lm",

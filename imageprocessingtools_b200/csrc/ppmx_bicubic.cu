@@ -1,0 +1,484 @@
+// ppmx_bicubic.cu -- the FP64 operators: bicubic rotate (ref:726-786) and the two imresize passes (ref:820-868), bit-exact.
+// Part of libppmx_gpu.so; see ppmx_common.cuh for conventions ("ref:N" = /root/reference/ppmx-edward.c line N).
+#include "ppmx_common.cuh"
+
+namespace ppmx {
+
+// ------------------------------------------------------------------------------------------
+// FP64 helpers: every operation is a separately rounded IEEE multiply or add, in the
+// reference's order; nvcc may not contract them (intrinsics) and the file is built -fmad=false.
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+// exact u8 -> double without the slow I2F.F64 path: 2^52 + v has v in its low mantissa bits
+__device__ __forceinline__ double u8_to_double(uint32_t v)
+{
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+
+// four u8 -> double conversions from one word.
+//   CONV 0: I2F.F64.U8 with a byte selector (cvt.rn.f64.u8 of the shifted word folds into it);
+//           XU pipe, measured 15.2 conversions/clk/SM (tools/dp_peak).
+//   CONV 1: the exact 2^52 trick: PRMT + one DADD on the FP64 pipe (64 inst/clk/SM).
+//   CONV 2: bytes 0 and 2 on the XU pipe, bytes 1 and 3 on the FP64 pipe, so neither pipe alone
+//           limits the K-tap loops (XU 16/clk vs FP64 64/clk at 2-3 DP instructions per tap byte).
+__device__ __forceinline__ double cvt_byte_xu(uint32_t shifted)
+{
+    double d;
+    asm("cvt.rn.f64.u8 %0, %1;" : "=d"(d) : "r"(shifted));
+    return d;
+}
+__device__ __forceinline__ double cvt_byte_dp(uint32_t w, int i)
+{
+    return __hiloint2double(0x43300000, (int)__byte_perm(w, 0, 0x4440 | i)) - 4503599627370496.0;
+}
+template <int CONV>
+__device__ __forceinline__ void word_to_double4(uint32_t w, double (&d)[4])
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const bool xu = (CONV == 0) || (CONV == 2 && (i & 1) == 0);
+        d[i] = xu ? cvt_byte_xu(w >> (8 * i)) : cvt_byte_dp(w, i);
+    }
+}
+
+// Keys cubic convolution kernel, a = -0.5 (ref:477-489), same association as the source
+__device__ __forceinline__ double cubic(double x)
+{
+    double a1 = fabs(x), a2 = dmul(a1, a1), a3 = dmul(a2, a1), r = 0.0;
+    if (a1 <= 1.0) r = dadd(dsub(dmul(1.5, a3), dmul(2.5, a2)), 1.0);
+    if (1.0 < a1 && a1 <= 2.0) {
+        double t = dadd(dmul(-0.5, a3), dmul(2.5, a2));
+        t = dsub(t, dmul(4.0, a1));
+        t = dadd(t, 2.0);
+        r = dadd(r, t);
+    }
+    return r;
+}
+
+__device__ __forceinline__ double round_half_up(double v) { return floor(dadd(v, 0.5)); }  // ref:27
+
+// ------------------------------------------------------------------------------------------
+// rotate, arbitrary angle  (ref:726-786): inverse map + 4x4 bicubic, nearest on a 2-pixel ring
+// ------------------------------------------------------------------------------------------
+
+// WORDS: w % 4 == 0 and an aligned raster -- the 12 bytes of a tap row come in as aligned words.
+template <bool WORDS, int CONV>
+__global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__restrict__ src,
+                                                             uint8_t *__restrict__ dst, uint32_t w, uint32_t h,
+                                                             uint32_t nw, uint32_t nh, double cs, double sn,
+                                                             int xc, int yc, int xo, int yo)
+{
+    PDL_PROLOGUE();
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nw || y >= nh) return;
+    uint8_t *out = dst + ((size_t)y * nw + x) * 3;
+
+    const int x0 = ((int)x - xo) - xc, y0 = ((int)y - yo) - yc;                              // ref:731-735
+    const double nX = dadd(dadd(dmul(cs, (double)x0), dmul(sn, (double)y0)), (double)xc);     // ref:741
+    const double nY = dadd(dadd(-dmul(sn, (double)x0), dmul(cs, (double)y0)), (double)yc);    // ref:742
+    const double rx = round_half_up(nX), ry = round_half_up(nY);
+
+    uint32_t r = 0, g = 0, b = 0;  // uncovered output stays 0 (ref:727)
+    if (rx < (double)w && ry < (double)h && ry >= 0.0 && rx >= 0.0) {                         // ref:744
+        if (rx > 1.0 && ry > 1.0 && rx < (double)(uint32_t)(w - 2u) && ry < (double)(uint32_t)(h - 2u)) {  // ref:752
+            const double fx = floor(nX), fy = floor(nY);
+            double wx[4], wy[4];
+            int u0 = (int)(fx - 1.0), v0 = (int)(fy - 1.0);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int u = (int)dadd(dsub(fx, 1.0), (double)i);  // ref:761
+                int v = (int)dadd(dsub(fy, 1.0), (double)i);  // ref:758
+                wx[i] = cubic(dsub(nX, (double)u));
+                wy[i] = cubic(dsub(nY, (double)v));
+            }
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+                if (WORDS) {
+                    const uint32_t b0 = 3u * (uint32_t)u0, sh = (b0 & 3u) * 8u;
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(src + (size_t)(v0 + j) * w * 3) + (b0 >> 2);
+                    const uint32_t q0w = __ldg(rw), q1w = __ldg(rw + 1), q2w = __ldg(rw + 2);
+                    const uint32_t q3w = (b0 & 3u) ? __ldg(rw + 3) : 0u;  // only needed when the run is unaligned
+                    double d[3][4];
+                    word_to_double4<CONV>(__funnelshift_r(q0w, q1w, sh), d[0]);
+                    word_to_double4<CONV>(__funnelshift_r(q1w, q2w, sh), d[1]);
+                    word_to_double4<CONV>(__funnelshift_r(q2w, q3w, sh), d[2]);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {  // ref:762-764
+                        p0 = dadd(p0, dmul(d[(3 * i) >> 2][(3 * i) & 3], wx[i]));
+                        p1 = dadd(p1, dmul(d[(3 * i + 1) >> 2][(3 * i + 1) & 3], wx[i]));
+                        p2 = dadd(p2, dmul(d[(3 * i + 2) >> 2][(3 * i + 2) & 3], wx[i]));
+                    }
+                } else {
+                    const uint8_t *row = src + ((size_t)(v0 + j) * w + u0) * 3;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {  // ref:762-764
+                        p0 = dadd(p0, dmul(u8_to_double(row[3 * i]), wx[i]));
+                        p1 = dadd(p1, dmul(u8_to_double(row[3 * i + 1]), wx[i]));
+                        p2 = dadd(p2, dmul(u8_to_double(row[3 * i + 2]), wx[i]));
+                    }
+                }
+                q0 = dadd(q0, dmul(p0, wy[j]));  // ref:766-768
+                q1 = dadd(q1, dmul(p1, wy[j]));
+                q2 = dadd(q2, dmul(p2, wy[j]));
+            }
+            if (q0 < 0.0) q0 = 0.0;  // ref:771-777
+            if (q1 < 0.0) q1 = 0.0;
+            if (q2 < 0.0) q2 = 0.0;
+            if (q0 >= 256.0) q0 = 255.0;
+            if (q1 >= 256.0) q1 = 255.0;
+            if (q2 >= 256.0) q2 = 255.0;
+            // truncation (ref:779-781) of a value in [0, 256): floor, as the low word of q + 1.5*2^52
+            r = (uint32_t)__double2loint(__dadd_rd(q0, 6755399441055744.0));
+            g = (uint32_t)__double2loint(__dadd_rd(q1, 6755399441055744.0));
+            b = (uint32_t)__double2loint(__dadd_rd(q2, 6755399441055744.0));
+        } else {  // nearest, ref:783
+            const uint8_t *p = src + ((size_t)(int)ry * w + (size_t)(int)rx) * 3;
+            r = p[0];
+            g = p[1];
+            b = p[2];
+        }
+    }
+    out[0] = (uint8_t)r;
+    out[1] = (uint8_t)g;
+    out[2] = (uint8_t)b;
+}
+
+cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t nw, uint32_t nh,
+                           double cos_t, double sin_t, cudaStream_t s)
+{
+    if (!nw || !nh) return cudaSuccess;
+    // centre and offset exactly as ref:694-698 (integer halves)
+    int xc = (int)(w / 2u), yc = (int)(h / 2u);
+    int xo = (int)(nw / 2u) - (int)(w / 2u), yo = (int)(nh / 2u) - (int)(h / 2u);
+    dim3 block(32, 8), grid((nw + 31) / 32, (nh + 7) / 8);
+    if (grid.y > 65535u) return cudaErrorInvalidValue;
+    if ((w % 4u) == 0 && aligned4(src) && g_variant != 1) {
+        if (g_variant == 2)
+            launch(rotate_bicubic_kernel<true, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+        else if (g_variant == 3)
+            launch(rotate_bicubic_kernel<true, 0>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+        else
+            launch(rotate_bicubic_kernel<true, 2>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+    } else {
+        launch(rotate_bicubic_kernel<false, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+    }
+    return PPMX_LAUNCHED();
+}
+
+
+// ------------------------------------------------------------------------------------------
+// imresize  (ref:820-838 height pass, ref:846-868 width pass): K-tap gather, FP64 accumulate
+// in tap order, floor(s + 0.5), clamp, u8 store.
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t quantise(double s)
+{
+    s = round_half_up(s);                                           // ref:831
+    return (s < 0.0) ? 0u : (s >= 256.0) ? 255u : (uint32_t)__double2int_rz(s);  // ref:835
+}
+
+// The same result with one DP add instead of FRND + compares + F2I: for |v| < 2^31,
+// v + 1.5*2^52 rounded toward -inf is floor(v) + 1.5*2^52 exactly and its low word is floor(v) as
+// an int32; "< 0 -> 0" and ">= 256 -> 255" on floor(v) (ref:835) become an integer clamp.
+__device__ __forceinline__ uint32_t quantise_fast(double s)
+{
+    const double v = dadd(s, 0.5);                                                // ref:27, 831
+    const int n = __double2loint(__dadd_rd(v, 6755399441055744.0));
+    return (uint32_t)min(max(n, 0), 255);
+}
+
+// height pass, fast path (row pitch % 16 == 0, aligned, K <= 64): one thread = 16 bytes of an
+// output row.  The row's K weights and source-row numbers are staged once per CTA in shared memory
+// so the K source loads of a thread are independent of each other and fly four at a time.
+constexpr int ROWS16_MAXK = 64;
+template <int CONV>
+__global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource src, uint8_t *__restrict__ dst,
+                                                              uint32_t row_vecs, int taps,
+                                                              const double *__restrict__ wts, const int *__restrict__ idx)
+{
+    PDL_PROLOGUE();
+    __shared__ double s_w[ROWS16_MAXK];
+    __shared__ int s_i[ROWS16_MAXK];
+    const int y = blockIdx.y;
+    if ((int)threadIdx.x < taps) {
+        s_w[threadIdx.x] = __ldg(wts + (size_t)y * taps + threadIdx.x);
+        s_i[threadIdx.x] = __ldg(idx + (size_t)y * taps + threadIdx.x);
+    }
+    __syncthreads();
+    const uint32_t xv = blockIdx.x * 256 + threadIdx.x;
+    if (xv >= row_vecs) return;
+    const size_t row_bytes = (size_t)row_vecs * 16;
+
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = 0.0;
+    for (int z0 = 0; z0 < taps; z0 += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (z0 + u < taps) v[u] = __ldg(reinterpret_cast<const uint4 *>(src.row_plain(s_i[z0 + u], row_bytes)) + xv);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {  // tap order is the reference's summation order (ref:826-830)
+            if (z0 + u >= taps) break;
+            const double wz = s_w[z0 + u];
+            const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double d[4];
+                word_to_double4<CONV>(wd[q], d);
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[4 * q + b] = dadd(acc[4 * q + b], dmul(d[b], wz));
+            }
+        }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        o[q] = quantise_fast(acc[4 * q]) | (quantise_fast(acc[4 * q + 1]) << 8) | (quantise_fast(acc[4 * q + 2]) << 16) |
+               (quantise_fast(acc[4 * q + 3]) << 24);
+    reinterpret_cast<uint4 *>(dst + (size_t)y * row_bytes)[xv] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// width pass, fast path (w % 4 == 0, aligned, 4 <= K <= 8): one thread = one output column for a
+// run of rows; its K weights and indices live in registers.  When the K taps are consecutive source
+// pixels (always, except where the table mirrors at the raster's edge) their 3K bytes are fetched as
+// aligned words and funnel-shifted into place; otherwise tap by tap.
+template <int K, int CONV>
+__global__ void __launch_bounds__(128) imresize_colsK_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                             uint32_t w, uint32_t h, int out_w, int rows_per_cta,
+                                                             const double *__restrict__ wts, const int *__restrict__ idx)
+{
+    PDL_PROLOGUE();
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    if (x >= out_w) return;
+    double wk[K];
+    int ik[K];
+#pragma unroll
+    for (int z = 0; z < K; z++) {
+        wk[z] = __ldg(wts + (size_t)x * K + z);
+        ik[z] = __ldg(idx + (size_t)x * K + z);
+    }
+    bool consecutive = true;
+#pragma unroll
+    for (int z = 1; z < K; z++) consecutive = consecutive && (ik[z] == ik[0] + z);
+    constexpr int NS = (3 * K + 3) / 4;  // words of the aligned 3K-byte stream
+    const uint32_t b0 = 3u * (uint32_t)ik[0], w0 = b0 >> 2, sh = (b0 & 3u) * 8u;
+    const uint32_t y0 = blockIdx.y * (uint32_t)rows_per_cta, y1 = min(h, y0 + (uint32_t)rows_per_cta);
+    const size_t in_pitch = (size_t)w * 3, out_pitch = (size_t)out_w * 3;
+    if (consecutive) {
+        // the words of row y+1 are requested before row y is evaluated
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(src + (size_t)y0 * in_pitch) + w0;
+        const size_t pitch_words = in_pitch / 4;
+        uint32_t q[NS + 1], qn[NS + 1];
+#pragma unroll
+        for (int j = 0; j <= NS; j++)  // word j is needed iff it starts before the last tap byte
+            q[j] = (y0 < y1 && 4u * j < (b0 & 3u) + 3u * K) ? __ldg(rw + j) : 0u;
+        for (uint32_t y = y0; y < y1; y++) {
+            rw += pitch_words;
+#pragma unroll
+            for (int j = 0; j <= NS; j++) qn[j] = (y + 1 < y1 && 4u * j < (b0 & 3u) + 3u * K) ? __ldg(rw + j) : 0u;
+            double d[NS][4];
+#pragma unroll
+            for (int j = 0; j < NS; j++) word_to_double4<CONV>(__funnelshift_r(q[j], q[j + 1], sh), d[j]);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int z = 0; z < K; z++) {  // ref:852-858, tap order
+                s0 = dadd(s0, dmul(d[(3 * z) >> 2][(3 * z) & 3], wk[z]));
+                s1 = dadd(s1, dmul(d[(3 * z + 1) >> 2][(3 * z + 1) & 3], wk[z]));
+                s2 = dadd(s2, dmul(d[(3 * z + 2) >> 2][(3 * z + 2) & 3], wk[z]));
+            }
+            uint8_t *o = dst + (size_t)y * out_pitch + (size_t)x * 3;
+            o[0] = (uint8_t)quantise_fast(s0);
+            o[1] = (uint8_t)quantise_fast(s1);
+            o[2] = (uint8_t)quantise_fast(s2);
+#pragma unroll
+            for (int j = 0; j <= NS; j++) q[j] = qn[j];
+        }
+    } else {
+        for (uint32_t y = y0; y < y1; y++) {
+            const uint8_t *row = src + (size_t)y * in_pitch;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int z = 0; z < K; z++) {
+                const uint8_t *p = row + (size_t)ik[z] * 3;
+                s0 = dadd(s0, dmul(u8_to_double(p[0]), wk[z]));
+                s1 = dadd(s1, dmul(u8_to_double(p[1]), wk[z]));
+                s2 = dadd(s2, dmul(u8_to_double(p[2]), wk[z]));
+            }
+            uint8_t *o = dst + (size_t)y * out_pitch + (size_t)x * 3;
+            o[0] = (uint8_t)quantise_fast(s0);
+            o[1] = (uint8_t)quantise_fast(s1);
+            o[2] = (uint8_t)quantise_fast(s2);
+        }
+    }
+}
+
+template <int K>
+static void launch_colsK(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int out_w, const double *wts,
+                         const int *idx, cudaStream_t s)
+{
+    const int rows_per_cta = 16;
+    for (uint32_t y0 = 0; y0 < h; y0 += 65535u * rows_per_cta) {
+        uint32_t rows = min(65535u * rows_per_cta, h - y0);
+        dim3 grid((out_w + 127) / 128, (rows + rows_per_cta - 1) / rows_per_cta);
+        if (g_variant == 2)
+            launch(imresize_colsK_kernel<K, 1>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
+                   dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
+        else if (g_variant == 3)
+            launch(imresize_colsK_kernel<K, 0>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
+                   dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
+        else
+            launch(imresize_colsK_kernel<K, 2>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
+                   dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
+    }
+}
+
+// height pass: every byte of an output row uses the same K source rows and weights, so the
+// raster is treated as rows of 3*w independent bytes; VEC bytes per thread.
+template <int VEC>
+__global__ void __launch_bounds__(256) imresize_rows_kernel(const RowSource src, uint8_t *__restrict__ dst,
+                                                            uint32_t row_bytes, int out_h, int taps,
+                                                            const double *__restrict__ wts, const int *__restrict__ idx)
+{
+    PDL_PROLOGUE();
+    const uint32_t xb = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const int y = blockIdx.y;
+    if (xb >= row_bytes || y >= out_h) return;
+    const double *wy = wts + (size_t)y * taps;
+    const int *iy = idx + (size_t)y * taps;
+    double acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) acc[v] = 0.0;
+    for (int z = 0; z < taps; z++) {
+        const double wz = __ldg(wy + z);
+        const uint8_t *p = src.row_plain(__ldg(iy + z), row_bytes) + xb;
+        if (VEC == 4) {
+            uint32_t v4 = __ldg(reinterpret_cast<const uint32_t *>(p));
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[v] = dadd(acc[v], dmul(u8_to_double((v4 >> (8 * v)) & 0xFFu), wz));
+        } else {
+            acc[0] = dadd(acc[0], dmul(u8_to_double(p[0]), wz));
+        }
+    }
+    uint8_t *o = dst + (size_t)y * row_bytes + xb;
+    if (VEC == 4) {
+        uint32_t v4 = quantise(acc[0]) | (quantise(acc[1]) << 8) | (quantise(acc[2]) << 16) | (quantise(acc[3]) << 24);
+        *reinterpret_cast<uint32_t *>(o) = v4;
+    } else {
+        o[0] = (uint8_t)quantise(acc[0]);
+    }
+}
+
+// width pass: one thread = one output pixel; taps gather 3-byte pixels along the row
+__global__ void __launch_bounds__(256) imresize_cols_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                            uint32_t w, uint32_t h, int out_w, int taps,
+                                                            const double *__restrict__ wts, const int *__restrict__ idx)
+{
+    PDL_PROLOGUE();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out_w || y >= h) return;
+    const double *wx = wts + (size_t)x * taps;
+    const int *ix = idx + (size_t)x * taps;
+    const uint8_t *row = src + (size_t)y * w * 3;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int z = 0; z < taps; z++) {
+        const double wz = __ldg(wx + z);
+        const uint8_t *p = row + (size_t)__ldg(ix + z) * 3;
+        s0 = dadd(s0, dmul(u8_to_double(p[0]), wz));
+        s1 = dadd(s1, dmul(u8_to_double(p[1]), wz));
+        s2 = dadd(s2, dmul(u8_to_double(p[2]), wz));
+    }
+    uint8_t *o = dst + ((size_t)y * out_w + x) * 3;
+    o[0] = (uint8_t)quantise(s0);
+    o[1] = (uint8_t)quantise(s1);
+    o[2] = (uint8_t)quantise(s2);
+}
+
+cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t h, int out_size, int dim, int taps,
+                     const double *d_weights, const int *d_indices, const Band &band, cudaStream_t s)
+{
+    if (out_size <= 0 || !w || !h) return cudaSuccess;
+    if (dim == 0) {
+        // a band computes output rows [out_y0, out_y0 + out_rows) from its own source rows plus halos
+        const RowSource src = make_row_source(src_ptr, h, band);
+        if (band.full_h) {
+            if (band.out_y0 + band.out_rows > (uint32_t)out_size) return cudaErrorInvalidValue;
+            d_weights += (size_t)band.out_y0 * taps;
+            d_indices += (size_t)band.out_y0 * taps;
+            out_size = (int)band.out_rows;
+            if (out_size <= 0) return cudaSuccess;
+        }
+        const bool halo_ok = (!band.top || aligned16(band.top)) && (!band.bottom || aligned16(band.bottom));
+        uint32_t row_bytes = w * 3u;
+        if (row_bytes % 16 == 0 && aligned16(src_ptr) && aligned16(dst) && halo_ok && taps <= ROWS16_MAXK && g_variant != 1) {
+            dim3 grid((row_bytes / 16 + 255) / 256, 1);
+            for (int y0 = 0; y0 < out_size; y0 += 65535) {
+                int rows = min(65535, out_size - y0);
+                grid.y = rows;
+                if (g_variant == 2)
+                    launch(imresize_rows16_kernel<1>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
+                           taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+                else if (g_variant == 3)
+                    launch(imresize_rows16_kernel<0>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
+                           taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+                else
+                    launch(imresize_rows16_kernel<2>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
+                           taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+            }
+            return cudaGetLastError();
+        }
+        if (row_bytes % 4 == 0 && aligned4(src_ptr) && aligned4(dst) && halo_ok) {
+            dim3 grid((row_bytes / 4 + 255) / 256, 1);
+            // rows go on grid.y in slabs of <= 65535
+            for (int y0 = 0; y0 < out_size; y0 += 65535) {
+                int rows = min(65535, out_size - y0);
+                grid.y = rows;
+                launch(imresize_rows_kernel<4>, dim3(grid), dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes, rows, taps,
+                                                             d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+                            }
+        } else {
+            dim3 grid((row_bytes + 255) / 256, 1);
+            for (int y0 = 0; y0 < out_size; y0 += 65535) {
+                int rows = min(65535, out_size - y0);
+                grid.y = rows;
+                launch(imresize_rows_kernel<1>, dim3(grid), dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes, rows, taps,
+                                                             d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+                            }
+        }
+        return cudaGetLastError();
+    }
+    const uint8_t *src = src_ptr;
+    if ((w % 4u) == 0 && aligned4(src) && taps >= 4 && taps <= 8 && g_variant != 1) {
+        switch (taps) {
+        case 4: launch_colsK<4>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
+        case 5: launch_colsK<5>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
+        case 6: launch_colsK<6>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
+        case 7: launch_colsK<7>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
+        default: launch_colsK<8>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
+        }
+        return cudaGetLastError();
+    }
+    dim3 block(64, 4), grid((out_size + 63) / 64, (h + 3) / 4);
+    if (grid.y > 65535u) {
+        for (uint32_t y0 = 0; y0 < h; y0 += 65535u * 4u) {
+            uint32_t rows = min(65535u * 4u, h - y0);
+            dim3 g2(grid.x, (rows + 3) / 4);
+            launch(imresize_cols_kernel, dim3(g2), dim3(block), 0, s, src + (size_t)y0 * w * 3, dst + (size_t)y0 * out_size * 3, w, rows,
+                                                     out_size, taps, d_weights, d_indices);
+                    }
+        return cudaGetLastError();
+    }
+    launch(imresize_cols_kernel, dim3(grid), dim3(block), 0, s, src, dst, w, h, out_size, taps, d_weights, d_indices);
+    return PPMX_LAUNCHED();
+}
+
+
+}  // namespace ppmx

@@ -1,0 +1,186 @@
+// ppmx_common.cuh -- shared by the kernel translation units: the PDL launch helper, alignment and
+// grid helpers, the integer building blocks (exact /3, 4-pixel grey sums, Bayer thresholds) and the
+// row resolver for banded rasters.  "ref:N" = /root/reference/ppmx-edward.c line N.
+//
+// Rasters are flat, packed, row-major: RGB8 = 3 bytes per pixel (the reference's `pixel`,
+// ref:39-43), R8 = the .r member only.  Everything integer is done in integers; the two bicubic
+// operators run in FP64 with explicit round-to-nearest multiplies and adds (never an FMA) in the
+// reference's order.  Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
+#pragma once
+
+#include "ppmx_kernels.h"
+
+#include <cuda.h>
+
+namespace ppmx {
+
+extern unsigned long long g_launches;
+
+static int g_sm_count = 0;
+static inline int sm_count()
+{
+    if (!g_sm_count) {  // every device a process sees in this pool is the same B200 part
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
+            g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+#define PPMX_LAUNCHED() (cudaGetLastError())
+
+// Programmatic dependent launch (sm_90+): every kernel in this file starts with pdl_wait(), so a
+// launch may be scheduled while its predecessor in the stream is still draining; only index
+// arithmetic runs before the wait, all global-memory traffic after it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define PDL_PROLOGUE() \
+    do {               \
+        pdl_trigger(); \
+        pdl_wait();    \
+    } while (0)
+
+// opt in to > 48 KB dynamic shared memory once per (kernel, device)
+template <typename K>
+static void allow_smem(K kernel, size_t bytes, bool (&done)[64])
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || done[dev]) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    done[dev] = true;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ++g_launches;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned4(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+// grid size for a grid-stride kernel: whole waves of the 148 SMs, capped by the work
+static inline unsigned wave_grid(size_t work_items, unsigned block, unsigned ctas_per_sm)
+{
+    size_t need = (work_items + block - 1) / block;
+    size_t wave = (size_t)sm_count() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (unsigned)(need < wave ? need : wave);
+}
+
+// ------------------------------------------------------------------------------------------
+// integer helpers
+// ------------------------------------------------------------------------------------------
+
+// s / 3 for 0 <= s <= 765, exact (checked exhaustively in tests/test_host_logic.py)
+__device__ __forceinline__ uint32_t div3(uint32_t s) { return (s * 43691u) >> 17; }
+// (one multiply-high, __umulhi(s, 0x55555556), is also exact but measured 10% slower: IMAD.HI
+// is not a full-rate instruction)
+
+// greys of 4 consecutive pixels held in 3 little-endian words (12 bytes r0 g0 b0 r1 ...), ref:1000
+__device__ __forceinline__ void gray4_split(uint32_t a, uint32_t b, uint32_t c, uint32_t (&q)[4])
+{
+    q[0] = div3(__dp4a(a, 0x00010101u, 0u));
+    q[1] = div3(__dp4a(a, 0x01000000u, __dp4a(b, 0x00000101u, 0u)));
+    q[2] = div3(__dp4a(b, 0x01010000u, __dp4a(c, 0x00000001u, 0u)));
+    q[3] = div3(__dp4a(c, 0x01010100u, 0u));
+}
+__device__ __forceinline__ uint32_t pack4(const uint32_t (&q)[4])
+{  // one byte per pixel, pixel 0 in the low byte
+    return __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+}
+__device__ __forceinline__ uint32_t gray4(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t q[4];
+    gray4_split(a, b, c, q);
+    return pack4(q);
+}
+
+// 16 pixels = 48 bytes = three 16-byte vectors -> 16 grey bytes
+__device__ __forceinline__ uint4 gray16(uint4 p, uint4 q, uint4 r)
+{
+    uint4 o;
+    o.x = gray4(p.x, p.y, p.z);
+    o.y = gray4(p.w, q.x, q.y);
+    o.z = gray4(q.z, q.w, r.x);
+    o.w = gray4(r.y, r.z, r.w);
+    return o;
+}
+
+// Bayer thresholds of ref:954 times 255 (all exact), in the reference's own index order
+// (x%4)*4 + (y%4), ref:967.  bit = grey < threshold  <=>  !(grey >= matrix*255).
+static __constant__ uint8_t c_bayer[16] = {32, 255, 48, 208, 160, 96, 176, 112, 64, 224, 16, 240, 192, 128, 144, 80};
+
+// thresholds for 4 consecutive pixels starting at x % 4 == 0 on row y, packed like gray4's result
+__device__ __forceinline__ uint32_t bayer_row4(uint32_t y)
+{
+    uint32_t yy = y & 3u;
+    return (uint32_t)c_bayer[yy] | ((uint32_t)c_bayer[4 + yy] << 8) | ((uint32_t)c_bayer[8 + yy] << 16) |
+           ((uint32_t)c_bayer[12 + yy] << 24);
+}
+
+// 4 packed greys vs 4 packed thresholds -> nibble, pixel 0 in bit 3 (MSB first, ref:273)
+__device__ __forceinline__ uint32_t mono_nibble(uint32_t g4, uint32_t t4)
+{
+    uint32_t m = __vcmpltu4(g4, t4) & 0x01010101u;  // byte i = 1 iff grey_i < thr_i
+    return ((m * 0x08040201u) >> 24) & 0xFu;        // b0<<3 | b1<<2 | b2<<1 | b3
+}
+
+// ---- rows of a raster that may be spread over a band and its neighbours' halos ----------------
+__host__ __device__ __forceinline__ int mirror_index(int i, int n)
+{
+    int m = i % (2 * n);
+    if (m < 0) m += 2 * n;
+    return m < n ? m : 2 * n - 1 - m;
+}
+
+// resolves a row of the WHOLE raster to memory: own band, halo above, halo below (maybe peer HBM)
+struct RowSource {
+    const uint8_t *own, *top, *bottom;
+    int y0, h, halo, full_h;
+    __device__ __forceinline__ const uint8_t *row(int gy, size_t pitch) const
+    {
+        gy = mirror_index(gy, full_h);
+        if (gy >= y0 && gy < y0 + h) return own + (size_t)(gy - y0) * pitch;
+        if (gy < y0) return top + (size_t)(gy - (y0 - halo)) * pitch;
+        return bottom + (size_t)(gy - (y0 + h)) * pitch;
+    }
+    // the same without the mirror step, for row numbers that are already inside the raster
+    __device__ __forceinline__ const uint8_t *row_plain(int gy, size_t pitch) const
+    {
+        if (gy >= y0 && gy < y0 + h) return own + (size_t)(gy - y0) * pitch;
+        if (gy < y0) return top + (size_t)(gy - (y0 - halo)) * pitch;
+        return bottom + (size_t)(gy - (y0 + h)) * pitch;
+    }
+};
+
+static inline RowSource make_row_source(const uint8_t *src, uint32_t h, const Band &band)
+{
+    RowSource rs;
+    rs.own = src;
+    rs.top = band.top;
+    rs.bottom = band.bottom;
+    rs.y0 = band.full_h ? (int)band.y0 : 0;
+    rs.h = (int)h;
+    rs.halo = (int)band.halo;
+    rs.full_h = band.full_h ? (int)band.full_h : (int)h;
+    return rs;
+}
+
+
+
+
+}  // namespace ppmx

@@ -1,0 +1,279 @@
+// ppmx_conv.cu -- EXTENSION (no reference counterpart, parity unpinned): k x k integer convolution with mirror border and row-band halos.
+// Part of libppmx_gpu.so; see ppmx_common.cuh for conventions ("ref:N" = /root/reference/ppmx-edward.c line N).
+#include "ppmx_common.cuh"
+
+namespace ppmx {
+
+// ------------------------------------------------------------------------------------------
+// EXTENSION (no reference counterpart, parity unpinned): k x k integer convolution.
+// Border = symmetric mirror (the aux-table idiom of ref:551-555,589); result =
+// floor(acc/div + 0.5) + bias computed in integers, clamped like ref:835.  Integer sums are
+// exact in any order, so the fast kernel may regroup taps freely and still match the self-oracle.
+// ------------------------------------------------------------------------------------------
+
+constexpr int CONV_MAXK = 15;
+
+// exact floor((2*acc + div) / (2*div)) + bias with one multiply-high: the numerator is shifted to
+// be non-negative by a multiple K of the divisor d = 2*div, then n/d = (n * M) >> (31 + l) for all
+// n < 2^31 with l = ceil(log2 d), M = ceil(2^(31+l) / d)  (Granlund & Montgomery, N = 31).
+struct ConvRound {
+    uint32_t M, shift;  // shift = l - 1, applied to the high word of n * M
+    int32_t add, K, bias;  // n = 2*acc + add, add = div + d*K
+    int32_t pow2;          // d is a power of two: a plain shift by l replaces the multiply-high
+    __device__ __forceinline__ int32_t quotient(int32_t acc) const  // before the 0..255 clamp
+    {
+        uint32_t n = (uint32_t)(2 * acc + add);
+        uint32_t qn = pow2 ? (n >> (shift + 1)) : (__umulhi(n, M) >> shift);
+        return (int32_t)qn - K + bias;
+    }
+    __device__ __forceinline__ uint32_t operator()(int32_t acc) const { return (uint32_t)min(max(quotient(acc), 0), 255); }
+    // four results clamped to 0..255 and packed, result 0 in the low byte: two I2IP instructions
+    __device__ __forceinline__ uint32_t pack4(int32_t a0, int32_t a1, int32_t a2, int32_t a3) const
+    {
+        uint32_t hi, out;
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(quotient(a3)), "r"(quotient(a2)), "r"(0));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(quotient(a1)), "r"(quotient(a0)), "r"(hi));
+        return out;
+    }
+};
+
+static bool make_conv_round(int64_t sum_abs, int32_t div, int32_t bias, ConvRound *r)
+{
+    const uint64_t d = 2ull * (uint64_t)div;
+    int l = 0;
+    while ((1ull << l) < d) l++;
+    if (l < 1 || l > 30) return false;
+    const uint64_t K = (2ull * 255ull * (uint64_t)sum_abs + d - 1) / d + 1;  // makes every numerator >= 0
+    const uint64_t nmax = 2ull * 255ull * (uint64_t)sum_abs + (uint64_t)div + d * K;
+    if (nmax >= (1ull << 31) || K >= (1ull << 30)) return false;
+    const unsigned __int128 pw = (unsigned __int128)1 << (31 + l);
+    r->M = (uint32_t)((pw + d - 1) / d);
+    r->shift = (uint32_t)(l - 1);
+    r->add = (int32_t)((uint64_t)div + d * K);
+    r->K = (int32_t)K;
+    r->bias = bias;
+    r->pow2 = ((d & (d - 1)) == 0) ? 1 : 0;
+    return true;
+}
+
+// ---- generic kernel: any odd k <= 15, any coefficients, any width; scalar MACs ---------------
+struct ConvCoefGeneric {
+    int32_t c[CONV_MAXK * CONV_MAXK];
+};
+constexpr int CONV_TW = 64;  // output tile: 64 pixels x 16 rows per CTA
+constexpr int CONV_TH = 16;
+
+__global__ void __launch_bounds__(256) conv_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t w, int k,
+                                                   int32_t div, int32_t bias, const ConvCoefGeneric cf)
+{
+    PDL_PROLOGUE();
+    extern __shared__ uint8_t tile[];  // (CONV_TH + k - 1) rows x (CONV_TW + k - 1) pixels x 3
+    const int r = k / 2, tw = CONV_TW + k - 1, th = CONV_TH + k - 1, tpitch = tw * 3;
+    const int tx0 = blockIdx.x * CONV_TW, ty0 = blockIdx.y * CONV_TH;  // band-local output origin
+    const size_t pitch = (size_t)w * 3;
+
+    for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
+        int ty = i / tw, tx = i - ty * tw;
+        int gx = mirror_index(tx0 + tx - r, (int)w);
+        const uint8_t *p = rs.row(rs.y0 + ty0 + ty - r, pitch) + (size_t)gx * 3;
+        uint8_t *t = tile + ty * tpitch + tx * 3;
+        t[0] = p[0];
+        t[1] = p[1];
+        t[2] = p[2];
+    }
+    __syncthreads();
+
+    for (int i = threadIdx.x; i < CONV_TH * CONV_TW * 3; i += blockDim.x) {
+        int ty = i / (CONV_TW * 3), b = i - ty * (CONV_TW * 3);
+        int x = tx0 + b / 3, y = ty0 + ty;
+        if (x >= (int)w || y >= rs.h) continue;
+        long long acc = 0;
+        for (int dy = 0; dy < k; dy++) {
+            const uint8_t *t = tile + (ty + dy) * tpitch + b;
+            for (int dx = 0; dx < k; dx++) acc += (long long)cf.c[dy * k + dx] * (int)t[dx * 3];
+        }
+        // floor((2*acc + div) / (2*div)) for div > 0
+        long long num = 2 * acc + div, den = 2 * (long long)div, q = num / den;
+        if ((num % den != 0) && (num < 0)) q--;
+        q += bias;
+        dst[(size_t)y * pitch + (size_t)tx0 * 3 + b] = (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q);
+    }
+}
+
+// ---- fast kernel: k in {3,5,7}, coefficients in [-128,127], w % 16 == 0, aligned rasters ------
+// The tile is de-interleaved into three byte planes in shared memory, so horizontally adjacent taps
+// of one channel are adjacent bytes and four of them feed one dp4a.  A thread produces 4 pixels x
+// FC_RV rows x 3 channels.  Instead of shifting data to the tap window, the COEFFICIENTS are
+// pre-shifted: for output j (0..3) of a 4-pixel word and source word wi (left, centre, right),
+// cw[dy][j][wi] holds the 4 coefficients that multiply that word's bytes (0 where a tap does not
+// reach).  Words that are all zero for a given (j, wi) are skipped at compile time.
+constexpr int FC_TW = 128, FC_TH = 32, FC_RV = 4;
+constexpr int FC_PITCH = FC_TW + 32;  // one 16-pixel group of halo on each side
+
+// unsigned pixel bytes times signed coefficient bytes (the CUDA intrinsic has no mixed form)
+__device__ __forceinline__ int32_t dp4a_u8s8(uint32_t px4, uint32_t coef4, int32_t acc)
+{
+    int32_t d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px4), "r"(coef4), "r"(acc));
+    return d;
+}
+
+template <int K>
+struct ConvCoefPacked {
+    uint32_t cw[K][4][3];
+};
+
+template <int K>
+__device__ __forceinline__ constexpr bool fc_reaches(int j, int wi)
+{
+    // does any byte b of source word wi (pixels 4(wi-1)+b relative to x) lie within K/2 of output j
+    for (int b = 0; b < 4; b++) {
+        int dx = 4 * (wi - 1) + b - j;
+        if (dx >= -(K / 2) && dx <= K / 2) return true;
+    }
+    return false;
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) conv_dp4a_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t w,
+                                                        const ConvCoefPacked<K> cf, const ConvRound rnd)
+{
+    PDL_PROLOGUE();
+    constexpr int R = K / 2, IN_ROWS = FC_TH + K - 1;
+    __shared__ __align__(16) uint8_t plane[3][IN_ROWS][FC_PITCH];
+    const int tx0 = blockIdx.x * FC_TW, ty0 = blockIdx.y * FC_TH;
+    const size_t pitch = (size_t)w * 3;
+
+    // ---- stage: 16-pixel groups, IN_ROWS x (FC_PITCH / 16) of them ----
+    constexpr int GROUPS_X = FC_PITCH / 16;
+    for (int i = threadIdx.x; i < IN_ROWS * GROUPS_X; i += 256) {
+        const int ty = i / GROUPS_X, gx = i - ty * GROUPS_X;
+        const int x0 = tx0 - 16 + 16 * gx;  // first source pixel of the group (may be outside the raster)
+        const uint8_t *row = rs.row(rs.y0 + ty0 + ty - R, pitch);
+        if (x0 >= 0 && x0 + 16 <= (int)w) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(row + (size_t)x0 * 3);
+            const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+            const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+            uint32_t pr[4], pg[4], pb[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // 4 pixels (3 words) -> one word per plane
+                const uint32_t u = wd[3 * q], v = wd[3 * q + 1], t = wd[3 * q + 2];
+                pr[q] = __byte_perm(__byte_perm(u, v, 0x0630), t, 0x5210);  // u0 u3 v2 | t1
+                pg[q] = __byte_perm(__byte_perm(u, v, 0x0741), t, 0x6210);  // u1 v0 v3 | t2
+                pb[q] = __byte_perm(__byte_perm(u, v, 0x0052), t, 0x7410);  // u2 v1 | t0 t3
+            }
+            *reinterpret_cast<uint4 *>(&plane[0][ty][16 * gx]) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+            *reinterpret_cast<uint4 *>(&plane[1][ty][16 * gx]) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+            *reinterpret_cast<uint4 *>(&plane[2][ty][16 * gx]) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+        } else {  // raster edge: mirrored columns, pixel by pixel
+            for (int q = 0; q < 16; q++) {
+                const uint8_t *p = row + (size_t)mirror_index(x0 + q, (int)w) * 3;
+                plane[0][ty][16 * gx + q] = p[0];
+                plane[1][ty][16 * gx + q] = p[1];
+                plane[2][ty][16 * gx + q] = p[2];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- compute: thread = 4 pixels x FC_RV rows x 3 channels ----
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // 32 x 8 threads
+    const int x = tx0 + 4 * lx, oy0 = ly * FC_RV;
+    if (x >= (int)w) return;
+    uint32_t outw[FC_RV][3];  // per output row: 4 result bytes of r, g, b
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        int32_t acc[FC_RV][4];
+#pragma unroll
+        for (int a = 0; a < FC_RV; a++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[a][j] = 0;
+#pragma unroll
+        for (int iy = 0; iy < FC_RV + K - 1; iy++) {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(&plane[ch][oy0 + iy][0]) + 3 + lx;
+            const uint32_t wsrc[3] = {rw[0], rw[1], rw[2]};  // pixels x-4..x-1, x..x+3, x+4..x+7
+#pragma unroll
+            for (int a = 0; a < FC_RV; a++) {
+                const int dy = iy - a;
+                if (dy < 0 || dy >= K) continue;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int wi = 0; wi < 3; wi++)
+                        if (fc_reaches<K>(j, wi)) acc[a][j] = dp4a_u8s8(wsrc[wi], cf.cw[dy][j][wi], acc[a][j]);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < FC_RV; a++)
+            outw[a][ch] = rnd.pack4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    }
+#pragma unroll
+    for (int a = 0; a < FC_RV; a++) {
+        const int y = ty0 + oy0 + a;
+        if (y >= rs.h) break;
+        const uint32_t r4 = outw[a][0], g4 = outw[a][1], b4 = outw[a][2];
+        // re-interleave 4 pixels: r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+        const uint32_t o0 = __byte_perm(__byte_perm(r4, g4, 0x1040), b4, 0x3410);
+        const uint32_t o1 = __byte_perm(__byte_perm(g4, b4, 0x0051), __byte_perm(r4, g4, 0x0062), 0x5410);
+        const uint32_t o2 = __byte_perm(__byte_perm(b4, r4, 0x0072), __byte_perm(g4, b4, 0x0073), 0x5410);
+        uint32_t *o = reinterpret_cast<uint32_t *>(dst + (size_t)y * pitch + (size_t)x * 3);
+        o[0] = o0;
+        o[1] = o1;
+        o[2] = o2;
+    }
+}
+
+template <int K>
+static cudaError_t conv_fast(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef,
+                             const ConvRound &rnd, cudaStream_t s)
+{
+    ConvCoefPacked<K> cf;
+    for (int dy = 0; dy < K; dy++)
+        for (int j = 0; j < 4; j++)
+            for (int wi = 0; wi < 3; wi++) {
+                uint32_t word = 0;
+                for (int b = 0; b < 4; b++) {
+                    int dx = 4 * (wi - 1) + b - j;
+                    if (dx >= -(K / 2) && dx <= K / 2)
+                        word |= (uint32_t)(uint8_t)(int8_t)coef[dy * K + dx + K / 2] << (8 * b);
+                }
+                cf.cw[dy][j][wi] = word;
+            }
+    dim3 grid((w + FC_TW - 1) / FC_TW, (h + FC_TH - 1) / FC_TH);
+    if (grid.y > 65535u) return cudaErrorInvalidValue;
+    launch(conv_dp4a_kernel<K>, grid, dim3(256), 0, s, rs, dst, w, cf, rnd);
+    return PPMX_LAUNCHED();
+}
+
+cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef, int32_t div,
+                 int32_t bias, const Band &band, cudaStream_t s)
+{
+    if (k < 1 || k > CONV_MAXK || !(k & 1) || div < 1) return cudaErrorInvalidValue;
+    if (!w || !h) return cudaSuccess;
+    const RowSource rs = make_row_source(src, h, band);
+
+    bool s8 = true;
+    int64_t sum_abs = 0;
+    for (int i = 0; i < k * k; i++) {
+        if (coef[i] < -128 || coef[i] > 127) s8 = false;
+        sum_abs += coef[i] < 0 ? -(int64_t)coef[i] : coef[i];
+    }
+    ConvRound rnd;
+    if (s8 && (k == 3 || k == 5 || k == 7) && (w % 16u) == 0 && aligned16(src) && aligned4(dst) &&
+        (!band.top || aligned16(band.top)) && (!band.bottom || aligned16(band.bottom)) && g_variant != 1 &&
+        make_conv_round(sum_abs, div, bias, &rnd)) {
+        if (k == 3) return conv_fast<3>(rs, dst, w, h, coef, rnd, s);
+        if (k == 5) return conv_fast<5>(rs, dst, w, h, coef, rnd, s);
+        return conv_fast<7>(rs, dst, w, h, coef, rnd, s);
+    }
+    ConvCoefGeneric cf;
+    for (int i = 0; i < CONV_MAXK * CONV_MAXK; i++) cf.c[i] = i < k * k ? coef[i] : 0;
+    dim3 grid((w + CONV_TW - 1) / CONV_TW, (h + CONV_TH - 1) / CONV_TH);
+    if (grid.y > 65535u) return cudaErrorInvalidValue;
+    size_t smem = (size_t)(CONV_TH + k - 1) * (CONV_TW + k - 1) * 3;
+    launch(conv_kernel, dim3(grid), dim3(256), smem, s, rs, dst, w, k, div, bias, cf);
+    return PPMX_LAUNCHED();
+}
+
+
+}  // namespace ppmx

@@ -144,7 +144,7 @@ def test_cli_flag_errors_match_reference(pp, tmp_path):
 
 
 def test_conv_rounding_magic():
-    """The convolution's exact floor((2*acc+div)/(2*div)) via one multiply-high (ppmx_kernels.cu
+    """The convolution's exact floor((2*acc+div)/(2*div)) via one multiply-high (ppmx_conv.cu
     make_conv_round / ConvRound): n/d == (n*M) >> (31+l) for all 0 <= n < 2^31."""
     rng = np.random.default_rng(0)
     for div in [1, 2, 3, 7, 9, 16, 25, 49, 81, 100, 255, 256, 1000, 4096, 65535, 12345678]:
