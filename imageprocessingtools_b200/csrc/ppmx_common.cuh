@@ -142,6 +142,7 @@ __device__ __forceinline__ uint32_t mono_nibble(uint32_t g4, uint32_t t4)
 // ---- rows of a raster that may be spread over a band and its neighbours' halos ----------------
 __host__ __device__ __forceinline__ int mirror_index(int i, int n)
 {
+    if ((unsigned)i < (unsigned)n) return i;  // inside the raster: the common case costs one compare
     int m = i % (2 * n);
     if (m < 0) m += 2 * n;
     return m < n ? m : 2 * n - 1 - m;

@@ -16,23 +16,30 @@ constexpr int CONV_MAXK = 15;
 // exact floor((2*acc + div) / (2*div)) + bias with one multiply-high: the numerator is shifted to
 // be non-negative by a multiple K of the divisor d = 2*div, then n/d = (n * M) >> (31 + l) for all
 // n < 2^31 with l = ceil(log2 d), M = ceil(2^(31+l) / d)  (Granlund & Montgomery, N = 31).
+//
+// Two cheaper modes, chosen at compile time, fold the constants into the accumulator's START value (the first
+// dp4a adds it for free): MODE 0, div == 1: start = bias, result = acc.  MODE 1, div = 2^m (m >= 1):
+// floor((2*acc + div) / (2*div)) + bias = (acc + div/2 + bias*div) >> m with an arithmetic shift, so
+// start = div/2 + bias*div and the result is one shift.  MODE 2 is the general multiply-high form.
 struct ConvRound {
     uint32_t M, shift;  // shift = l - 1, applied to the high word of n * M
     int32_t add, K, bias;  // n = 2*acc + add, add = div + d*K
-    int32_t pow2;          // d is a power of two: a plain shift by l replaces the multiply-high
+    int32_t mode, start, m;
+    template <int MODE>
     __device__ __forceinline__ int32_t quotient(int32_t acc) const  // before the 0..255 clamp
     {
+        if (MODE == 0) return acc;
+        if (MODE == 1) return acc >> m;
         uint32_t n = (uint32_t)(2 * acc + add);
-        uint32_t qn = pow2 ? (n >> (shift + 1)) : (__umulhi(n, M) >> shift);
-        return (int32_t)qn - K + bias;
+        return (int32_t)(__umulhi(n, M) >> shift) - K + bias;
     }
-    __device__ __forceinline__ uint32_t operator()(int32_t acc) const { return (uint32_t)min(max(quotient(acc), 0), 255); }
     // four results clamped to 0..255 and packed, result 0 in the low byte: two I2IP instructions
+    template <int MODE>
     __device__ __forceinline__ uint32_t pack4(int32_t a0, int32_t a1, int32_t a2, int32_t a3) const
     {
         uint32_t hi, out;
-        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(quotient(a3)), "r"(quotient(a2)), "r"(0));
-        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(quotient(a1)), "r"(quotient(a0)), "r"(hi));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(quotient<MODE>(a3)), "r"(quotient<MODE>(a2)), "r"(0));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(quotient<MODE>(a1)), "r"(quotient<MODE>(a0)), "r"(hi));
         return out;
     }
 };
@@ -52,7 +59,18 @@ static bool make_conv_round(int64_t sum_abs, int32_t div, int32_t bias, ConvRoun
     r->add = (int32_t)((uint64_t)div + d * K);
     r->K = (int32_t)K;
     r->bias = bias;
-    r->pow2 = ((d & (d - 1)) == 0) ? 1 : 0;
+    r->mode = 2;
+    r->start = 0;
+    r->m = 0;
+    const int64_t folded = (int64_t)div / 2 + (int64_t)bias * div;  // MODE 1 start value
+    if (div == 1 && bias > -(1 << 20) && bias < (1 << 20)) {
+        r->mode = 0;
+        r->start = bias;
+    } else if ((d & (d - 1)) == 0 && folded > -(1ll << 28) && folded < (1ll << 28)) {
+        r->mode = 1;
+        r->start = (int32_t)folded;
+        r->m = l - 1;  // div = 2^(l-1)
+    }
     return true;
 }
 
@@ -134,7 +152,7 @@ __device__ __forceinline__ constexpr bool fc_reaches(int j, int wi)
     return false;
 }
 
-template <int K>
+template <int K, int MODE>
 __global__ void __launch_bounds__(256) conv_dp4a_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t w,
                                                         const ConvCoefPacked<K> cf, const ConvRound rnd)
 {
@@ -187,7 +205,7 @@ __global__ void __launch_bounds__(256) conv_dp4a_kernel(RowSource rs, uint8_t *_
 #pragma unroll
         for (int a = 0; a < FC_RV; a++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[a][j] = 0;
+            for (int j = 0; j < 4; j++) acc[a][j] = rnd.start;
 #pragma unroll
         for (int iy = 0; iy < FC_RV + K - 1; iy++) {
             const uint32_t *rw = reinterpret_cast<const uint32_t *>(&plane[ch][oy0 + iy][0]) + 3 + lx;
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(256) conv_dp4a_kernel(RowSource rs, uint8_t *_
         }
 #pragma unroll
         for (int a = 0; a < FC_RV; a++)
-            outw[a][ch] = rnd.pack4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+            outw[a][ch] = rnd.template pack4<MODE>(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
     }
 #pragma unroll
     for (int a = 0; a < FC_RV; a++) {
@@ -241,7 +259,9 @@ static cudaError_t conv_fast(const RowSource &rs, uint8_t *dst, uint32_t w, uint
             }
     dim3 grid((w + FC_TW - 1) / FC_TW, (h + FC_TH - 1) / FC_TH);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
-    launch(conv_dp4a_kernel<K>, grid, dim3(256), 0, s, rs, dst, w, cf, rnd);
+    if (rnd.mode == 0) launch(conv_dp4a_kernel<K, 0>, grid, dim3(256), 0, s, rs, dst, w, cf, rnd);
+    else if (rnd.mode == 1) launch(conv_dp4a_kernel<K, 1>, grid, dim3(256), 0, s, rs, dst, w, cf, rnd);
+    else launch(conv_dp4a_kernel<K, 2>, grid, dim3(256), 0, s, rs, dst, w, cf, rnd);
     return PPMX_LAUNCHED();
 }
 

@@ -208,6 +208,8 @@ KERNELS = {
 }
 
 
+KERNELS["mix3_div8_biasneg"] = (np.array([[-1, 2, -1], [2, 4, 2], [-1, 2, -1]]), 8, -5)   # power-of-two divisor + bias
+KERNELS["neg7_div64_bias"] = (np.tile(np.array([[3, -2, 1, 4, 1, -2, 3]]), (7, 1)), 64, 17)
 KERNELS["big5"] = (np.array([[300, -200, 0, 5, 1]] * 5), 7, -3)  # coefficients beyond int8: generic kernel
 
 
