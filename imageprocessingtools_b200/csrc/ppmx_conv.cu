@@ -313,7 +313,7 @@ static cudaError_t conv_fast(const RowSource &rs, uint8_t *dst, uint32_t w, uint
             }
     }
     // separable kernels amortise the horizontal sums over more rows per thread (8 instead of 4)
-    constexpr int RV_SEP = 8, RV_DIR = 4;
+    constexpr int RV_SEP = 8, RV_DIR = 4;  // (8 rows per thread for the direct form measured slower: 0.47 vs 0.51)
     const int th = 8 * (sep ? RV_SEP : RV_DIR);
     dim3 grid((w + FC_TW - 1) / FC_TW, (h + th - 1) / th);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
