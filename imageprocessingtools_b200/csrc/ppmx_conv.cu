@@ -165,11 +165,17 @@ __global__ void __launch_bounds__(256) conv_dp4a_kernel(RowSource rs, uint8_t *_
 
     // ---- stage: 16-pixel groups, IN_ROWS x (FC_PITCH / 16) of them ----
     constexpr int GROUPS_X = FC_PITCH / 16;
+    // a tile that lies wholly inside the band and away from the raster's left/right edge (almost all of
+    // them) needs no mirror, halo or bounds logic: its rows are consecutive rows of `own`
+    const int gy_first = rs.y0 + ty0 - R;
+    const bool inner = gy_first >= rs.y0 && gy_first + IN_ROWS <= rs.y0 + rs.h && tx0 >= 16 && tx0 + FC_TW + 16 <= (int)w;
+    const uint8_t *inner_base = rs.own + (size_t)(gy_first - rs.y0) * pitch + (size_t)(tx0 - 16) * 3;
     for (int i = threadIdx.x; i < IN_ROWS * GROUPS_X; i += 256) {
         const int ty = i / GROUPS_X, gx = i - ty * GROUPS_X;
         const int x0 = tx0 - 16 + 16 * gx;  // first source pixel of the group (may be outside the raster)
-        const uint8_t *row = rs.row(rs.y0 + ty0 + ty - R, pitch);
-        if (x0 >= 0 && x0 + 16 <= (int)w) {
+        const uint8_t *row = inner ? inner_base + (size_t)ty * pitch - (size_t)(tx0 - 16) * 3
+                                   : rs.row(gy_first + ty, pitch);
+        if (inner || (x0 >= 0 && x0 + 16 <= (int)w)) {
             const uint4 *p = reinterpret_cast<const uint4 *>(row + (size_t)x0 * 3);
             const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
             const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
