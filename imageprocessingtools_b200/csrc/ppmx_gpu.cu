@@ -125,6 +125,8 @@ extern "C" void ppmx_gpu_free(ppmx_gpu_ctx *c)
             cudaStreamDestroy(c->lane[i]);
         }
     if (c->tables_ready) cudaEventDestroy(c->tables_ready);
+    cudaMemPool_t pool;  // hand the cached rasters back to the driver
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     if (c->d_hist) cudaFree(c->d_hist);
     if (c->h_hist) cudaFreeHost(c->h_hist);
     delete c;
