@@ -447,3 +447,24 @@ def test_extension_cli_conv_presets(gpu, orc, tmp_path):
         assert open(path + ".out", "rb").read() == orc.header(oracle.FT_PPM, 40, 64) + exp.tobytes(), flag
     p = subprocess.run([pp.CLI, "-blur", "-edge", path], capture_output=True, text=True)
     assert p.returncode == 255 and "Duplicate" in p.stdout
+
+
+def test_degenerate_rasters_cli(gpu, tmp_path):
+    """Zero-height / zero-width rasters and 1-pixel rasters go through the same code in both programs."""
+    import imageprocessingtools_b200.ppmx as pp
+    if not os.path.exists(oracle.REF_CLI):
+        pytest.skip("compiled reference CLI (oracle/_ref) did not travel")
+    cases = [(b"P6\n5 0\n255\n", ["-gray"]), (b"P6\n0 4\n255\n", ["-fh"]), (b"P6\n1 1\n255\n\x10\x80\xf0", ["-mono"]),
+             (b"P6\n1 1\n255\n\x10\x80\xf0", ["-r90"]), (b"P6\n2 1\n255\n\x01\x02\x03\x04\x05\x06", ["-fv"]),
+             (b"P6\n3 3\n255\n" + bytes(range(27)), ["-w7"]), (b"P6\n3 3\n255\n" + bytes(range(27)), ["-r45", "-gray"])]
+    for data, args in cases:
+        a, b = str(tmp_path / "a.ppm"), str(tmp_path / "b.ppm")
+        for p in (a, b):
+            open(p, "wb").write(data)
+            if os.path.exists(p + ".out"):
+                os.remove(p + ".out")
+        r = subprocess.run([oracle.REF_CLI] + args + [a], capture_output=True, text=True)
+        o = subprocess.run([pp.CLI] + args + [b], capture_output=True, text=True)
+        assert r.returncode == o.returncode, (data[:12], args, r.stdout, o.stdout)
+        if r.returncode == 0:
+            assert open(a + ".out", "rb").read() == open(b + ".out", "rb").read(), (data[:12], args)
