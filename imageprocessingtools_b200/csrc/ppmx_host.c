@@ -140,6 +140,8 @@ void ppmx_contributions_free(ppmx_contributions *c)
 static void set_new(ppmx_image_handler *h, ppmx_gpu_image *img)
 {
     unsigned int w = 0, hh = 0;
+    /* a superseded result (the reference leaks it, e.g. gray's output in "-gray -fh") goes back to the pool */
+    if (h->imginfo.new_buff && h->imginfo.new_buff != h->imginfo.buff) ppmx_gpu_image_free(h->ctx, h->imginfo.new_buff);
     h->imginfo.new_buff = img;
     ppmx_gpu_image_info(img, &w, &hh, NULL, NULL, NULL);
     h->imginfo.new_width = w;

@@ -468,3 +468,31 @@ def test_degenerate_rasters_cli(gpu, tmp_path):
         assert r.returncode == o.returncode, (data[:12], args, r.stdout, o.stdout)
         if r.returncode == 0:
             assert open(a + ".out", "rb").read() == open(b + ".out", "rb").read(), (data[:12], args)
+
+
+def test_operator_level_host_api_stepwise(gpu, tmp_path):
+    """the reference's doProcessPPM control flow over the operator-level C
+    functions (ppmx_getImageInfo, ppmx_imresize, ppmx_renewBuffer, ppmx_rotate, ppmx_gray, ppmx_mono,
+    ppmx_flip, ppmx_putImageToFile), compiled here from tests/c/stepwise.c, must write the same files as
+    the one-shot CLI and as the compiled reference."""
+    import imageprocessingtools_b200.ppmx as pp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "stepwise")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-std=gnu99", "-I" + os.path.join(root, "include"), "-o", exe,
+                    os.path.join(root, "tests", "c", "stepwise.c"), "-L" + pp.PKG, "-lppmx_host", "-lppmx_gpu", "-lm",
+                    "-Wl,-rpath," + pp.PKG], check=True)
+    img = P.lcg(64, 40, 21)
+    chains = [["-gray"], ["-mono"], ["-fv"], ["-fh"], ["-r90"], ["-r30"], ["-r0"], ["-w100"], ["-w30"], ["-w64"],
+              ["-w30", "-r90", "-gray", "-fv"], ["-w100", "-r45", "-mono", "-fh"], ["-gray", "-fh"], ["-mono", "-fv"],
+              ["-r270", "-mono", "-fh"], ["-w20", "-fv"]]
+    for args in chains:
+        a, b, c = (str(tmp_path / n) for n in ("a.ppm", "b.ppm", "c.ppm"))
+        for p in (a, b, c):
+            oracle.write_p6(p, img)
+        r1 = subprocess.run([exe] + args + [a], capture_output=True, text=True)
+        r2 = subprocess.run([pp.CLI] + args + [b], capture_output=True, text=True)
+        assert r1.returncode == 0 and r2.returncode == 0, (args, r1.stdout, r2.stdout)
+        assert open(a + ".out", "rb").read() == open(b + ".out", "rb").read(), args
+        if os.path.exists(oracle.REF_CLI):
+            rc, _ = oracle.ref_cli(args, c)
+            assert rc == 0 and open(c + ".out", "rb").read() == open(a + ".out", "rb").read(), args
