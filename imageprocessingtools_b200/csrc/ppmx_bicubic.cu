@@ -198,11 +198,21 @@ __device__ __forceinline__ uint32_t quantise_fast(double s)
 // output row.  The row's K weights and source-row numbers are staged once per CTA in shared memory
 // so the K source loads of a thread are independent of each other and fly four at a time.
 constexpr int ROWS16_MAXK = 64;
-template <int CONV>
+template <int NW> struct RowVec;
+template <> struct RowVec<4> { typedef uint4 type; };
+template <> struct RowVec<2> { typedef uint2 type; };
+__device__ __forceinline__ void vec_words(const uint4 &v, uint32_t (&w)[4]) { w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+__device__ __forceinline__ void vec_words(const uint2 &v, uint32_t (&w)[2]) { w[0] = v.x; w[1] = v.y; }
+__device__ __forceinline__ void words_vec(const uint32_t (&w)[4], uint4 &v) { v = make_uint4(w[0], w[1], w[2], w[3]); }
+__device__ __forceinline__ void words_vec(const uint32_t (&w)[2], uint2 &v) { v = make_uint2(w[0], w[1]); }
+
+// NW = words per thread: 4 (16 bytes, 57-64 registers) or 2 (8 bytes, fewer registers, more warps in flight)
+template <int CONV, int NW>
 __global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource src, uint8_t *__restrict__ dst,
                                                               uint32_t row_vecs, int taps,
                                                               const double *__restrict__ wts, const int *__restrict__ idx)
 {
+    typedef typename RowVec<NW>::type vec_t;
     PDL_PROLOGUE();
     __shared__ double s_w[ROWS16_MAXK];
     __shared__ int s_i[ROWS16_MAXK];
@@ -214,23 +224,24 @@ __global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource sr
     __syncthreads();
     const uint32_t xv = blockIdx.x * 256 + threadIdx.x;
     if (xv >= row_vecs) return;
-    const size_t row_bytes = (size_t)row_vecs * 16;
+    const size_t row_bytes = (size_t)row_vecs * (4 * NW);
 
-    double acc[16];
+    double acc[4 * NW];
 #pragma unroll
-    for (int i = 0; i < 16; i++) acc[i] = 0.0;
+    for (int i = 0; i < 4 * NW; i++) acc[i] = 0.0;
     for (int z0 = 0; z0 < taps; z0 += 4) {
-        uint4 v[4];
+        vec_t v[4];
 #pragma unroll
         for (int u = 0; u < 4; u++)
-            if (z0 + u < taps) v[u] = __ldg(reinterpret_cast<const uint4 *>(src.row_plain(s_i[z0 + u], row_bytes)) + xv);
+            if (z0 + u < taps) v[u] = __ldg(reinterpret_cast<const vec_t *>(src.row_plain(s_i[z0 + u], row_bytes)) + xv);
 #pragma unroll
         for (int u = 0; u < 4; u++) {  // tap order is the reference's summation order (ref:826-830)
             if (z0 + u >= taps) break;
             const double wz = s_w[z0 + u];
-            const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t wd[NW];
+            vec_words(v[u], wd);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < NW; q++) {
                 double d[4];
                 word_to_double4<CONV>(wd[q], d);
 #pragma unroll
@@ -238,12 +249,14 @@ __global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource sr
             }
         }
     }
-    uint32_t o[4];
+    uint32_t o[NW];
 #pragma unroll
-    for (int q = 0; q < 4; q++)
+    for (int q = 0; q < NW; q++)
         o[q] = quantise_fast(acc[4 * q]) | (quantise_fast(acc[4 * q + 1]) << 8) | (quantise_fast(acc[4 * q + 2]) << 16) |
                (quantise_fast(acc[4 * q + 3]) << 24);
-    reinterpret_cast<uint4 *>(dst + (size_t)y * row_bytes)[xv] = make_uint4(o[0], o[1], o[2], o[3]);
+    vec_t ov;
+    words_vec(o, ov);
+    reinterpret_cast<vec_t *>(dst + (size_t)y * row_bytes)[xv] = ov;
 }
 
 // width pass, fast path (w % 4 == 0, aligned, 4 <= K <= 8): one thread = one output column for a
@@ -419,19 +432,19 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
         const bool halo_ok = (!band.top || aligned16(band.top)) && (!band.bottom || aligned16(band.bottom));
         uint32_t row_bytes = w * 3u;
         if (row_bytes % 16 == 0 && aligned16(src_ptr) && aligned16(dst) && halo_ok && taps <= ROWS16_MAXK && g_variant != 1) {
-            dim3 grid((row_bytes / 16 + 255) / 256, 1);
+            const bool narrow = (g_variant == 6);  // 8 bytes per thread
+            const uint32_t vecs = narrow ? row_bytes / 8 : row_bytes / 16;
+            dim3 grid((vecs + 255) / 256, 1);
             for (int y0 = 0; y0 < out_size; y0 += 65535) {
                 int rows = min(65535, out_size - y0);
                 grid.y = rows;
-                if (g_variant == 2)
-                    launch(imresize_rows16_kernel<1>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
-                           taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
-                else if (g_variant == 3)
-                    launch(imresize_rows16_kernel<0>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
-                           taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
-                else
-                    launch(imresize_rows16_kernel<2>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, row_bytes / 16,
-                           taps, d_weights + (size_t)y0 * taps, d_indices + (size_t)y0 * taps);
+                uint8_t *d0 = dst + (size_t)y0 * row_bytes;
+                const double *w0 = d_weights + (size_t)y0 * taps;
+                const int *i0 = d_indices + (size_t)y0 * taps;
+                if (narrow) launch(imresize_rows16_kernel<2, 2>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (g_variant == 2) launch(imresize_rows16_kernel<1, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (g_variant == 3) launch(imresize_rows16_kernel<0, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else launch(imresize_rows16_kernel<2, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
             }
             return cudaGetLastError();
         }
