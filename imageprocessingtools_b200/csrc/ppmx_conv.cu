@@ -266,6 +266,187 @@ __global__ void __launch_bounds__(256) conv_dp4a_kernel(RowSource rs, uint8_t *_
     }
 }
 
+// ---- 3x3 strip kernel: vertical dp4a on the interleaved raster, registers only ----------------
+// The horizontal neighbour of a byte of an RGB raster is the byte 3 columns away, so no de-interleaving is needed
+// if the dp4a runs DOWN the image instead of along it.  A thread owns 16 byte columns (one 16-byte vector per row)
+// and walks down RH rows two at a time.  For every byte column it keeps the "vertical word"
+//     V = in[y-1] | in[y] << 8 | in[y+1] << 16 | in[y+2] << 24          (rows around the output pair y, y+1)
+// built from four source rows by 4x4 byte transposes (PRMT); successive pairs share two rows, so the first
+// transpose stage of those is reused (6 PRMT per 4 columns per pair).  Output (y, c) is then three dp4a:
+// V[c-3], V[c], V[c+3] against the coefficient column packed in bytes 0..2, output (y+1, c) the same words
+// against the coefficients in bytes 1..3: 3 dp4a per output byte with 3 of the 4 multipliers busy (the
+// row-wise form needs 4.5 and two (de)interleaving passes).  No shared memory, no barrier: the one word left
+// and right of the thread's vector comes from L1 (it is the neighbouring lane's vector), or from the mirror
+// rule at the raster's edge.  Instruction mix per output byte: 3 IDP (fma pipe), ~1.1 PRMT + 0.75..1.5
+// finishing (alu pipe) -- both pipes issue 64 lanes/clk/SM (tools/int_peak.cu), so the kernel is bound by HBM.
+struct Conv3Coef {
+    uint32_t a[3], b[3];  // per tap column dx = -1, 0, +1: the coefficient bytes for the upper / lower row of a pair
+};
+
+template <int MODE>
+__device__ __forceinline__ uint32_t strip_pack4(const ConvRound &rnd, int32_t a0, int32_t a1, int32_t a2, int32_t a3)
+{
+    if (MODE == 3)  // coefficients pre-scaled so that the result is byte 1 of the sum and cannot leave 0..255
+        return __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
+    return rnd.template pack4<(MODE == 3 ? 0 : MODE)>(a0, a1, a2, a3);
+}
+
+template <int MODE, int RH, int PF, bool INNER>
+__device__ __forceinline__ void conv3_strip_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, uint32_t cx,
+                                                 int ys, const Conv3Coef &cf, const ConvRound &rnd)
+{
+    const size_t pitch = (size_t)nchunks * 16;
+    const bool left = cx == 0, right = cx == nchunks - 1;
+    const int gy0 = rs.y0 + ys;
+    const uint8_t *src = rs.own + (size_t)cx * 16 + (size_t)(INNER ? ys - 1 : 0) * pitch;
+    auto load_row = [&](int i, uint32_t(&r)[6]) {  // row i counted from the strip's first source row (gy0 - 1)
+        const uint8_t *p = INNER ? src + (size_t)i * pitch : rs.row(gy0 - 1 + i, pitch) + (size_t)cx * 16;
+        const uint4 m = __ldg(reinterpret_cast<const uint4 *>(p));
+        r[1] = m.x, r[2] = m.y, r[3] = m.z, r[4] = m.w;
+        // columns -3..-1 / 16..18; at the raster's edge pixel -1 mirrors to pixel 0 and pixel W to W-1
+        r[0] = left ? (m.x << 8) : __ldg(reinterpret_cast<const uint32_t *>(p - 4));
+        r[5] = right ? (m.w >> 8) : __ldg(reinterpret_cast<const uint32_t *>(p + 16));
+    };
+    pdl_wait();
+
+    uint32_t tlo[6], thi[6];  // first transpose stage of the pair's two upper rows
+    uint32_t nb[PF][2][6];    // the two new rows of the next PF pairs, in flight during the arithmetic
+    {
+        uint32_t a[6], b[6];
+        load_row(0, a);
+        load_row(1, b);
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            load_row(2 * u + 2, nb[u][0]);
+            load_row(2 * u + 3, nb[u][1]);
+        }
+#pragma unroll
+        for (int wc = 0; wc < 6; wc++) {
+            tlo[wc] = __byte_perm(a[wc], b[wc], 0x5140);
+            thi[wc] = __byte_perm(a[wc], b[wc], 0x7362);
+        }
+    }
+    uint8_t *out = dst + (size_t)ys * pitch + (size_t)cx * 16;
+#pragma unroll 1
+    for (int g0 = 0; g0 < RH / 2; g0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            const int g = g0 + u;
+            if (!INNER && ys + 2 * g >= rs.h) return;
+            uint32_t ulo[6], uhi[6];
+#pragma unroll
+            for (int wc = 0; wc < 6; wc++) {
+                ulo[wc] = __byte_perm(nb[u][0][wc], nb[u][1][wc], 0x5140);
+                uhi[wc] = __byte_perm(nb[u][0][wc], nb[u][1][wc], 0x7362);
+            }
+            if (g + PF < RH / 2 && (INNER || ys + 2 * (g + PF) < rs.h)) {
+                load_row(2 * (g + PF) + 2, nb[u][0]);
+                load_row(2 * (g + PF) + 3, nb[u][1]);
+            }
+            uint32_t V[24];  // V[i] = byte column 16 cx - 4 + i
+#pragma unroll
+            for (int wc = 0; wc < 6; wc++) {
+                V[4 * wc + 0] = __byte_perm(tlo[wc], ulo[wc], 0x5410);
+                V[4 * wc + 1] = __byte_perm(tlo[wc], ulo[wc], 0x7632);
+                V[4 * wc + 2] = __byte_perm(thi[wc], uhi[wc], 0x5410);
+                V[4 * wc + 3] = __byte_perm(thi[wc], uhi[wc], 0x7632);
+                tlo[wc] = ulo[wc];
+                thi[wc] = uhi[wc];
+            }
+            uint32_t oa[4], ob[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int32_t accA[4], accB[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int c = 4 * b + j + 4;
+                    accA[j] = dp4a_u8s8(V[c + 3], cf.a[2], dp4a_u8s8(V[c], cf.a[1], dp4a_u8s8(V[c - 3], cf.a[0], rnd.start)));
+                    accB[j] = dp4a_u8s8(V[c + 3], cf.b[2], dp4a_u8s8(V[c], cf.b[1], dp4a_u8s8(V[c - 3], cf.b[0], rnd.start)));
+                }
+                oa[b] = strip_pack4<MODE>(rnd, accA[0], accA[1], accA[2], accA[3]);
+                ob[b] = strip_pack4<MODE>(rnd, accB[0], accB[1], accB[2], accB[3]);
+            }
+            *reinterpret_cast<uint4 *>(out) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+            if (INNER || ys + 2 * g + 1 < rs.h) *reinterpret_cast<uint4 *>(out + pitch) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+            out += 2 * pitch;
+        }
+    }
+}
+
+template <int MODE, int RH, int PF, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) conv3_strip_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks,
+                                                            const Conv3Coef cf, const ConvRound rnd)
+{
+    pdl_trigger();
+    const uint32_t cx = blockIdx.x * BLOCK + threadIdx.x;
+    if (cx >= nchunks) return;
+    const int ys = blockIdx.y * RH;  // first output row of the strip, band-local
+    // source rows ys-1 .. ys+RH all inside the own band (all strips but the first and last of a band): plain
+    // pointer steps; otherwise every row goes through the mirror / halo resolver
+    if (ys >= 1 && ys + RH + 1 <= rs.h) conv3_strip_body<MODE, RH, PF, true>(rs, dst, nchunks, cx, ys, cf, rnd);
+    else conv3_strip_body<MODE, RH, PF, false>(rs, dst, nchunks, cx, ys, cf, rnd);
+}
+
+static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef,
+                               ConvRound rnd, int32_t div, int32_t bias, cudaStream_t s)
+{
+    int32_t c[9];
+    for (int i = 0; i < 9; i++) c[i] = coef[i];
+    int mode = rnd.mode;
+    if (mode == 1 && bias == 0 && rnd.m <= 8 && g_variant != 8) {
+        // non-negative coefficients that sum to at most div cannot leave 0..255; scaled by 2^(8-m) the rounded
+        // quotient is byte 1 of the sum and the shift + saturating pack become three PRMTs per four bytes
+        int64_t sum = 0;
+        int32_t mx = 0;
+        bool nonneg = true;
+        for (int i = 0; i < 9; i++) {
+            nonneg = nonneg && c[i] >= 0;
+            sum += c[i];
+            mx = c[i] > mx ? c[i] : mx;
+        }
+        const int up = 8 - rnd.m;
+        if (nonneg && sum <= div && ((int64_t)mx << up) <= 127) {
+            for (int i = 0; i < 9; i++) c[i] <<= up;
+            rnd.start = (div / 2) << up;
+            mode = 3;
+        }
+    }
+    Conv3Coef cf;
+    for (int dx = 0; dx < 3; dx++) {
+        const uint32_t t = (uint32_t)(uint8_t)(int8_t)c[dx], m = (uint32_t)(uint8_t)(int8_t)c[3 + dx],
+                       b = (uint32_t)(uint8_t)(int8_t)c[6 + dx];
+        cf.a[dx] = t | m << 8 | b << 16;
+        cf.b[dx] = t << 8 | m << 16 | b << 24;
+    }
+    const uint32_t nchunks = w * 3 / 16;
+#define PPMX_CONV3_LAUNCH(MODE, RH, PF, BLOCK)                                                                   \
+    do {                                                                                                         \
+        dim3 grid((nchunks + BLOCK - 1) / BLOCK, (h + RH - 1) / RH);                                             \
+        if (grid.y > 65535u) return cudaErrorInvalidValue;                                                       \
+        launch(conv3_strip_kernel<MODE, RH, PF, BLOCK>, grid, dim3(BLOCK), 0, s, rs, dst, nchunks, cf, rnd);     \
+    } while (0)
+#define PPMX_CONV3_MODES(RH, PF, BLOCK)                          \
+    do {                                                         \
+        if (mode == 0) PPMX_CONV3_LAUNCH(0, RH, PF, BLOCK);      \
+        else if (mode == 1) PPMX_CONV3_LAUNCH(1, RH, PF, BLOCK); \
+        else if (mode == 2) PPMX_CONV3_LAUNCH(2, RH, PF, BLOCK); \
+        else PPMX_CONV3_LAUNCH(3, RH, PF, BLOCK);                \
+    } while (0)
+    // rows per strip / row pairs in flight / threads per CTA.  Measured on 8192x8192 (profiles/r1_sweep_conv3_strip.txt):
+    // 4/2/128: 0.94 of the HBM roofline, 4/2/256: 0.92, 8/2/128: 0.84, 8/4/128: 0.84, 16/1/128: 0.74, 32/1/128: 0.68 --
+    // the flatter the better (all six source rows of a strip are requested before the first dp4a, and the CTAs
+    // resident at any moment cover a compact block of rows), as for the colour kernels.
+    if (g_variant == 9) PPMX_CONV3_MODES(2, 1, 128);
+    else if (g_variant == 10) PPMX_CONV3_MODES(4, 2, 256);
+    else if (g_variant == 11) PPMX_CONV3_MODES(8, 2, 128);
+    else if (g_variant == 12) PPMX_CONV3_MODES(16, 1, 128);
+    else if (g_variant == 13) PPMX_CONV3_MODES(4, 2, 64);
+    else PPMX_CONV3_MODES(4, 2, 128);
+#undef PPMX_CONV3_MODES
+#undef PPMX_CONV3_LAUNCH
+    return PPMX_LAUNCHED();
+}
+
 // coef = u * v^T with integer factors, v within int8?  (box, binomial/"Gaussian" blurs are; sharpen and
 // edge kernels are not)
 template <int K>
@@ -352,6 +533,8 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
     if (s8 && (k == 3 || k == 5 || k == 7) && (w % 16u) == 0 && aligned16(src) && aligned4(dst) &&
         (!band.top || aligned16(band.top)) && (!band.bottom || aligned16(band.bottom)) && g_variant != 1 &&
         make_conv_round(sum_abs, div, bias, &rnd)) {
+        // variant 7 keeps the row-wise (planar dp4a) kernel for 3x3; the strip kernel is the default
+        if (k == 3 && g_variant != 7 && aligned16(dst)) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s);
         if (k == 3) return conv_fast<3>(rs, dst, w, h, coef, rnd, s);
         if (k == 5) return conv_fast<5>(rs, dst, w, h, coef, rnd, s);
         return conv_fast<7>(rs, dst, w, h, coef, rnd, s);

@@ -218,7 +218,7 @@ KERNELS["big5"] = (np.array([[300, -200, 0, 5, 1]] * 5), 7, -3)  # coefficients 
 
 def test_extension_conv(gpu, orc):
     for (w, h) in [(1, 1), (2, 3), (5, 4), (37, 23), (64, 48), (130, 70), (301, 211), (16, 1), (16, 40), (128, 32),
-                   (144, 37), (256, 64), (400, 33)]:
+                   (144, 37), (256, 64), (400, 33), (64, 200), (48, 131), (2064, 67)]:
         for pname in ("lcg", "checker", "mixed"):
             img = P.all_patterns(w, h)[pname]
             for kname, (coef, div, bias) in KERNELS.items():
@@ -425,6 +425,25 @@ def test_tuning_variants_are_bit_identical(gpu, orc):
     finally:
         gpu.set_tuning("variant", 0)
         gpu.set_tuning("pdl", 1)
+
+
+def test_extension_conv3_strip_variants(gpu, orc):
+    """3x3: the strip kernel (default; other strip heights / CTA sizes = variants 9-13; variant 8 = without the
+    scaled-coefficient byte extraction) and the row-wise planar kernel (variant 7) give the self-oracle's bytes,
+    on flat extremes too (saturation at both ends)."""
+    imgs = [P.lcg(64, 200, 5), P.const(64, 131, 255), P.const(32, 70, 0), P.all_patterns(48, 133)["checker"]]
+    names = ("blur3", "sharpen3", "edge3", "mix3_div8_biasneg", "sobel3")
+    exp = {(i, k): orc.conv(img, *KERNELS[k]) for i, img in enumerate(imgs) for k in names}
+    exp_big = orc.conv(imgs[0], np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]]) * 4, 64, 0)  # scaled coefficients would pass 127
+    try:
+        for v in (0, 7, 8, 9, 10, 11, 12, 13):
+            gpu.set_tuning("variant", v)
+            for i, img in enumerate(imgs):
+                for k in names:
+                    assert np.array_equal(gpu.conv(img, *KERNELS[k]), exp[(i, k)]), (v, i, k)
+            assert np.array_equal(gpu.conv(imgs[0], np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]]) * 4, 64, 0), exp_big), v
+    finally:
+        gpu.set_tuning("variant", 0)
 
 
 def test_extension_cli_conv_presets(gpu, orc, tmp_path):
