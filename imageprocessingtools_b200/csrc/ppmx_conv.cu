@@ -447,6 +447,198 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
     return PPMX_LAUNCHED();
 }
 
+// ---- box kernel (all coefficients equal, e.g. the 7x7 blur preset): running sums ---------------
+// A k x k box sum is a vertical running sum followed by a horizontal one, so its cost need not grow with k.
+// A thread owns 16 byte columns and walks down RH rows keeping S[c] = sum of the K source rows around the
+// current row for each of its columns; moving down one row is S += in[y+R+1] - in[y-R], one PRMT (pairing the
+// leaving and the entering byte) and one dp4a against (-1, +1, 0, 0) per column.  The horizontal sum of S over
+// the K pixels around a byte (columns 3 apart) needs 3R columns of the neighbouring threads: they come by warp
+// shuffle, and so that no lane lacks a neighbour the warps overlap by two lanes (lanes 0 and 31 only supply
+// their sums; 30 lanes write).  Along the row the sum slides too: h[c+3] = h[c] + S[c+3R+3] - S[c-3R], one
+// IADD3.  The quotient is one multiply-add whose byte 3 is the result (constants verified on the host for every
+// possible sum).  Source rows stream global -> shared with cp.async into thread-private slots of a 16-row ring
+// (no barrier), requested 16-K rows ahead; the row that leaves the window is re-read from the ring, not from L2.
+// Per output byte: ~2 fma-pipe (IDP, IMAD) + ~3.2 alu-pipe (PRMT, IADD3) + 1.1 SHFL, whatever K is.
+constexpr int BOX_SLOTS = 16;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int K, int RH, bool INNER>
+__device__ __forceinline__ void conv_box_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, int chunk,
+                                              int ys, uint32_t M, uint32_t C, uint4 (*ring)[128])
+{
+    constexpr int R = K / 2, H = 3 * R, TOTAL = RH + K - 1, PEND = BOX_SLOTS - K;
+    const int lane = threadIdx.x & 31;
+    const bool valid = chunk >= 0 && chunk < (int)nchunks;
+    const uint32_t cx = (uint32_t)(chunk < 0 ? 0 : chunk >= (int)nchunks ? (int)nchunks - 1 : chunk);
+    const bool writes = valid && lane >= 1 && lane <= 30;
+    const bool left = chunk == 0, right = chunk == (int)nchunks - 1;
+    const size_t pitch = (size_t)nchunks * 16;
+    const int gy0 = rs.y0 + ys;
+    const uint8_t *src = rs.own + (size_t)cx * 16 + (size_t)(INNER ? ys - R : 0) * pitch;
+    auto row_ptr = [&](int i) {  // row i counted from the strip's first source row (gy0 - R)
+        return INNER ? src + (size_t)i * pitch : rs.row(gy0 - R + i, pitch) + (size_t)cx * 16;
+    };
+    uint4 *slot0 = &ring[0][threadIdx.x];
+    auto slot = [&](int i) { return slot0 + (size_t)(i & (BOX_SLOTS - 1)) * 128; };
+    // rows a strip shortened by the band's end never uses are still fetched (the resolver mirrors them): harmless
+    pdl_wait();
+#pragma unroll
+    for (int i = 0; i < BOX_SLOTS; i++) {
+        if (i < TOTAL) cp_async16(slot(i), row_ptr(i));
+        cp_async_commit();
+    }
+    cp_async_wait<PEND>();
+
+    // S = sum of rows 0..K-1, four rows at a time through 4x4 byte transposes and dp4a against (1,1,1,1)
+    uint32_t S[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) S[c] = 0;
+#pragma unroll
+    for (int i0 = 0; i0 < K; i0 += 4) {
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) q[u] = i0 + u < K ? *slot(i0 + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int wc = 0; wc < 4; wc++) {
+            const uint32_t a = (&q[0].x)[wc], b = (&q[1].x)[wc], c = (&q[2].x)[wc], d = (&q[3].x)[wc];
+            const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(c, d, 0x5140);
+            const uint32_t t2 = __byte_perm(a, b, 0x7362), t3 = __byte_perm(c, d, 0x7362);
+            S[4 * wc + 0] = __dp4a(__byte_perm(t0, t1, 0x5410), 0x01010101u, S[4 * wc + 0]);
+            S[4 * wc + 1] = __dp4a(__byte_perm(t0, t1, 0x7632), 0x01010101u, S[4 * wc + 1]);
+            S[4 * wc + 2] = __dp4a(__byte_perm(t2, t3, 0x5410), 0x01010101u, S[4 * wc + 2]);
+            S[4 * wc + 3] = __dp4a(__byte_perm(t2, t3, 0x7632), 0x01010101u, S[4 * wc + 3]);
+        }
+    }
+
+    uint8_t *out = dst + (size_t)ys * pitch + (size_t)cx * 16;
+#pragma unroll 1
+    for (int r = 0; r < RH; r++) {
+        if (!INNER && ys + r >= rs.h) break;
+        // ---- the slot of the row that left the window one step ago takes the next row to fetch ----
+        if (r >= 1) {  // (one group per step, empty or not, keeps the wait count below a constant)
+            if (BOX_SLOTS + r - 1 < TOTAL) cp_async16(slot(r - 1), row_ptr(BOX_SLOTS + r - 1));
+            cp_async_commit();
+        }
+        // ---- horizontal sums: 3R columns from the lane on either side ----
+        uint32_t X[16 + 2 * H];  // X[H + c] = S of byte column c, c = -H .. 15 + H
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+            X[i] = __shfl_up_sync(0xffffffffu, S[16 - H + i], 1);
+            X[H + 16 + i] = __shfl_down_sync(0xffffffffu, S[i], 1);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; c++) X[H + c] = S[c];
+        if (left) {  // pixel -m mirrors to pixel m-1: columns -3m+j come from columns 3(m-1)+j
+#pragma unroll
+            for (int i = 0; i < H; i++) X[i] = S[3 * (R - 1 - i / 3) + i % 3];
+        }
+        if (right) {  // pixel W-1+m mirrors to pixel W-m: columns 16+i come from 13 - 3(i/3) + i%3
+#pragma unroll
+            for (int i = 0; i < H; i++) X[H + 16 + i] = S[13 - 3 * (i / 3) + i % 3];
+        }
+        uint32_t hs[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            if (c < 3) {
+                uint32_t t = 0;
+#pragma unroll
+                for (int k = -R; k <= R; k++) t += X[H + c + 3 * k];
+                hs[c] = t;
+            } else {
+                hs[c] = hs[c - 3] + X[H + c + 3 * R] - X[H + c - 3 * R - 3];
+            }
+        }
+        if (writes) {
+            uint32_t o[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t q0 = hs[4 * b] * M + C, q1 = hs[4 * b + 1] * M + C, q2 = hs[4 * b + 2] * M + C,
+                               q3 = hs[4 * b + 3] * M + C;  // the quotient is byte 3
+                o[b] = __byte_perm(__byte_perm(q0, q1, 0x0073), __byte_perm(q2, q3, 0x0073), 0x5410);
+            }
+            *reinterpret_cast<uint4 *>(out) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        out += pitch;
+        if (r == RH - 1) break;
+        // ---- move the window down: S += row (K + r) - row r ----
+        cp_async_wait<PEND - 1>();  // groups 0 .. K + r have landed
+        const uint4 nw = *slot(K + r), od = *slot(r);
+#pragma unroll
+        for (int wc = 0; wc < 4; wc++) {
+            const uint32_t a = (&od.x)[wc], b = (&nw.x)[wc];
+            S[4 * wc + 0] = dp4a_u8s8(__byte_perm(a, b, 0x0040), 0x000001ffu, S[4 * wc + 0]);
+            S[4 * wc + 1] = dp4a_u8s8(__byte_perm(a, b, 0x0051), 0x000001ffu, S[4 * wc + 1]);
+            S[4 * wc + 2] = dp4a_u8s8(__byte_perm(a, b, 0x0062), 0x000001ffu, S[4 * wc + 2]);
+            S[4 * wc + 3] = dp4a_u8s8(__byte_perm(a, b, 0x0073), 0x000001ffu, S[4 * wc + 3]);
+        }
+    }
+}
+
+template <int K, int RH>
+__global__ void __launch_bounds__(128) conv_box_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks, uint32_t M,
+                                                       uint32_t C)
+{
+    constexpr int R = K / 2;
+    __shared__ uint4 ring[BOX_SLOTS][128];
+    pdl_trigger();
+    const int wg = blockIdx.x * 4 + (threadIdx.x >> 5);  // warp number along the row: 30 chunks each
+    if (wg * 30 >= (int)nchunks) return;
+    const int chunk = wg * 30 - 1 + (int)(threadIdx.x & 31);
+    const int ys = blockIdx.y * RH;
+    if (ys >= R && ys + RH + R <= rs.h) conv_box_body<K, RH, true>(rs, dst, nchunks, chunk, ys, M, C, ring);
+    else conv_box_body<K, RH, false>(rs, dst, nchunks, chunk, ys, M, C, ring);
+}
+
+// all coefficients equal to a > 0, and (sum * M + C) >> 24 == floor((2 a sum + div) / (2 div)) + bias within 0..255
+// for every possible sum (checked one by one: at most 255 k^2 + 1 values)
+static bool box_constants(const int32_t *coef, int k, int32_t div, int32_t bias, uint32_t *M, uint32_t *C)
+{
+    const int32_t a = coef[0];
+    if (a <= 0) return false;
+    for (int i = 1; i < k * k; i++)
+        if (coef[i] != a) return false;
+    const int64_t smax = 255ll * k * k;
+    const uint64_t m = (((uint64_t)a << 24) + (uint64_t)div - 1) / (uint64_t)div;  // ceil(2^24 a / div)
+    // floor((2 a s + div) / (2 div)) = floor((a s + div / 2) / div) for integers, div / 2 rounded down
+    const int64_t c = (int64_t)((((uint64_t)(div / 2) << 24) + (uint64_t)div - 1) / (uint64_t)div) + ((int64_t)bias << 24);
+    if (c < 0 || m >= (1ull << 32) || (uint64_t)smax * m + (uint64_t)c >= (1ull << 32)) return false;
+    for (int64_t sum = 0; sum <= smax; sum++) {
+        const int64_t num = 2 * (int64_t)a * sum + div, den = 2 * (int64_t)div;
+        const int64_t q = num / den + bias;  // num >= 0
+        if (q < 0 || q > 255) return false;
+        if ((int64_t)(((uint64_t)sum * m + (uint64_t)c) >> 24) != q) return false;
+    }
+    *M = (uint32_t)m;
+    *C = (uint32_t)c;
+    return true;
+}
+
+template <int K>
+static cudaError_t conv_box(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, uint32_t M, uint32_t C, cudaStream_t s)
+{
+    const uint32_t nchunks = w * 3 / 16;
+#define PPMX_BOX_LAUNCH(RH)                                                                   \
+    do {                                                                                      \
+        dim3 grid((nchunks + 119) / 120, (h + RH - 1) / RH);                                  \
+        if (grid.y > 65535u) return cudaErrorInvalidValue;                                    \
+        launch(conv_box_kernel<K, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, M, C);        \
+    } while (0)
+    if (g_variant == 9) PPMX_BOX_LAUNCH(8);
+    else if (g_variant == 10) PPMX_BOX_LAUNCH(32);
+    else if (g_variant == 11) PPMX_BOX_LAUNCH(64);
+    else PPMX_BOX_LAUNCH(16);
+#undef PPMX_BOX_LAUNCH
+    return PPMX_LAUNCHED();
+}
+
 // coef = u * v^T with integer factors, v within int8?  (box, binomial/"Gaussian" blurs are; sharpen and
 // edge kernels are not)
 template <int K>
@@ -533,6 +725,9 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
     if (s8 && (k == 3 || k == 5 || k == 7) && (w % 16u) == 0 && aligned16(src) && aligned4(dst) &&
         (!band.top || aligned16(band.top)) && (!band.bottom || aligned16(band.bottom)) && g_variant != 1 &&
         make_conv_round(sum_abs, div, bias, &rnd)) {
+        uint32_t bm, bc;
+        if ((k == 5 || k == 7) && g_variant != 7 && aligned16(dst) && box_constants(coef, k, div, bias, &bm, &bc))
+            return k == 5 ? conv_box<5>(rs, dst, w, h, bm, bc, s) : conv_box<7>(rs, dst, w, h, bm, bc, s);
         // variant 7 keeps the row-wise (planar dp4a) kernel for 3x3; the strip kernel is the default
         if (k == 3 && g_variant != 7 && aligned16(dst)) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s);
         if (k == 3) return conv_fast<3>(rs, dst, w, h, coef, rnd, s);
