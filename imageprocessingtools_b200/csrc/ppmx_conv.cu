@@ -470,16 +470,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int K, int RH, bool INNER>
+template <int K, int RH, bool INNER, bool EDGE>
 __device__ __forceinline__ void conv_box_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, int chunk,
                                               int ys, uint32_t M, uint32_t C, uint4 (*ring)[128])
 {
     constexpr int R = K / 2, H = 3 * R, TOTAL = RH + K - 1, PEND = BOX_SLOTS - K;
+    constexpr int UNR = 4;  // rows per loop trip (a full unroll by the ring size made slot indices static but cost 90 KB of code)
+    static_assert(RH % UNR == 0, "strip height");
     const int lane = threadIdx.x & 31;
     const bool valid = chunk >= 0 && chunk < (int)nchunks;
     const uint32_t cx = (uint32_t)(chunk < 0 ? 0 : chunk >= (int)nchunks ? (int)nchunks - 1 : chunk);
     const bool writes = valid && lane >= 1 && lane <= 30;
-    const bool left = chunk == 0, right = chunk == (int)nchunks - 1;
+    const bool left = EDGE && chunk == 0, right = EDGE && chunk == (int)nchunks - 1;
     const size_t pitch = (size_t)nchunks * 16;
     const int gy0 = rs.y0 + ys;
     const uint8_t *src = rs.own + (size_t)cx * 16 + (size_t)(INNER ? ys - R : 0) * pitch;
@@ -520,43 +522,45 @@ __device__ __forceinline__ void conv_box_body(const RowSource &rs, uint8_t *__re
 
     uint8_t *out = dst + (size_t)ys * pitch + (size_t)cx * 16;
 #pragma unroll 1
-    for (int r = 0; r < RH; r++) {
-        if (!INNER && ys + r >= rs.h) break;
-        // ---- the slot of the row that left the window one step ago takes the next row to fetch ----
-        if (r >= 1) {  // (one group per step, empty or not, keeps the wait count below a constant)
-            if (BOX_SLOTS + r - 1 < TOTAL) cp_async16(slot(r - 1), row_ptr(BOX_SLOTS + r - 1));
-            cp_async_commit();
-        }
-        // ---- horizontal sums: 3R columns from the lane on either side ----
-        uint32_t X[16 + 2 * H];  // X[H + c] = S of byte column c, c = -H .. 15 + H
+    for (int r0 = 0; r0 < RH; r0 += UNR) {
 #pragma unroll
-        for (int i = 0; i < H; i++) {
-            X[i] = __shfl_up_sync(0xffffffffu, S[16 - H + i], 1);
-            X[H + 16 + i] = __shfl_down_sync(0xffffffffu, S[i], 1);
-        }
-#pragma unroll
-        for (int c = 0; c < 16; c++) X[H + c] = S[c];
-        if (left) {  // pixel -m mirrors to pixel m-1: columns -3m+j come from columns 3(m-1)+j
-#pragma unroll
-            for (int i = 0; i < H; i++) X[i] = S[3 * (R - 1 - i / 3) + i % 3];
-        }
-        if (right) {  // pixel W-1+m mirrors to pixel W-m: columns 16+i come from 13 - 3(i/3) + i%3
-#pragma unroll
-            for (int i = 0; i < H; i++) X[H + 16 + i] = S[13 - 3 * (i / 3) + i % 3];
-        }
-        uint32_t hs[16];
-#pragma unroll
-        for (int c = 0; c < 16; c++) {
-            if (c < 3) {
-                uint32_t t = 0;
-#pragma unroll
-                for (int k = -R; k <= R; k++) t += X[H + c + 3 * k];
-                hs[c] = t;
-            } else {
-                hs[c] = hs[c - 3] + X[H + c + 3 * R] - X[H + c - 3 * R - 3];
+        for (int u = 0; u < UNR; u++) {
+            const int r = r0 + u;
+            if (!INNER && ys + r >= rs.h) return;
+            // ---- the slot of the row that left the window one step ago takes the next row to fetch ----
+            if (r0 + u >= 1) {  // (one group per step, empty or not, keeps the wait count below a constant)
+                if (BOX_SLOTS + r - 1 < TOTAL) cp_async16(slot(r - 1), row_ptr(BOX_SLOTS + r - 1));
+                cp_async_commit();
             }
-        }
-        if (writes) {
+            // ---- horizontal sums: 3R columns from the lane on either side ----
+            uint32_t XL[H], XR[H];  // S of byte columns -H .. -1 and 16 .. 15 + H
+#pragma unroll
+            for (int i = 0; i < H; i++) {
+                XL[i] = __shfl_up_sync(0xffffffffu, S[16 - H + i], 1);
+                XR[i] = __shfl_down_sync(0xffffffffu, S[i], 1);
+            }
+            if (EDGE) {  // only the warps holding the raster's first or last 16 bytes compile this in
+#pragma unroll
+                for (int i = 0; i < H; i++) {
+                    // pixel -m mirrors to pixel m-1: columns -3m+j come from columns 3(m-1)+j;
+                    // pixel W-1+m mirrors to pixel W-m: columns 16+i come from 13 - 3(i/3) + i%3
+                    XL[i] = left ? S[3 * (R - 1 - i / 3) + i % 3] : XL[i];
+                    XR[i] = right ? S[13 - 3 * (i / 3) + i % 3] : XR[i];
+                }
+            }
+            auto X = [&](int c) { return c < 0 ? XL[c + H] : c < 16 ? S[c] : XR[c - 16]; };
+            uint32_t hs[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                if (c < 3) {
+                    uint32_t t = 0;
+#pragma unroll
+                    for (int k = -R; k <= R; k++) t += X(c + 3 * k);
+                    hs[c] = t;
+                } else {
+                    hs[c] = hs[c - 3] + X(c + 3 * R) - X(c - 3 * R - 3);
+                }
+            }
             uint32_t o[4];
 #pragma unroll
             for (int b = 0; b < 4; b++) {
@@ -564,20 +568,19 @@ __device__ __forceinline__ void conv_box_body(const RowSource &rs, uint8_t *__re
                                q3 = hs[4 * b + 3] * M + C;  // the quotient is byte 3
                 o[b] = __byte_perm(__byte_perm(q0, q1, 0x0073), __byte_perm(q2, q3, 0x0073), 0x5410);
             }
-            *reinterpret_cast<uint4 *>(out) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        out += pitch;
-        if (r == RH - 1) break;
-        // ---- move the window down: S += row (K + r) - row r ----
-        cp_async_wait<PEND - 1>();  // groups 0 .. K + r have landed
-        const uint4 nw = *slot(K + r), od = *slot(r);
+            if (writes) *reinterpret_cast<uint4 *>(out) = make_uint4(o[0], o[1], o[2], o[3]);
+            out += pitch;
+            if (r == RH - 1) return;
+            // ---- move the window down: S += row (K + r) - row r, one byte-selecting dp4a each ----
+            cp_async_wait<PEND - 1>();  // groups 0 .. K + r have landed
+            const uint4 nw = *slot(K + r), od = *slot(r);
 #pragma unroll
-        for (int wc = 0; wc < 4; wc++) {
-            const uint32_t a = (&od.x)[wc], b = (&nw.x)[wc];
-            S[4 * wc + 0] = dp4a_u8s8(__byte_perm(a, b, 0x0040), 0x000001ffu, S[4 * wc + 0]);
-            S[4 * wc + 1] = dp4a_u8s8(__byte_perm(a, b, 0x0051), 0x000001ffu, S[4 * wc + 1]);
-            S[4 * wc + 2] = dp4a_u8s8(__byte_perm(a, b, 0x0062), 0x000001ffu, S[4 * wc + 2]);
-            S[4 * wc + 3] = dp4a_u8s8(__byte_perm(a, b, 0x0073), 0x000001ffu, S[4 * wc + 3]);
+            for (int wc = 0; wc < 4; wc++) {
+                const uint32_t a = (&od.x)[wc], b = (&nw.x)[wc];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    S[4 * wc + j] = dp4a_u8s8(b, 0x01u << (8 * j), dp4a_u8s8(a, 0xffu << (8 * j), S[4 * wc + j]));
+            }
         }
     }
 }
@@ -593,8 +596,11 @@ __global__ void __launch_bounds__(128) conv_box_kernel(RowSource rs, uint8_t *__
     if (wg * 30 >= (int)nchunks) return;
     const int chunk = wg * 30 - 1 + (int)(threadIdx.x & 31);
     const int ys = blockIdx.y * RH;
-    if (ys >= R && ys + RH + R <= rs.h) conv_box_body<K, RH, true>(rs, dst, nchunks, chunk, ys, M, C, ring);
-    else conv_box_body<K, RH, false>(rs, dst, nchunks, chunk, ys, M, C, ring);
+    const bool inner = ys >= R && ys + RH + R <= rs.h;
+    const bool edge = wg == 0 || wg * 30 + 30 >= (int)nchunks;  // this warp holds the raster's first or last chunk
+    if (inner && !edge) conv_box_body<K, RH, true, false>(rs, dst, nchunks, chunk, ys, M, C, ring);
+    else if (inner) conv_box_body<K, RH, true, true>(rs, dst, nchunks, chunk, ys, M, C, ring);
+    else conv_box_body<K, RH, false, true>(rs, dst, nchunks, chunk, ys, M, C, ring);
 }
 
 // all coefficients equal to a > 0, and (sum * M + C) >> 24 == floor((2 a sum + div) / (2 div)) + bias within 0..255
@@ -631,8 +637,7 @@ static cudaError_t conv_box(const RowSource &rs, uint8_t *dst, uint32_t w, uint3
         if (grid.y > 65535u) return cudaErrorInvalidValue;                                    \
         launch(conv_box_kernel<K, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, M, C);        \
     } while (0)
-    if (g_variant == 9) PPMX_BOX_LAUNCH(8);
-    else if (g_variant == 10) PPMX_BOX_LAUNCH(32);
+    if (g_variant == 10) PPMX_BOX_LAUNCH(32);
     else if (g_variant == 11) PPMX_BOX_LAUNCH(64);
     else PPMX_BOX_LAUNCH(16);
 #undef PPMX_BOX_LAUNCH
