@@ -59,6 +59,24 @@ __device__ __forceinline__ double cubic(double x)
     return r;
 }
 
+// The 4 taps of the bicubic stencil sit at u = floor(n) - 1 + i, so the argument n - u is 1+f, f, f-1, f-2 with
+// f = n - floor(n) in [0, 1) (the subtraction is exact): taps 1 and 2 always take the |x| <= 1 polynomial (ref:481-483),
+// tap 3 always the 1 < |x| <= 2 one (ref:484-487), and tap 0 too except for f == 0, where |x| == 1 and BOTH polynomials
+// give exactly +0.0.  The "r = 0.0 + t" of ref:487 is skipped: t is never -0.0 (a sum that cancels rounds to +0.0).
+// Same operations in the same order as `cubic`, minus the branch not taken: 6 resp. 8 FP64 instructions instead of 16.
+__device__ __forceinline__ double cubic_near(double x)  // |x| <= 1
+{
+    const double a1 = fabs(x), a2 = dmul(a1, a1), a3 = dmul(a2, a1);
+    return dadd(dsub(dmul(1.5, a3), dmul(2.5, a2)), 1.0);
+}
+__device__ __forceinline__ double cubic_far(double x)  // 1 <= |x| <= 2
+{
+    const double a1 = fabs(x), a2 = dmul(a1, a1), a3 = dmul(a2, a1);
+    double t = dadd(dmul(-0.5, a3), dmul(2.5, a2));
+    t = dsub(t, dmul(4.0, a1));
+    return dadd(t, 2.0);
+}
+
 __device__ __forceinline__ double round_half_up(double v) { return floor(dadd(v, 0.5)); }  // ref:27
 
 // ------------------------------------------------------------------------------------------
@@ -84,8 +102,11 @@ __global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__re
     const double rx = round_half_up(nX), ry = round_half_up(nY);
 
     uint32_t r = 0, g = 0, b = 0;  // uncovered output stays 0 (ref:727)
-    if (rx < (double)w && ry < (double)h && ry >= 0.0 && rx >= 0.0) {                         // ref:744
-        if (rx > 1.0 && ry > 1.0 && rx < (double)(uint32_t)(w - 2u) && ry < (double)(uint32_t)(h - 2u)) {  // ref:752
+    // rx, ry are integer-valued and far inside the int range, so the comparisons of ref:744,752 are done on integers
+    // (the alu pipe is idle, the FP64 pipe is the bottleneck); w - 2u wraps for w < 2 exactly like the reference's
+    const int irx = (int)rx, iry = (int)ry;
+    if ((uint32_t)irx < w && (uint32_t)iry < h) {                                              // ref:744
+        if (irx > 1 && iry > 1 && (uint32_t)irx < w - 2u && (uint32_t)iry < h - 2u) {          // ref:752
             const double fx = floor(nX), fy = floor(nY);
             double wx[4], wy[4];
             int u0 = (int)(fx - 1.0), v0 = (int)(fy - 1.0);
@@ -93,8 +114,8 @@ __global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__re
             for (int i = 0; i < 4; i++) {
                 int u = (int)dadd(dsub(fx, 1.0), (double)i);  // ref:761
                 int v = (int)dadd(dsub(fy, 1.0), (double)i);  // ref:758
-                wx[i] = cubic(dsub(nX, (double)u));
-                wy[i] = cubic(dsub(nY, (double)v));
+                wx[i] = (i == 1 || i == 2) ? cubic_near(dsub(nX, (double)u)) : cubic_far(dsub(nX, (double)u));
+                wy[i] = (i == 1 || i == 2) ? cubic_near(dsub(nY, (double)v)) : cubic_far(dsub(nY, (double)v));
             }
             double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
@@ -109,8 +130,12 @@ __global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__re
                     word_to_double4<CONV>(__funnelshift_r(q0w, q1w, sh), d[0]);
                     word_to_double4<CONV>(__funnelshift_r(q1w, q2w, sh), d[1]);
                     word_to_double4<CONV>(__funnelshift_r(q2w, q3w, sh), d[2]);
+                    // (0.0 + x == x up to the sign of a zero, which no later step can see: first terms are not added)
+                    p0 = dmul(d[0][0], wx[0]);
+                    p1 = dmul(d[0][1], wx[0]);
+                    p2 = dmul(d[0][2], wx[0]);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {  // ref:762-764
+                    for (int i = 1; i < 4; i++) {  // ref:762-764
                         p0 = dadd(p0, dmul(d[(3 * i) >> 2][(3 * i) & 3], wx[i]));
                         p1 = dadd(p1, dmul(d[(3 * i + 1) >> 2][(3 * i + 1) & 3], wx[i]));
                         p2 = dadd(p2, dmul(d[(3 * i + 2) >> 2][(3 * i + 2) & 3], wx[i]));
@@ -124,22 +149,17 @@ __global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__re
                         p2 = dadd(p2, dmul(u8_to_double(row[3 * i + 2]), wx[i]));
                     }
                 }
-                q0 = dadd(q0, dmul(p0, wy[j]));  // ref:766-768
-                q1 = dadd(q1, dmul(p1, wy[j]));
-                q2 = dadd(q2, dmul(p2, wy[j]));
+                q0 = j ? dadd(q0, dmul(p0, wy[j])) : dmul(p0, wy[0]);  // ref:766-768
+                q1 = j ? dadd(q1, dmul(p1, wy[j])) : dmul(p1, wy[0]);
+                q2 = j ? dadd(q2, dmul(p2, wy[j])) : dmul(p2, wy[0]);
             }
-            if (q0 < 0.0) q0 = 0.0;  // ref:771-777
-            if (q1 < 0.0) q1 = 0.0;
-            if (q2 < 0.0) q2 = 0.0;
-            if (q0 >= 256.0) q0 = 255.0;
-            if (q1 >= 256.0) q1 = 255.0;
-            if (q2 >= 256.0) q2 = 255.0;
-            // truncation (ref:779-781) of a value in [0, 256): floor, as the low word of q + 1.5*2^52
-            r = (uint32_t)__double2loint(__dadd_rd(q0, 6755399441055744.0));
-            g = (uint32_t)__double2loint(__dadd_rd(q1, 6755399441055744.0));
-            b = (uint32_t)__double2loint(__dadd_rd(q2, 6755399441055744.0));
+            // ref:771-781: q < 0 -> 0, q >= 256 -> 255, else truncate.  floor(q) = the low word of q + 1.5*2^52 rounded
+            // down (|q| is small); floor(q) < 0 <=> q < 0 and floor(q) >= 256 <=> q >= 256, so the clamp is an integer one
+            r = (uint32_t)min(max(__double2loint(__dadd_rd(q0, 6755399441055744.0)), 0), 255);
+            g = (uint32_t)min(max(__double2loint(__dadd_rd(q1, 6755399441055744.0)), 0), 255);
+            b = (uint32_t)min(max(__double2loint(__dadd_rd(q2, 6755399441055744.0)), 0), 255);
         } else {  // nearest, ref:783
-            const uint8_t *p = src + ((size_t)(int)ry * w + (size_t)(int)rx) * 3;
+            const uint8_t *p = src + ((size_t)iry * w + (size_t)irx) * 3;
             r = p[0];
             g = p[1];
             b = p[2];
@@ -245,7 +265,8 @@ __global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource sr
                 double d[4];
                 word_to_double4<CONV>(wd[q], d);
 #pragma unroll
-                for (int b = 0; b < 4; b++) acc[4 * q + b] = dadd(acc[4 * q + b], dmul(d[b], wz));
+                for (int b = 0; b < 4; b++)  // the first tap is not added to 0.0 (same value; a zero's sign is never seen)
+                    acc[4 * q + b] = (z0 + u) ? dadd(acc[4 * q + b], dmul(d[b], wz)) : dmul(d[b], wz);
             }
         }
     }
@@ -300,9 +321,9 @@ __global__ void __launch_bounds__(128) imresize_colsK_kernel(const uint8_t *__re
             double d[NS][4];
 #pragma unroll
             for (int j = 0; j < NS; j++) word_to_double4<CONV>(__funnelshift_r(q[j], q[j + 1], sh), d[j]);
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            double s0 = dmul(d[0][0], wk[0]), s1 = dmul(d[0][1], wk[0]), s2 = dmul(d[0][2], wk[0]);  // 0.0 + x == x
 #pragma unroll
-            for (int z = 0; z < K; z++) {  // ref:852-858, tap order
+            for (int z = 1; z < K; z++) {  // ref:852-858, tap order
                 s0 = dadd(s0, dmul(d[(3 * z) >> 2][(3 * z) & 3], wk[z]));
                 s1 = dadd(s1, dmul(d[(3 * z + 1) >> 2][(3 * z + 1) & 3], wk[z]));
                 s2 = dadd(s2, dmul(d[(3 * z + 2) >> 2][(3 * z + 2) & 3], wk[z]));
