@@ -40,7 +40,7 @@ __device__ __forceinline__ void word_to_double4(uint32_t w, double (&d)[4])
 {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const bool xu = (CONV == 0) || (CONV == 2 && (i & 1) == 0);
+        const bool xu = (CONV == 0) || (CONV == 2 && (i & 1) == 0) || (CONV == 3 && i != 3);  // CONV 3: three of four on the XU pipe
         d[i] = xu ? cvt_byte_xu(w >> (8 * i)) : cvt_byte_dp(w, i);
     }
 }
@@ -77,6 +77,16 @@ __device__ __forceinline__ double cubic_far(double x)  // 1 <= |x| <= 2
     return dadd(t, 2.0);
 }
 
+// floor of a small double (|v| < 2^31) on the FP64 pipe: v + 1.5*2^52 rounded toward -inf is floor(v) + 1.5*2^52
+// exactly; its low word is floor(v) as an int32 and subtracting the constant again gives floor(v) as a double
+__device__ __forceinline__ int floor_int(double v) { return __double2loint(__dadd_rd(v, 6755399441055744.0)); }
+__device__ __forceinline__ double floor_both(double v, int &i)
+{
+    const double t = __dadd_rd(v, 6755399441055744.0);
+    i = __double2loint(t);
+    return dsub(t, 6755399441055744.0);
+}
+
 __device__ __forceinline__ double round_half_up(double v) { return floor(dadd(v, 0.5)); }  // ref:27
 
 // ------------------------------------------------------------------------------------------
@@ -88,7 +98,7 @@ template <bool WORDS, int CONV>
 __global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__restrict__ src,
                                                              uint8_t *__restrict__ dst, uint32_t w, uint32_t h,
                                                              uint32_t nw, uint32_t nh, double cs, double sn,
-                                                             int xc, int yc, int xo, int yo)
+                                                             int xc, int yc, int xo, int yo, double xcd, double ycd)
 {
     PDL_PROLOGUE();
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,25 +107,28 @@ __global__ void __launch_bounds__(256) rotate_bicubic_kernel(const uint8_t *__re
     uint8_t *out = dst + ((size_t)y * nw + x) * 3;
 
     const int x0 = ((int)x - xo) - xc, y0 = ((int)y - yo) - yc;                              // ref:731-735
-    const double nX = dadd(dadd(dmul(cs, (double)x0), dmul(sn, (double)y0)), (double)xc);     // ref:741
-    const double nY = dadd(dadd(-dmul(sn, (double)x0), dmul(cs, (double)y0)), (double)yc);    // ref:742
-    const double rx = round_half_up(nX), ry = round_half_up(nY);
-
+    const double xd = (double)x0, yd = (double)y0;
+    const double nX = dadd(dadd(dmul(cs, xd), dmul(sn, yd)), xcd);     // ref:741
+    const double nY = dadd(dadd(-dmul(sn, xd), dmul(cs, yd)), ycd);    // ref:742
     uint32_t r = 0, g = 0, b = 0;  // uncovered output stays 0 (ref:727)
-    // rx, ry are integer-valued and far inside the int range, so the comparisons of ref:744,752 are done on integers
-    // (the alu pipe is idle, the FP64 pipe is the bottleneck); w - 2u wraps for w < 2 exactly like the reference's
-    const int irx = (int)rx, iry = (int)ry;
+    // round(n) = floor(n + 0.5) (ref:27) is integer-valued and far inside the int range, so it is taken as the low word
+    // of (n + 0.5) + 1.5*2^52 rounded down -- no FRND/F2I on the 16-lane XU pipe -- and the comparisons of ref:744,752
+    // are done on integers (the alu pipe is idle, the FP64 pipe is the bottleneck); w - 2u wraps for w < 2 exactly
+    // like the reference's unsigned arithmetic
+    const int irx = floor_int(dadd(nX, 0.5)), iry = floor_int(dadd(nY, 0.5));
     if ((uint32_t)irx < w && (uint32_t)iry < h) {                                              // ref:744
         if (irx > 1 && iry > 1 && (uint32_t)irx < w - 2u && (uint32_t)iry < h - 2u) {          // ref:752
-            const double fx = floor(nX), fy = floor(nY);
+            int fxi, fyi;
+            const double fx = floor_both(nX, fxi), fy = floor_both(nY, fyi);
             double wx[4], wy[4];
-            int u0 = (int)(fx - 1.0), v0 = (int)(fy - 1.0);
+            const int u0 = fxi - 1, v0 = fyi - 1;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                int u = (int)dadd(dsub(fx, 1.0), (double)i);  // ref:761
-                int v = (int)dadd(dsub(fy, 1.0), (double)i);  // ref:758
-                wx[i] = (i == 1 || i == 2) ? cubic_near(dsub(nX, (double)u)) : cubic_far(dsub(nX, (double)u));
-                wy[i] = (i == 1 || i == 2) ? cubic_near(dsub(nY, (double)v)) : cubic_far(dsub(nY, (double)v));
+                // ref:758,761 compute u = floor(n) - 1 + i in double, cast it to int and convert it back for n - u:
+                // the double is integer-valued, so the round trip (two XU-pipe conversions) is the identity
+                const double u = dadd(dsub(fx, 1.0), (double)i), v = dadd(dsub(fy, 1.0), (double)i);
+                wx[i] = (i == 1 || i == 2) ? cubic_near(dsub(nX, u)) : cubic_far(dsub(nX, u));
+                wy[i] = (i == 1 || i == 2) ? cubic_near(dsub(nY, v)) : cubic_far(dsub(nY, v));
             }
             double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
@@ -180,14 +193,18 @@ cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_
     dim3 block(32, 8), grid((nw + 31) / 32, (nh + 7) / 8);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
     if ((w % 4u) == 0 && aligned4(src) && g_variant != 1) {
+        // with the index conversions off the XU pipe (floor_int/floor_both) all 48 byte conversions fit there:
+        // measured 56.5 Gpix/s (CONV 0) vs 53.5 (3 of 4 on XU) vs 51.0 (half) vs 47.8 (all on the FP64 pipe)
         if (g_variant == 2)
-            launch(rotate_bicubic_kernel<true, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+            launch(rotate_bicubic_kernel<true, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
         else if (g_variant == 3)
-            launch(rotate_bicubic_kernel<true, 0>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+            launch(rotate_bicubic_kernel<true, 2>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
+        else if (g_variant == 4)
+            launch(rotate_bicubic_kernel<true, 3>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
         else
-            launch(rotate_bicubic_kernel<true, 2>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+            launch(rotate_bicubic_kernel<true, 0>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
     } else {
-        launch(rotate_bicubic_kernel<false, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo);
+        launch(rotate_bicubic_kernel<false, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
     }
     return PPMX_LAUNCHED();
 }
@@ -280,6 +297,11 @@ __global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource sr
     reinterpret_cast<vec_t *>(dst + (size_t)y * row_bytes)[xv] = ov;
 }
 
+// (A pipelined variant -- a CTA owning 8 consecutive output rows, tables staged once, the next group of four source
+// vectors in flight in a second register buffer while the current one is multiplied -- measured SLOWER than the
+// one-row-per-CTA kernel above: 67.6 vs 73.1 Gpix/s at x1.5 and 135 vs 178 at x0.5, profiles/r1_sweep_fp64.txt.
+// Many short CTAs hide the two trips to memory better than a software pipeline at 78 registers.)
+
 // width pass, fast path (w % 4 == 0, aligned, 4 <= K <= 8): one thread = one output column for a
 // run of rows; its K weights and indices live in registers.  When the K taps are consecutive source
 // pixels (always, except where the table mirrors at the raster's edge) their 3K bytes are fetched as
@@ -368,8 +390,11 @@ static void launch_colsK(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t 
         else if (g_variant == 3)
             launch(imresize_colsK_kernel<K, 0>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
                    dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
-        else
+        else if (g_variant == 4)
             launch(imresize_colsK_kernel<K, 2>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
+                   dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
+        else  // three of four byte conversions on the XU pipe: 1-3 % faster than half/half once the first-tap adds are gone
+            launch(imresize_colsK_kernel<K, 3>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
                    dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
     }
 }
@@ -465,7 +490,8 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
                 if (narrow) launch(imresize_rows16_kernel<2, 2>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (g_variant == 2) launch(imresize_rows16_kernel<1, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (g_variant == 3) launch(imresize_rows16_kernel<0, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else launch(imresize_rows16_kernel<2, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (g_variant == 4) launch(imresize_rows16_kernel<2, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else launch(imresize_rows16_kernel<3, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
             }
             return cudaGetLastError();
         }

@@ -413,7 +413,7 @@ def test_tuning_variants_are_bit_identical(gpu, orc):
     wt2, ix2 = gpu.calc_contributions(256, 128, 0.5)
     coef = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]])
     try:
-        for v in (0, 1, 2, 3, 4, 5):
+        for v in (0, 1, 2, 3, 4, 5, 6, 7, 8):
             for pdl in (1, 0):
                 gpu.set_tuning("variant", v)
                 gpu.set_tuning("pdl", pdl)
