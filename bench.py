@@ -46,6 +46,7 @@ WORKLOADS = {
     "mono_16k": (16384, 16384, 2, 3.125, "16384x16384 -> Bayer bilevel P4 bits, two rasters per step"),
     "fliph_16k": (16384, 16384, 2, 6.0, "16384x16384 horizontal flip, two rasters per step"),
     "rot90_16k": (16384, 16384, 2, 6.0, "16384x16384 rotate 90, two rasters per step"),
+    "levels": (4096, 4096, 8, 6.0, "4096x4096 levels (256-entry table on every byte, extension), 8 rasters per step"),
     "conv3": (8192, 8192, 2, 6.0, "8192x8192 3x3 blur (extension, config 3), 2 rasters per step"),
     "conv7": (8192, 8192, 2, 6.0, "8192x8192 7x7 box (extension, config 3), 2 rasters per step"),
     "resize_up": (4096, 4096, 2, None, "4096x4096 -w6144 bicubic resize (FP64), 2 rasters per step"),
@@ -54,7 +55,7 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "gray_hist"
 PER_OP = ["gray", "gray_hist", "mono", "fliph", "flipv", "rot90", "rot180", "gray_16k", "mono_16k", "fliph_16k",
-          "rot90_16k", "conv3", "conv7", "resize_up", "resize_down", "rot30"]
+          "rot90_16k", "levels", "conv3", "conv7", "resize_up", "resize_down", "rot30"]
 
 
 def traffic_for(name):
@@ -176,6 +177,8 @@ class Runner:
         elif name in ("rot90", "rot180", "rot30"):
             op = g.rotate_op(int(name[3:]), w, h)
             self.ops = [(op, op.new_width, op.new_height, op.new_width * op.new_height * 3)]
+        elif name == "levels":
+            self.ops = [(g.levels_op(g.levels_lut_linear(16, 235)), w, h, w * h * 3)]
         elif name in ("conv3", "conv7"):
             if name == "conv3":
                 coef, div = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], np.int32), 16

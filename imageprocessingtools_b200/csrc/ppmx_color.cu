@@ -595,4 +595,121 @@ cudaError_t extract_r(const uint8_t *src, uint8_t *dst, size_t npix, cudaStream_
 }
 
 
+
+// ------------------------------------------------------------------------------------------
+// EXTENSION (no reference counterpart, parity unpinned): levels = every byte through a 256-entry table.
+// The table travels as a kernel argument (256 B) and is unpacked to one word per entry in shared memory (1 KB), so
+// entry v sits in bank v % 32 and two lanes collide only when their bytes differ by a multiple of 32.  A thread maps
+// one 16-byte vector: 16 LDS, 12 PRMT to pack, HBM-bound (6 B/px on RGB8).
+// ------------------------------------------------------------------------------------------
+struct LevelsLut {
+    uint32_t w[64];  // 256 entries, 4 per word
+};
+
+__device__ __forceinline__ uint32_t levels_word(const uint32_t *lut_s, uint32_t v)
+{
+    const uint32_t a = lut_s[v & 0xFFu], b = lut_s[(v >> 8) & 0xFFu], c = lut_s[(v >> 16) & 0xFFu], d = lut_s[v >> 24];
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+__global__ void __launch_bounds__(256) levels_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t nbytes,
+                                                     const LevelsLut lut)
+{
+    pdl_trigger();
+    __shared__ uint32_t lut_s[256];
+    lut_s[threadIdx.x] = (lut.w[threadIdx.x >> 2] >> (8 * (threadIdx.x & 3))) & 0xFFu;
+    __syncthreads();
+    const size_t nvec = nbytes / 16, g = (size_t)blockIdx.x * 256 + threadIdx.x;
+    pdl_wait();
+    if (g < nvec) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src) + g);
+        uint4 o;
+        o.x = levels_word(lut_s, v.x);
+        o.y = levels_word(lut_s, v.y);
+        o.z = levels_word(lut_s, v.z);
+        o.w = levels_word(lut_s, v.w);
+        reinterpret_cast<uint4 *>(dst)[g] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < nbytes - nvec * 16) {  // ragged tail
+        const size_t i = nvec * 16 + threadIdx.x;
+        dst[i] = (uint8_t)lut_s[src[i]];
+    }
+}
+
+// The same with one table COLUMN PER LANE, like the histogram: lut_l[v][lane] (32 KB), so lane l only reads bank l
+// and the 16 lookups of a vector never collide, whatever the pixel values; one fat CTA per SM fills its copy once
+// and strides over the raster with two vectors in flight per thread.  (The one-word-per-entry kernel above
+// serialises ~3.5 ways on noise: 0.52 of the HBM roofline; it remains for small rasters and as variant 1.)
+constexpr int LV_THREADS = 1024;
+constexpr size_t LV_SMEM = 256 * 32 * sizeof(uint32_t);
+
+__device__ __forceinline__ uint32_t levels_word_lane(const uint32_t *col, uint32_t v)
+{
+    const uint32_t a = col[(v & 0xFFu) << 5], b = col[((v >> 8) & 0xFFu) << 5], c = col[((v >> 16) & 0xFFu) << 5], d = col[(v >> 24) << 5];
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+__device__ __forceinline__ uint4 levels_vec_lane(const uint32_t *col, uint4 v)
+{
+    return make_uint4(levels_word_lane(col, v.x), levels_word_lane(col, v.y), levels_word_lane(col, v.z), levels_word_lane(col, v.w));
+}
+
+__global__ void __launch_bounds__(LV_THREADS, 1) levels_lanes_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
+                                                                     size_t nvec, size_t nbytes, const LevelsLut lut)
+{
+    pdl_trigger();
+    extern __shared__ __align__(16) uint32_t lut_l[];
+    for (uint32_t i = threadIdx.x; i < 256 * 32; i += LV_THREADS) {
+        const uint32_t v = i >> 5;
+        lut_l[i] = (lut.w[v >> 2] >> (8 * (v & 3))) & 0xFFu;
+    }
+    __syncthreads();
+    const uint32_t *col = lut_l + (threadIdx.x & 31u);
+    pdl_wait();
+    const size_t stride = (size_t)gridDim.x * LV_THREADS;
+    size_t g = (size_t)blockIdx.x * LV_THREADS + threadIdx.x;
+    for (; g + stride < nvec; g += 2 * stride) {
+        const uint4 a = __ldg(src + g), b = __ldg(src + g + stride);
+        dst[g] = levels_vec_lane(col, a);
+        dst[g + stride] = levels_vec_lane(col, b);
+    }
+    if (g < nvec) dst[g] = levels_vec_lane(col, __ldg(src + g));
+    if (blockIdx.x == 0 && threadIdx.x < nbytes - nvec * 16) {  // ragged tail
+        const size_t i = nvec * 16 + threadIdx.x;
+        reinterpret_cast<uint8_t *>(dst)[i] = (uint8_t)col[(uint32_t)reinterpret_cast<const uint8_t *>(src)[i] << 5];
+    }
+}
+
+__global__ void __launch_bounds__(256) levels_bytes_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                           size_t nbytes, const LevelsLut lut)
+{  // unaligned rasters
+    PDL_PROLOGUE();
+    __shared__ uint32_t lut_s[256];
+    lut_s[threadIdx.x] = (lut.w[threadIdx.x >> 2] >> (8 * (threadIdx.x & 3))) & 0xFFu;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nbytes; i += (size_t)gridDim.x * 256) dst[i] = (uint8_t)lut_s[src[i]];
+}
+
+cudaError_t levels(const uint8_t *src, uint8_t *dst, size_t nbytes, const uint8_t *lut, cudaStream_t s)
+{
+    if (!lut) return cudaErrorInvalidValue;
+    if (!nbytes) return cudaSuccess;
+    LevelsLut l;
+    for (int i = 0; i < 64; i++)
+        l.w[i] = (uint32_t)lut[4 * i] | (uint32_t)lut[4 * i + 1] << 8 | (uint32_t)lut[4 * i + 2] << 16 | (uint32_t)lut[4 * i + 3] << 24;
+    if (aligned16(src) && aligned16(dst) && nbytes >= (size_t)1 << 20 && g_variant != 1) {
+        static bool ok[64] = {};
+        allow_smem(levels_lanes_kernel, LV_SMEM, ok);
+        const size_t nvec = nbytes / 16, want = (nvec + LV_THREADS - 1) / LV_THREADS, wave = (size_t)sm_count();
+        launch(levels_lanes_kernel, dim3((unsigned)(want < wave ? want : wave)), dim3(LV_THREADS), LV_SMEM, s,
+               reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), nvec, nbytes, l);
+    } else if (aligned16(src) && aligned16(dst) && nbytes >= 16) {
+        const size_t nvec = nbytes / 16, ctas = (nvec + 255) / 256;
+        if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+        launch(levels_kernel, dim3((unsigned)ctas), dim3(256), 0, s, src, dst, nbytes, l);
+    } else {
+        launch(levels_bytes_kernel, dim3(wave_grid(nbytes, 256, 8)), dim3(256), 0, s, src, dst, nbytes, l);
+    }
+    return PPMX_LAUNCHED();
+}
+
 }  // namespace ppmx

@@ -273,6 +273,9 @@ extern "C" int ppmx_gpu_op_output(const ppmx_op *op, uint32_t w, uint32_t h, int
     case PPMX_OP_CONV:
         if (layout != PPMX_LAYOUT_RGB8) return PPMX_ERROR;
         break;
+    case PPMX_OP_LEVELS:
+        if (layout == PPMX_LAYOUT_BITS) return PPMX_ERROR;
+        break;
     case PPMX_OP_HIST_GRAY:
         if (layout != PPMX_LAYOUT_RGB8) return PPMX_ERROR;
         nw = nh = 0;
@@ -351,6 +354,10 @@ static int launch_op(const ppmx_op *op, const uint8_t *d_src, uint32_t w, uint32
     case PPMX_OP_CONV:
         if (!op->conv_coef) return fail("conv: no coefficients");
         CK(ppmx::conv(d_src, d_dst, w, h, op->conv_k, op->conv_coef, op->conv_div, op->conv_bias, band, s), "conv");
+        return PPMX_OK;
+    case PPMX_OP_LEVELS:
+        if (!op->levels_lut) return fail("levels: no table");
+        CK(ppmx::levels(d_src, d_dst, npix * (layout == PPMX_LAYOUT_RGB8 ? 3 : 1), op->levels_lut, s), "levels");
         return PPMX_OK;
     default:
         return fail("unknown operator kind");
@@ -532,6 +539,7 @@ static int run_chain(Chain &ch, const ppmx_op *ops, int nops, const std::vector<
             /* fall through */
         case PPMX_OP_IMRESIZE:
         case PPMX_OP_CONV:
+        case PPMX_OP_LEVELS:
             if (op_on(c, ch.lane, &op, ch.buff, &out, t, nullptr) != PPMX_OK) return PPMX_ERROR;
             ch.drop_new();
             ch.newb = out;

@@ -259,6 +259,40 @@ int ppmx_plan_chain(const ppmx_args_flag *f, unsigned int output_width_size, dou
 int ppmx_plan_chain_ext(const ppmx_args_flag *f, unsigned int output_width_size, double angle, unsigned int width,
                         unsigned int height, int conv_preset, ppmx_plan *plan)
 {
+    return ppmx_plan_chain_ext2(f, output_width_size, angle, width, height, conv_preset, -1, -1, plan);
+}
+
+/* EXTENSION: levels table, round(x) = floor(x + 0.5) as ref:27, in integers */
+int ppmx_levels_lut_linear(int lo, int hi, unsigned char lut[256])
+{
+    int v;
+    if (lo < 0 || hi > 255 || lo >= hi) return PPMX_ERROR;
+    for (v = 0; v < 256; v++) {
+        if (v <= lo) lut[v] = 0;
+        else if (v >= hi) lut[v] = 255;
+        else lut[v] = (unsigned char)((2 * (v - lo) * 255 + (hi - lo)) / (2 * (hi - lo)));
+    }
+    return PPMX_OK;
+}
+
+int ppmx_levels_points_from_hist(const unsigned long long hist[256], unsigned int clip_permille, int *lo, int *hi)
+{
+    unsigned long long total = 0, allow, acc;
+    int v, a, b;
+    for (v = 0; v < 256; v++) total += hist[v];
+    if (!total || clip_permille > 499) return PPMX_ERROR;
+    allow = total / 1000 * clip_permille + total % 1000 * clip_permille / 1000;
+    for (a = 0, acc = 0; a < 255 && acc + hist[a] <= allow; a++) acc += hist[a];
+    for (b = 255, acc = 0; b > 0 && acc + hist[b] <= allow; b--) acc += hist[b];
+    if (a >= b) return PPMX_ERROR;
+    *lo = a;
+    *hi = b;
+    return PPMX_OK;
+}
+
+int ppmx_plan_chain_ext2(const ppmx_args_flag *f, unsigned int output_width_size, double angle, unsigned int width,
+                         unsigned int height, int conv_preset, int levels_lo, int levels_hi, ppmx_plan *plan)
+{
     unsigned int w = width, h = height;
     /* the condition of ref:1138,1143,1148,1153; an extension stage counts like -w / -r */
     int renew = f->resize_enable || f->rotate_enable;
@@ -309,6 +343,17 @@ int ppmx_plan_chain_ext(const ppmx_args_flag *f, unsigned int output_width_size,
         case PPMX_CONV_EDGE: op->conv_k = 3; op->conv_div = 1; op->conv_coef = k_edge; break;
         default: printf("Error: unknown convolution preset\n"); goto bad;
         }
+        renew = 1;
+    }
+    if (levels_lo >= 0) { /* second extension stage */
+        ppmx_op *op = &plan->ops[n++];
+        if (ppmx_levels_lut_linear(levels_lo, levels_hi, plan->levels_lut) != PPMX_OK) {
+            printf("Error: invalid levels (need 0 <= lo < hi <= 255)\n");
+            goto bad;
+        }
+        op->kind = PPMX_OP_LEVELS;
+        op->renew_before = renew;
+        op->levels_lut = plan->levels_lut;
         renew = 1;
     }
     if (f->gray_enable) { /* ref:1137-1140 */
@@ -549,7 +594,8 @@ int ppmx_doProcessPPM(ppmx_image_handler *h)
     if (ppmx_parse_header(h->file_buffer, h->filesize, &w, &hh, &mx, &off) != PPMX_OK) goto done;
     h->imginfo.width = w; h->imginfo.height = hh; h->imginfo.max_color = mx; h->index_buffer = off;
 
-    if (ppmx_plan_chain_ext(&h->arg_flag, h->output_width_size, h->angle, w, hh, h->conv_preset, &plan) != PPMX_OK) goto done;
+    if (ppmx_plan_chain_ext2(&h->arg_flag, h->output_width_size, h->angle, w, hh, h->conv_preset,
+                             h->levels_enable ? h->levels_lo : -1, h->levels_hi, &plan) != PPMX_OK) goto done;
     if (plan.nops == 0) { printf("Error: no data to write\n"); goto done; } /* ref:235 */
 
     /* the largest raster any stage can hand to the writer is RGB at the final size */
@@ -638,6 +684,14 @@ int ppmx_main(int argc, char *argv[])
             if (hd.conv_preset) BAIL("Error: Duplicate options not allowed\n");
             hd.conv_preset = a[1] == 's' ? PPMX_CONV_SHARPEN : a[1] == 'e' ? PPMX_CONV_EDGE
                              : a[5] == '7' ? PPMX_CONV_BLUR7 : PPMX_CONV_BLUR3;
+        } else if (strncmp(a + 1, "levels", 6) == 0) { /* EXTENSION flag -levelsLO-HI, e.g. -levels16-235 */
+            int lo = -1, hi = -1, used = 0;
+            if (hd.levels_enable) BAIL("Error: Duplicate options not allowed\n");
+            if (sscanf(a + 7, "%d-%d%n", &lo, &hi, &used) != 2 || a[7 + used] != 0 || lo < 0 || hi > 255 || lo >= hi)
+                BAIL("Error: invalid option for levels.\n");
+            hd.levels_enable = 1;
+            hd.levels_lo = lo;
+            hd.levels_hi = hi;
         } else if (strcmp(a + 1, "gray") == 0) {
             if (hd.arg_flag.gray_enable) BAIL("Error: Duplicate options not allowed\n");
             if (hd.arg_flag.mono_enable) BAIL("Error: Conflicting options not allowed\n");

@@ -40,6 +40,9 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
 cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef /*host*/,
                  int32_t div, int32_t bias, const Band &band, cudaStream_t s);
 
+// every byte of the raster through a 256-entry table (host pointer)
+cudaError_t levels(const uint8_t *src, uint8_t *dst, size_t nbytes, const uint8_t *lut /*host*/, cudaStream_t s);
+
 unsigned long long launch_count();
 
 }  // namespace ppmx

@@ -20,7 +20,7 @@ CLI = os.path.join(PKG, "ppmx-b200")
 FT_PPM, FT_PGM, FT_PBM = 0, 1, 2
 LAYOUT_RGB8, LAYOUT_R8, LAYOUT_BITS = 0, 1, 2
 OP_GRAY, OP_MONO, OP_FLIP, OP_ROTATE, OP_IMRESIZE, OP_MONO_BITS, OP_PACK_PBM, OP_EXTRACT_R = range(8)
-OP_CONV, OP_HIST_GRAY, OP_GRAY_HIST = 16, 17, 18
+OP_CONV, OP_HIST_GRAY, OP_GRAY_HIST, OP_LEVELS = 16, 17, 18, 19
 
 _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
@@ -40,7 +40,7 @@ class PpmxOp(C.Structure):
                 ("dim", C.c_int32), ("out_size", C.c_int32), ("weights_sz", C.c_int32),
                 ("weights", _dblp), ("indices", _i32p),
                 ("conv_k", C.c_int32), ("conv_div", C.c_int32), ("conv_bias", C.c_int32), ("conv_coef", _i32p),
-                ("hist_out", C.POINTER(C.c_uint64))]
+                ("hist_out", C.POINTER(C.c_uint64)), ("levels_lut", C.POINTER(C.c_uint8))]
 
 
 class PpmxBand(C.Structure):
@@ -59,7 +59,7 @@ class _Contrib(C.Structure):
 
 
 class _Plan(C.Structure):
-    _fields_ = [("ops", PpmxOp * 8), ("nops", C.c_int), ("contrib", _Contrib * 2)]
+    _fields_ = [("ops", PpmxOp * 8), ("nops", C.c_int), ("contrib", _Contrib * 2), ("levels_lut", C.c_uint8 * 256)]
 
 
 _gpu = None
@@ -135,6 +135,10 @@ def host_lib() -> C.CDLL:
         H.ppmx_plan_chain.argtypes = [C.POINTER(_ArgsFlag), C.c_uint, C.c_double, C.c_uint, C.c_uint, C.POINTER(_Plan)]
         H.ppmx_plan_chain_ext.argtypes = [C.POINTER(_ArgsFlag), C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_int,
                                           C.POINTER(_Plan)]
+        H.ppmx_plan_chain_ext2.argtypes = [C.POINTER(_ArgsFlag), C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_int, C.c_int,
+                                           C.c_int, C.POINTER(_Plan)]
+        H.ppmx_levels_lut_linear.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        H.ppmx_levels_points_from_hist.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         H.ppmx_plan_free.argtypes = [C.POINTER(_Plan)]
         H.ppmx_plan_free.restype = None
         H.ppmx_band_plan.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, _u32p, _u32p]
@@ -209,12 +213,13 @@ def format_header(file_type: int, w: int, h: int, maxval: int = 255) -> bytes:
 
 class _PlanHolder:
     def __init__(self, resize_w=None, angle=None, gray=False, mono=False, flipv=False, fliph=False, w=0, h=0,
-                 conv_preset=0):
+                 conv_preset=0, levels=None):
         self.plan = _Plan()
         f = _ArgsFlag(bytes([int(resize_w is not None)]), bytes([int(angle is not None)]), bytes([int(flipv)]),
                       bytes([int(fliph)]), bytes([int(gray)]), bytes([int(mono)]))
-        rc = host_lib().ppmx_plan_chain_ext(C.byref(f), int(resize_w or 0), float(angle or 0), w, h, int(conv_preset),
-                                            C.byref(self.plan))
+        lo, hi = levels if levels is not None else (-1, -1)
+        rc = host_lib().ppmx_plan_chain_ext2(C.byref(f), int(resize_w or 0), float(angle or 0), w, h, int(conv_preset),
+                                             int(lo), int(hi), C.byref(self.plan))
         if rc != 0:
             raise PpmxError("ppmx_plan_chain failed")
 
@@ -356,11 +361,11 @@ class Ppmx:
         return data.reshape(h, w, 3)
 
     def process(self, img, resize_w: Optional[int] = None, angle: Optional[int] = None, gray=False, mono=False,
-                flipv=False, fliph=False, conv_preset: int = 0):
+                flipv=False, fliph=False, conv_preset: int = 0, levels=None):
         """The whole chain through ppmx_plan_chain + ppmx_gpu_apply (host raster in, writer bytes out)."""
         img = _img(img)
         h, w, _ = img.shape
-        ph = _PlanHolder(resize_w, angle, gray, mono, flipv, fliph, w, h, conv_preset)
+        ph = _PlanHolder(resize_w, angle, gray, mono, flipv, fliph, w, h, conv_preset, levels)
         try:
             if ph.plan.nops == 0:
                 raise PpmxError("Error: no data to write")
@@ -415,6 +420,35 @@ class Ppmx:
     def conv(self, img, coef, div: int = 1, bias: int = 0) -> np.ndarray:
         data, w, h, _, _ = self._one(img, self.conv_op(coef, div, bias), FT_PPM)
         return data.reshape(h, w, 3)
+
+    @staticmethod
+    def levels_op(lut) -> PpmxOp:
+        lut = np.ascontiguousarray(lut, np.uint8)
+        assert lut.size == 256
+        op = PpmxOp(kind=OP_LEVELS, levels_lut=lut.ctypes.data_as(C.POINTER(C.c_uint8)))
+        op._keep = lut
+        return op
+
+    def levels(self, img, lut) -> np.ndarray:
+        """Every byte through a 256-entry table (extension); RGB (h, w, 3) in, same shape out."""
+        data, w, h, _, _ = self._one(img, self.levels_op(lut), FT_PPM)
+        return data.reshape(h, w, 3)
+
+    @staticmethod
+    def levels_lut_linear(lo: int, hi: int) -> np.ndarray:
+        lut = np.zeros(256, np.uint8)
+        if host_lib().ppmx_levels_lut_linear(int(lo), int(hi), lut.ctypes.data_as(C.c_void_p)) != 0:
+            raise PpmxError("ppmx_levels_lut_linear: need 0 <= lo < hi <= 255")
+        return lut
+
+    @staticmethod
+    def levels_points_from_hist(bins, clip_permille: int = 5):
+        bins = np.ascontiguousarray(bins, np.uint64)
+        lo, hi = C.c_int(), C.c_int()
+        if host_lib().ppmx_levels_points_from_hist(bins.ctypes.data_as(C.c_void_p), int(clip_permille), C.byref(lo),
+                                                   C.byref(hi)) != 0:
+            raise PpmxError("ppmx_levels_points_from_hist: empty or flat histogram")
+        return lo.value, hi.value
 
     def hist_gray(self, img) -> np.ndarray:
         _, _, _, _, bins = self._one(img, PpmxOp(kind=OP_HIST_GRAY), FT_PGM, hist=True)

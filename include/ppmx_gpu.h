@@ -53,6 +53,7 @@ extern "C" {
 #define PPMX_OP_CONV 16     /* k x k integer convolution, mirror border, RGB8 -> RGB8       */
 #define PPMX_OP_HIST_GRAY 17 /* 256-bin histogram of (r+g+b)/3, RGB8 -> 256 x u64 (no image) */
 #define PPMX_OP_GRAY_HIST 18 /* gray and its histogram in one pass over the raster          */
+#define PPMX_OP_LEVELS 19   /* levels: every byte through a 256-entry table, RGB8 or R8, same layout out */
 
 typedef struct ppmx_op {
     int32_t kind;            /* PPMX_OP_*                                                   */
@@ -78,6 +79,9 @@ typedef struct ppmx_op {
     /* extension: histogram.  GRAY_HIST inside a chain writes 256 bins per raster here (host
      * memory, raster i of a batch at hist_out + 256*i); ppmx_gpu_op takes its own argument.   */
     uint64_t *hist_out;
+    /* extension: levels.  256 bytes on the host; ppmx_levels_lut_linear (ppmx_host.h) builds the usual
+     * black-point / white-point stretch, and a histogram from HIST_GRAY picks the points.           */
+    const uint8_t *levels_lut;
 } ppmx_op;
 
 typedef struct ppmx_gpu_ctx ppmx_gpu_ctx;     /* one CUDA device, one stream, buffer pool   */

@@ -50,6 +50,7 @@ typedef struct ppmx_image_handler {
     double angle;
     char norotate;
     int conv_preset;            /* extension flags -blur/-blur7/-sharpen/-edge (0 = none); not in the reference */
+    int levels_enable, levels_lo, levels_hi; /* extension flag -levelsLO-HI (black/white point); not in the reference */
 } ppmx_image_handler;
 
 /* ref:92-96, flat: weights[out_size][weights_sz], indices likewise */
@@ -86,6 +87,7 @@ typedef struct ppmx_plan {
     ppmx_op ops[8];
     int nops;
     ppmx_contributions contrib[2]; /* owned tables of the two resize passes */
+    unsigned char levels_lut[256]; /* table of the extension levels stage, if any */
 } ppmx_plan;
 int ppmx_plan_chain(const ppmx_args_flag *flags, unsigned int output_width_size, double angle,
                     unsigned int width, unsigned int height, ppmx_plan *plan);
@@ -99,6 +101,18 @@ int ppmx_plan_chain(const ppmx_args_flag *flags, unsigned int output_width_size,
 #define PPMX_CONV_EDGE 4
 int ppmx_plan_chain_ext(const ppmx_args_flag *flags, unsigned int output_width_size, double angle,
                         unsigned int width, unsigned int height, int conv_preset, ppmx_plan *plan);
+/* The same plus a second EXTENSION stage after the convolution: levels with black point lo and white point hi
+ * (0 <= lo < hi <= 255; lo < 0 = no levels stage), table = ppmx_levels_lut_linear(lo, hi). */
+int ppmx_plan_chain_ext2(const ppmx_args_flag *flags, unsigned int output_width_size, double angle,
+                         unsigned int width, unsigned int height, int conv_preset, int levels_lo, int levels_hi,
+                         ppmx_plan *plan);
+/* EXTENSION helpers for PPMX_OP_LEVELS (no reference counterpart).  lut[v] = 0 below lo, 255 above hi and
+ * round((v - lo) * 255 / (hi - lo)) in between, with the reference's round(x) = floor(x + 0.5) (ref:27) evaluated
+ * in integers.  Returns -1 unless 0 <= lo < hi <= 255. */
+int ppmx_levels_lut_linear(int lo, int hi, unsigned char lut[256]);
+/* Black and white points from a 256-bin histogram (PPMX_OP_HIST_GRAY): the smallest lo / largest hi such that at
+ * most clip_permille / 1000 of the pixels lie below lo / above hi.  Returns -1 for an empty or flat histogram. */
+int ppmx_levels_points_from_hist(const unsigned long long hist[256], unsigned int clip_permille, int *lo, int *hi);
 void ppmx_plan_free(ppmx_plan *plan);
 
 /* Header tokenizer of ref:333-456 on an in-memory file: width, height, maxval and the offset

@@ -88,6 +88,8 @@ class Oracle:
         L.orx_conv.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int32), C.c_int32,
                                C.c_int32, _u8p]
         L.orx_hist_gray.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.orx_levels.argtypes = [_u8p, C.c_size_t, _u8p, _u8p]
+        L.orx_levels_lut_linear.argtypes = [C.c_int, C.c_int, _u8p]
         L.orc_lcg_fill.argtypes = [_u8p, C.c_size_t, C.c_uint32]
         L.orc_lcg_fill.restype = None
 
@@ -214,6 +216,19 @@ class Oracle:
         bins = np.zeros(256, np.uint64)
         assert self.lib.orx_hist_gray(_ptr(img), w, h, _ptr(bins, C.POINTER(C.c_uint64))) == 0
         return bins
+
+    def levels(self, img, lut) -> np.ndarray:
+        img = np.ascontiguousarray(img, np.uint8)
+        lut = np.ascontiguousarray(lut, np.uint8)
+        assert lut.size == 256
+        out = np.empty_like(img)
+        assert self.lib.orx_levels(_ptr(img), img.size, _ptr(lut), _ptr(out)) == 0
+        return out
+
+    def levels_lut_linear(self, lo: int, hi: int) -> np.ndarray:
+        lut = np.zeros(256, np.uint8)
+        assert self.lib.orx_levels_lut_linear(lo, hi, _ptr(lut)) == 0
+        return lut
 
     def lcg_image(self, w: int, h: int, seed: int) -> np.ndarray:
         out = np.empty((h, w, 3), np.uint8)

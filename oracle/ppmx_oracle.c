@@ -486,6 +486,24 @@ int orx_hist_gray(const uint8_t *rgb, uint32_t w, uint32_t h, uint64_t *bins)
     return ORC_OK;
 }
 
+int orx_levels(const uint8_t *src, size_t nbytes, const uint8_t *lut, uint8_t *out)
+{
+    size_t i;
+    for (i = 0; i < nbytes; i++) out[i] = lut[src[i]];
+    return ORC_OK;
+}
+
+int orx_levels_lut_linear(int lo, int hi, uint8_t *lut)
+{
+    int v;
+    if (lo < 0 || hi > 255 || lo >= hi) return ORC_ERR;
+    for (v = 0; v < 256; v++) {
+        double x = floor((double)(v - lo) * 255.0 / (double)(hi - lo) + 0.5); /* the round() of ref:27 */
+        lut[v] = (uint8_t)(v <= lo ? 0 : v >= hi ? 255 : (int)x);
+    }
+    return ORC_OK;
+}
+
 void orc_lcg_fill(uint8_t *rgb, size_t npix, uint32_t seed)
 {
     uint32_t s = seed;

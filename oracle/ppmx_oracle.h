@@ -104,6 +104,12 @@ int orx_conv(const uint8_t *rgb, uint32_t w, uint32_t h, int k, const int32_t *c
 /* 256-bin histogram of (r+g+b)/3 (grey of ref:1000). bins[256] u64, overwritten. */
 int orx_hist_gray(const uint8_t *rgb, uint32_t w, uint32_t h, uint64_t *bins);
 
+/* levels: out[i] = lut[in[i]] for every byte.  orx_levels_lut_linear: lut[v] = 0 for v <= lo, 255 for v >= hi,
+ * else round((v - lo) * 255.0 / (hi - lo)) with round(x) = floor(x + 0.5) (ref:27), here written with doubles the
+ * way the reference writes its roundings (the product library evaluates the same value in integers). */
+int orx_levels(const uint8_t *src, size_t nbytes, const uint8_t *lut, uint8_t *out);
+int orx_levels_lut_linear(int lo, int hi, uint8_t *lut);
+
 /* synthetic input generator shared by tests and bench:
  * s = s*1664525 + 1013904223; r = s>>24, g = s>>16, b = s>>8. */
 void orc_lcg_fill(uint8_t *rgb, size_t npix, uint32_t seed);

@@ -471,6 +471,46 @@ def test_extension_cli_conv_presets(gpu, orc, tmp_path):
     assert p.returncode == 255 and "Duplicate" in p.stdout
 
 
+def test_extension_levels(gpu, orc, tmp_path):
+    """EXTENSION levels (no reference counterpart, self-oracle): every byte through a 256-entry table, on aligned,
+    ragged and tiny rasters; tables from the host helper; auto points from the device histogram; the CLI flag."""
+    import imageprocessingtools_b200.ppmx as pp
+    rng = np.random.default_rng(3)
+    luts = [np.arange(256, dtype=np.uint8)[::-1].copy(), rng.integers(0, 256, 256).astype(np.uint8),
+            gpu.levels_lut_linear(16, 235), gpu.levels_lut_linear(0, 255), gpu.levels_lut_linear(100, 101)]
+    for (w, h) in [(1, 1), (5, 3), (16, 16), (37, 23), (256, 64), (301, 211), (1024, 33), (1024, 700), (1001, 707)]:  # last two: > 1 MB, the lane-column kernel
+        img = P.lcg(w, h, 9)
+        for lut in luts:
+            assert np.array_equal(gpu.levels(img, lut), orc.levels(img, lut)), (w, h)
+    # an R8 plane goes through the same kernel
+    plane = orc.gray(P.lcg(48, 31, 2))
+    d = gpu.upload(plane, pp.LAYOUT_R8)
+    out = gpu.op(gpu.levels_op(luts[1]), d, False)
+    assert np.array_equal(gpu.download(out, oracle.FT_PGM).reshape(31, 48), orc.levels(plane, luts[1]))
+    gpu.release(out)
+    gpu.release(d)
+    # auto levels: histogram on the device -> points on the host -> table -> levels
+    img = (P.lcg(128, 96, 4) // 2 + 40).astype(np.uint8)
+    bins = gpu.hist_gray(img)
+    lo, hi = gpu.levels_points_from_hist(bins, 5)
+    cum = np.cumsum(orc.hist_gray(img))
+    assert 40 <= lo < hi <= 167 and cum[lo - 1] * 1000 <= 5 * cum[-1] < cum[lo] * 1000
+    assert np.array_equal(gpu.levels(img, gpu.levels_lut_linear(lo, hi)), orc.levels(img, orc.levels_lut_linear(lo, hi)))
+    # chain placement: resize/rotate -> conv -> levels -> gray/mono/flip
+    got = gpu.process(img, angle=90, conv_preset=1, levels=(50, 150), gray=True)
+    blur = orc.conv(orc.rotate(img, 90), *KERNELS["blur3"])
+    assert np.array_equal(got[0].reshape(128, 96), orc.gray(orc.levels(blur, orc.levels_lut_linear(50, 150))))
+    path = str(tmp_path / "l.ppm")
+    oracle.write_p6(path, img)
+    p = subprocess.run([pp.CLI, "-levels50-150", "-fv", path], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout
+    exp = orc.flip(orc.levels(img, orc.levels_lut_linear(50, 150)), 1)
+    assert open(path + ".out", "rb").read() == orc.header(oracle.FT_PPM, 128, 96) + exp.tobytes()
+    for bad in ("-levels", "-levels10", "-levels200-100", "-levels0-256", "-levels1-2x"):
+        p = subprocess.run([pp.CLI, bad, path], capture_output=True, text=True)
+        assert p.returncode == 255 and "levels" in p.stdout, bad
+
+
 def test_degenerate_rasters_cli(gpu, tmp_path):
     """Zero-height / zero-width rasters and 1-pixel rasters go through the same code in both programs."""
     import imageprocessingtools_b200.ppmx as pp

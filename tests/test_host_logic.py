@@ -41,7 +41,7 @@ def test_abi_exports_every_declared_symbol(pp):
 
 
 def test_op_struct_layout(pp):
-    assert C.sizeof(pp.PpmxOp) == 104 and C.sizeof(pp.PpmxBand) == 40
+    assert C.sizeof(pp.PpmxOp) == 112 and C.sizeof(pp.PpmxBand) == 40
 
 
 def test_library_holds_sm100a_code_only(pp):
@@ -141,6 +141,27 @@ def test_cli_flag_errors_match_reference(pp, tmp_path):
         if os.path.exists(oracle.REF_CLI):
             ref = subprocess.run([oracle.REF_CLI] + args, capture_output=True, text=True)
             assert ref.returncode == 255 and ref.stdout == ours.stdout, (args, ref.stdout, ours.stdout)
+
+
+def test_levels_table_matches_oracle(pp, orc):
+    """The integer table of ppmx_levels_lut_linear equals the oracle's floor(x + 0.5) in doubles for every (lo, hi),
+    and the histogram clip picks the documented points."""
+    for lo in range(0, 255, 7):
+        for hi in list(range(lo + 1, 256, 5)) + [255]:
+            assert np.array_equal(pp.Ppmx.levels_lut_linear(lo, hi), orc.levels_lut_linear(lo, hi)), (lo, hi)
+    with pytest.raises(pp.PpmxError):
+        pp.Ppmx.levels_lut_linear(10, 10)
+    bins = np.zeros(256, np.uint64)
+    bins[30], bins[31], bins[100], bins[200], bins[201] = 4, 6, 1980, 7, 3          # 2000 pixels, 5 permille = 10
+    with pytest.raises(pp.PpmxError):                                                # both points land on grey 100: flat
+        pp.Ppmx.levels_points_from_hist(bins, 5)
+    assert pp.Ppmx.levels_points_from_hist(bins, 4) == (31, 200)                     # 8 pixels: 4 below, 3 above fit
+    bins2 = np.zeros(256, np.uint64)
+    bins2[10], bins2[20], bins2[240], bins2[250] = 5, 995, 990, 10                   # 2000 pixels
+    assert pp.Ppmx.levels_points_from_hist(bins2, 5) == (20, 240)                    # 5 and 10 pixels may be clipped
+    assert pp.Ppmx.levels_points_from_hist(bins2, 0) == (10, 250)
+    with pytest.raises(pp.PpmxError):
+        pp.Ppmx.levels_points_from_hist(np.zeros(256, np.uint64), 5)
 
 
 def test_conv_rounding_magic():
