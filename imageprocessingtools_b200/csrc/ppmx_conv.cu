@@ -286,9 +286,7 @@ struct Conv3Coef {
 template <int MODE>
 __device__ __forceinline__ uint32_t strip_pack4(const ConvRound &rnd, int32_t a0, int32_t a1, int32_t a2, int32_t a3)
 {
-    if (MODE == 3)  // coefficients pre-scaled so that the result is byte 1 of the sum and cannot leave 0..255
-        return __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
-    return rnd.template pack4<(MODE == 3 ? 0 : MODE)>(a0, a1, a2, a3);
+    return rnd.template pack4<MODE>(a0, a1, a2, a3);
 }
 
 template <int MODE, int RH, int PF, bool INNER>
@@ -390,27 +388,10 @@ __global__ void __launch_bounds__(BLOCK) conv3_strip_kernel(RowSource rs, uint8_
 static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef,
                                ConvRound rnd, int32_t div, int32_t bias, cudaStream_t s)
 {
-    int32_t c[9];
-    for (int i = 0; i < 9; i++) c[i] = coef[i];
-    int mode = rnd.mode;
-    if (mode == 1 && bias == 0 && rnd.m <= 8 && g_variant != 8) {
-        // non-negative coefficients that sum to at most div cannot leave 0..255; scaled by 2^(8-m) the rounded
-        // quotient is byte 1 of the sum and the shift + saturating pack become three PRMTs per four bytes
-        int64_t sum = 0;
-        int32_t mx = 0;
-        bool nonneg = true;
-        for (int i = 0; i < 9; i++) {
-            nonneg = nonneg && c[i] >= 0;
-            sum += c[i];
-            mx = c[i] > mx ? c[i] : mx;
-        }
-        const int up = 8 - rnd.m;
-        if (nonneg && sum <= div && ((int64_t)mx << up) <= 127) {
-            for (int i = 0; i < 9; i++) c[i] <<= up;
-            rnd.start = (div / 2) << up;
-            mode = 3;
-        }
-    }
+    const int32_t *c = coef;
+    // (pre-scaling the coefficients of a normalised non-negative filter so that the quotient is byte 1 of the sum
+    // -- three PRMT per four bytes instead of shift + saturating pack -- measured 2 % SLOWER: 0.934 vs 0.953)
+    const int mode = rnd.mode;
     Conv3Coef cf;
     for (int dx = 0; dx < 3; dx++) {
         const uint32_t t = (uint32_t)(uint8_t)(int8_t)c[dx], m = (uint32_t)(uint8_t)(int8_t)c[3 + dx],
@@ -429,8 +410,7 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
     do {                                                         \
         if (mode == 0) PPMX_CONV3_LAUNCH(0, RH, PF, BLOCK);      \
         else if (mode == 1) PPMX_CONV3_LAUNCH(1, RH, PF, BLOCK); \
-        else if (mode == 2) PPMX_CONV3_LAUNCH(2, RH, PF, BLOCK); \
-        else PPMX_CONV3_LAUNCH(3, RH, PF, BLOCK);                \
+        else PPMX_CONV3_LAUNCH(2, RH, PF, BLOCK);                \
     } while (0)
     // rows per strip / row pairs in flight / threads per CTA.  Measured on 8192x8192 (profiles/r1_sweep_conv3_strip.txt):
     // 4/2/128: 0.94 of the HBM roofline, 4/2/256: 0.92, 8/2/128: 0.84, 8/4/128: 0.84, 16/1/128: 0.74, 32/1/128: 0.68 --

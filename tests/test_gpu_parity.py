@@ -449,6 +449,20 @@ def test_extension_conv3_strip_variants(gpu, orc):
         gpu.set_tuning("variant", 0)
 
 
+def test_extension_full_size_conv_levels_8192(gpu, orc):
+    """BASELINE config 3 size (8192x8192): the strip and box kernels against the self-oracle directly (the C loops
+    need a few seconds per filter), the levels table against numpy indexing, and the identity filter."""
+    img = P.lcg(8192, 8192, 0xC0FFEE ^ 3)
+    for kname in ("blur3", "edge3", "box7"):
+        coef, div, bias = KERNELS[kname]
+        assert np.array_equal(gpu.conv(img, coef, div, bias), orc.conv(img, coef, div, bias)), kname
+    ident = np.zeros((3, 3), np.int64)
+    ident[1, 1] = 1
+    assert np.array_equal(gpu.conv(img, ident, 1, 0), img)
+    lut = gpu.levels_lut_linear(16, 235)
+    assert np.array_equal(gpu.levels(img, lut), lut[img])
+
+
 def test_extension_cli_conv_presets(gpu, orc, tmp_path):
     """EXTENSION flags of ppmx-b200 (-blur, -blur7, -sharpen, -edge; the reference rejects them): the stage
     sits after resize/rotate and before gray/mono/flip.  Self-oracle only (parity unpinned)."""
