@@ -707,12 +707,17 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         sum_abs += coef[i] < 0 ? -(int64_t)coef[i] : coef[i];
     }
     ConvRound rnd;
-    if (s8 && (k == 3 || k == 5 || k == 7) && (w % 16u) == 0 && aligned16(src) && aligned4(dst) &&
-        (!band.top || aligned16(band.top)) && (!band.bottom || aligned16(band.bottom)) && g_variant != 1 &&
-        make_conv_round(sum_abs, div, bias, &rnd)) {
-        uint32_t bm, bc;
-        if ((k == 5 || k == 7) && g_variant != 7 && aligned16(dst) && box_constants(coef, k, div, bias, &bm, &bc))
-            return k == 5 ? conv_box<5>(rs, dst, w, h, bm, bc, s) : conv_box<7>(rs, dst, w, h, bm, bc, s);
+    const bool fast_layout = (w % 16u) == 0 && aligned16(src) && (!band.top || aligned16(band.top)) &&
+                             (!band.bottom || aligned16(band.bottom)) && g_variant != 1;
+    uint32_t bm, bc;
+    if (fast_layout && k >= 5 && k <= 11 && g_variant != 7 && aligned16(dst) && box_constants(coef, k, div, bias, &bm, &bc)) {
+        // running sums: the cost does not depend on k (3R <= 15 halo columns come from one neighbouring lane)
+        if (k == 5) return conv_box<5>(rs, dst, w, h, bm, bc, s);
+        if (k == 7) return conv_box<7>(rs, dst, w, h, bm, bc, s);
+        if (k == 9) return conv_box<9>(rs, dst, w, h, bm, bc, s);
+        return conv_box<11>(rs, dst, w, h, bm, bc, s);
+    }
+    if (s8 && (k == 3 || k == 5 || k == 7) && fast_layout && aligned4(dst) && make_conv_round(sum_abs, div, bias, &rnd)) {
         // variant 7 keeps the row-wise (planar dp4a) kernel for 3x3; the strip kernel is the default
         if (k == 3 && g_variant != 7 && aligned16(dst)) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s);
         if (k == 3) return conv_fast<3>(rs, dst, w, h, coef, rnd, s);

@@ -214,6 +214,9 @@ KERNELS["gauss7"] = (np.outer([1, 6, 15, 20, 15, 6, 1], [1, 6, 15, 20, 15, 6, 1]
 KERNELS["sep5_signed"] = (np.outer([2, -4, 6, -4, 2], [-1, 3, 5, 3, -1]), 32, 9)                    # rank 1 with signs + gcd
 KERNELS["sobel3"] = (np.outer([1, 2, 1], [-1, 0, 1]), 1, 128)                                        # rank 1, zero column
 KERNELS["box5"] = (np.ones((5, 5), np.int64), 25, 0)                                                  # running-sum box kernel
+KERNELS["box9"] = (np.ones((9, 9), np.int64), 81, 0)
+KERNELS["box11"] = (np.ones((11, 11), np.int64), 121, 0)
+KERNELS["box11_bias"] = (np.ones((11, 11), np.int64), 121, 3)                                          # constants overflow 32 bits: generic kernel
 KERNELS["box7_twos_bias"] = (2 * np.ones((7, 7), np.int64), 196, 64)                                  # box with a factor and a bias
 KERNELS["box7_sat"] = (np.ones((7, 7), np.int64), 40, 0)                                              # would pass 255: not the box kernel
 KERNELS["big5"] = (np.array([[300, -200, 0, 5, 1]] * 5), 7, -3)  # coefficients beyond int8: generic kernel
