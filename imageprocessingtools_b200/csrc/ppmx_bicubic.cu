@@ -231,6 +231,20 @@ __device__ __forceinline__ uint32_t quantise_fast(double s)
     return (uint32_t)min(max(n, 0), 255);
 }
 
+// four results at once: floor(s + 0.5) as above, then ONE saturating pack per two values (I2IP) does the
+// "< 0 -> 0, >= 256 -> 255" clamp of ref:835 and the byte packing together
+__device__ __forceinline__ int quantise_floor(double s)
+{
+    return __double2loint(__dadd_rd(dadd(s, 0.5), 6755399441055744.0));
+}
+__device__ __forceinline__ uint32_t quantise_pack4(double s0, double s1, double s2, double s3)
+{
+    uint32_t hi, out;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(quantise_floor(s3)), "r"(quantise_floor(s2)), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(quantise_floor(s1)), "r"(quantise_floor(s0)), "r"(hi));
+    return out;
+}
+
 // height pass, fast path (row pitch % 16 == 0, aligned, K <= 64): one thread = 16 bytes of an
 // output row.  The row's K weights and source-row numbers are staged once per CTA in shared memory
 // so the K source loads of a thread are independent of each other and fly four at a time.
@@ -244,7 +258,9 @@ __device__ __forceinline__ void words_vec(const uint32_t (&w)[4], uint4 &v) { v 
 __device__ __forceinline__ void words_vec(const uint32_t (&w)[2], uint2 &v) { v = make_uint2(w[0], w[1]); }
 
 // NW = words per thread: 4 (16 bytes, 57-64 registers) or 2 (8 bytes, fewer registers, more warps in flight)
-template <int CONV, int NW>
+// KT > 0: the tap count as a compile-time constant (4 for every upscale, up to 8 down to x0.5): the group loop and
+// its bounds tests fold away (measured +8.5 % at K = 4)
+template <int CONV, int NW, int KT = 0>
 __global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource src, uint8_t *__restrict__ dst,
                                                               uint32_t row_vecs, int taps,
                                                               const double *__restrict__ wts, const int *__restrict__ idx)
@@ -266,14 +282,15 @@ __global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource sr
     double acc[4 * NW];
 #pragma unroll
     for (int i = 0; i < 4 * NW; i++) acc[i] = 0.0;
-    for (int z0 = 0; z0 < taps; z0 += 4) {
+    const int ntaps = KT ? KT : taps;
+    auto group = [&](int z0) {  // four taps: their source vectors fly together
         vec_t v[4];
 #pragma unroll
         for (int u = 0; u < 4; u++)
-            if (z0 + u < taps) v[u] = __ldg(reinterpret_cast<const vec_t *>(src.row_plain(s_i[z0 + u], row_bytes)) + xv);
+            if (z0 + u < ntaps) v[u] = __ldg(reinterpret_cast<const vec_t *>(src.row_plain(s_i[z0 + u], row_bytes)) + xv);
 #pragma unroll
         for (int u = 0; u < 4; u++) {  // tap order is the reference's summation order (ref:826-830)
-            if (z0 + u >= taps) break;
+            if (z0 + u >= ntaps) break;
             const double wz = s_w[z0 + u];
             uint32_t wd[NW];
             vec_words(v[u], wd);
@@ -286,12 +303,18 @@ __global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource sr
                     acc[4 * q + b] = (z0 + u) ? dadd(acc[4 * q + b], dmul(d[b], wz)) : dmul(d[b], wz);
             }
         }
+    };
+    if (KT) {
+#pragma unroll
+        for (int z0 = 0; z0 < KT; z0 += 4) group(z0);
+    } else {
+#pragma unroll 1
+        for (int z0 = 0; z0 < ntaps; z0 += 4) group(z0);
     }
     uint32_t o[NW];
 #pragma unroll
     for (int q = 0; q < NW; q++)
-        o[q] = quantise_fast(acc[4 * q]) | (quantise_fast(acc[4 * q + 1]) << 8) | (quantise_fast(acc[4 * q + 2]) << 16) |
-               (quantise_fast(acc[4 * q + 3]) << 24);
+        o[q] = quantise_pack4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
     vec_t ov;
     words_vec(o, ov);
     reinterpret_cast<vec_t *>(dst + (size_t)y * row_bytes)[xv] = ov;
@@ -329,17 +352,16 @@ __global__ void __launch_bounds__(128) imresize_colsK_kernel(const uint8_t *__re
     const uint32_t y0 = blockIdx.y * (uint32_t)rows_per_cta, y1 = min(h, y0 + (uint32_t)rows_per_cta);
     const size_t in_pitch = (size_t)w * 3, out_pitch = (size_t)out_w * 3;
     if (consecutive) {
-        // the words of row y+1 are requested before row y is evaluated
-        const uint32_t *rw = reinterpret_cast<const uint32_t *>(src + (size_t)y0 * in_pitch) + w0;
+        // the words of row y+1 are requested before row y is evaluated; two register sets alternate (no copies)
+        const uint32_t *rw0 = reinterpret_cast<const uint32_t *>(src) + w0;
         const size_t pitch_words = in_pitch / 4;
-        uint32_t q[NS + 1], qn[NS + 1];
+        auto fetch = [&](uint32_t y, uint32_t(&q)[NS + 1]) {
+            const uint32_t *rw = rw0 + (size_t)y * pitch_words;
 #pragma unroll
-        for (int j = 0; j <= NS; j++)  // word j is needed iff it starts before the last tap byte
-            q[j] = (y0 < y1 && 4u * j < (b0 & 3u) + 3u * K) ? __ldg(rw + j) : 0u;
-        for (uint32_t y = y0; y < y1; y++) {
-            rw += pitch_words;
-#pragma unroll
-            for (int j = 0; j <= NS; j++) qn[j] = (y + 1 < y1 && 4u * j < (b0 & 3u) + 3u * K) ? __ldg(rw + j) : 0u;
+            for (int j = 0; j <= NS; j++)  // word j is needed iff it starts before the last tap byte
+                q[j] = (y < y1 && 4u * j < (b0 & 3u) + 3u * K) ? __ldg(rw + j) : 0u;
+        };
+        auto eval = [&](uint32_t y, const uint32_t(&q)[NS + 1]) {
             double d[NS][4];
 #pragma unroll
             for (int j = 0; j < NS; j++) word_to_double4<CONV>(__funnelshift_r(q[j], q[j + 1], sh), d[j]);
@@ -354,8 +376,15 @@ __global__ void __launch_bounds__(128) imresize_colsK_kernel(const uint8_t *__re
             o[0] = (uint8_t)quantise_fast(s0);
             o[1] = (uint8_t)quantise_fast(s1);
             o[2] = (uint8_t)quantise_fast(s2);
-#pragma unroll
-            for (int j = 0; j <= NS; j++) q[j] = qn[j];
+        };
+        uint32_t qa[NS + 1], qb[NS + 1];
+        fetch(y0, qa);
+        for (uint32_t y = y0; y < y1; y += 2) {
+            fetch(y + 1, qb);
+            eval(y, qa);
+            if (y + 1 >= y1) break;
+            fetch(y + 2, qa);
+            eval(y + 1, qb);
         }
     } else {
         for (uint32_t y = y0; y < y1; y++) {
@@ -491,6 +520,11 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
                 else if (g_variant == 2) launch(imresize_rows16_kernel<1, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (g_variant == 3) launch(imresize_rows16_kernel<0, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (g_variant == 4) launch(imresize_rows16_kernel<2, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 4 && g_variant != 5) launch(imresize_rows16_kernel<3, 4, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 5 && g_variant != 5) launch(imresize_rows16_kernel<3, 4, 5>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 6 && g_variant != 5) launch(imresize_rows16_kernel<3, 4, 6>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 7 && g_variant != 5) launch(imresize_rows16_kernel<3, 4, 7>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 8 && g_variant != 5) launch(imresize_rows16_kernel<3, 4, 8>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else launch(imresize_rows16_kernel<3, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
             }
             return cudaGetLastError();

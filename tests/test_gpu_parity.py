@@ -96,6 +96,19 @@ def test_imresize_sweep(gpu, orc):
                     assert np.array_equal(a, b), (w, h, name, new, dim)
 
 
+def test_imresize_tap_count_specialisations(gpu, orc):
+    """Height pass with 4..8 taps as compile-time constants, 9+ through the loop; width pass templates K = 4..8."""
+    img = P.lcg(64, 120, 21)
+    seen = set()
+    for new in (180, 121, 100, 90, 84, 80, 72, 70, 66, 60, 50, 40):
+        wt, ix = gpu.calc_contributions(120, new, new / 120.0)
+        seen.add(wt.shape[1])
+        assert np.array_equal(gpu.imresize(img, new, 0, wt, ix), orc.imresize(img, new, 0, wt, ix)), new
+        t = np.ascontiguousarray(img.transpose(1, 0, 2))  # 120 wide: the same tables drive the width pass
+        assert np.array_equal(gpu.imresize(t, new, 1, wt, ix), orc.imresize(t, new, 1, wt, ix)), new
+    assert {4, 5, 6, 7, 8} <= seen and max(seen) > 8
+
+
 CHAINS = [dict(gray=True), dict(mono=True), dict(flipv=True), dict(fliph=True), dict(angle=90), dict(angle=180),
           dict(angle=270), dict(angle=30), dict(angle=0), dict(resize_w=74), dict(resize_w=20), dict(resize_w=37),
           dict(resize_w=55, angle=90), dict(resize_w=20, angle=45, gray=True), dict(resize_w=50, mono=True),
