@@ -566,7 +566,7 @@ __device__ __forceinline__ void conv_box_body(const RowSource &rs, uint8_t *__re
 }
 
 template <int K, int RH>
-__global__ void __launch_bounds__(128) conv_box_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks, uint32_t M,
+__global__ void __launch_bounds__(128, 7) conv_box_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks, uint32_t M,
                                                        uint32_t C)
 {
     constexpr int R = K / 2;
