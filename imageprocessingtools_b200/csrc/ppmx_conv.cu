@@ -653,6 +653,181 @@ static bool rank_one(const int32_t *coef, int32_t (&u)[K], int32_t (&v)[K])
     return true;
 }
 
+// ---- rank-1 kernels (coef = u v^T: Gaussian / binomial blurs, Sobel-like derivatives), K = 5 or 7 ----------
+// Same thread layout as the box kernel (16 byte columns per thread walking down RH rows, warps overlapped by two
+// lanes, neighbours' column sums by shuffle), but the vertical pass is a real dot product.  Per byte column the
+// thread keeps the last 8 source rows as two sliding "vertical words" (W_lo = rows y+R-7 .. y+R-4, W_hi = rows
+// y+R-3 .. y+R): a new row shifts them with two PRMT, and the K-tap column sum is two dp4a against u packed into
+// bytes -- no shared memory, no re-reads.  The horizontal pass multiplies the 32-bit column sums by v, with the
+// mirror pairs added first when v is symmetric (R adds + R+1 IMAD instead of K IMAD).
+// Per output byte at K = 7: 2 IDP + 4 IMAD on the fma pipe, 2 PRMT + 3 IADD3 + finishing on the alu pipe, 1.1 SHFL.
+template <int K>
+struct SepCoef {
+    uint32_t u_lo, u_hi;  // u[dy] in the byte of the row it multiplies: W_lo byte b <-> dy = R-7+b, W_hi byte b <-> dy = R-3+b
+    int32_t v[K];
+};
+
+template <int K, int MODE, bool SYM, int RH, bool INNER, bool EDGE>
+__device__ __forceinline__ void conv_sep_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, int chunk, int ys,
+                                              const SepCoef<K> &cf, const ConvRound &rnd)
+{
+    constexpr int R = K / 2, H = 3 * R, PF = 2;
+    static_assert(RH % PF == 0, "strip height");
+    const int lane = threadIdx.x & 31;
+    const bool valid = chunk >= 0 && chunk < (int)nchunks;
+    const uint32_t cx = (uint32_t)(chunk < 0 ? 0 : chunk >= (int)nchunks ? (int)nchunks - 1 : chunk);
+    const bool writes = valid && lane >= 1 && lane <= 30;
+    const bool left = EDGE && chunk == 0, right = EDGE && chunk == (int)nchunks - 1;
+    const size_t pitch = (size_t)nchunks * 16;
+    const int gy0 = rs.y0 + ys;
+    const uint8_t *src = rs.own + (size_t)cx * 16 + (size_t)(INNER ? ys - R : 0) * pitch;
+    auto load_row = [&](int i) {  // row i counted from the strip's first source row (gy0 - R)
+        const uint8_t *p = INNER ? src + (size_t)i * pitch : rs.row(gy0 - R + i, pitch) + (size_t)cx * 16;
+        return __ldg(reinterpret_cast<const uint4 *>(p));
+    };
+    uint32_t wlo[16], whi[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) wlo[c] = whi[c] = 0;
+    auto push = [&](const uint4 &row) {  // the window moves down one row
+        const uint32_t rw[4] = {row.x, row.y, row.z, row.w};
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            if (K > 4) wlo[c] = __byte_perm(wlo[c], whi[c], 0x4321);
+            whi[c] = __byte_perm(whi[c], rw[c >> 2], 0x0321 | ((4 + (c & 3)) << 12));
+        }
+    };
+    pdl_wait();
+    {
+        uint4 first[2 * R];
+#pragma unroll
+        for (int i = 0; i < 2 * R; i++) first[i] = load_row(i);
+#pragma unroll
+        for (int i = 0; i < 2 * R; i++) push(first[i]);
+    }
+    uint4 nx[PF];
+#pragma unroll
+    for (int u = 0; u < PF; u++) nx[u] = load_row(2 * R + u);
+
+    uint8_t *out = dst + (size_t)ys * pitch + (size_t)cx * 16;
+#pragma unroll 1
+    for (int r0 = 0; r0 < RH; r0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            const int r = r0 + u;
+            if (!INNER && ys + r >= rs.h) return;
+            push(nx[u]);
+            if (r + PF < RH && (INNER || ys + r + PF < rs.h)) nx[u] = load_row(2 * R + r + PF);
+            int32_t S[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) S[c] = dp4a_u8s8(whi[c], cf.u_hi, K > 4 ? dp4a_u8s8(wlo[c], cf.u_lo, 0) : 0);
+            int32_t XL[H], XR[H];  // column sums of byte columns -H .. -1 and 16 .. 15 + H
+#pragma unroll
+            for (int i = 0; i < H; i++) {
+                XL[i] = __shfl_up_sync(0xffffffffu, S[16 - H + i], 1);
+                XR[i] = __shfl_down_sync(0xffffffffu, S[i], 1);
+            }
+            if (EDGE) {  // mirror at the raster's left / right edge, as in the box kernel
+#pragma unroll
+                for (int i = 0; i < H; i++) {
+                    XL[i] = left ? S[3 * (R - 1 - i / 3) + i % 3] : XL[i];
+                    XR[i] = right ? S[13 - 3 * (i / 3) + i % 3] : XR[i];
+                }
+            }
+            auto X = [&](int c) { return c < 0 ? XL[c + H] : c < 16 ? S[c] : XR[c - 16]; };
+            uint32_t o[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int32_t a[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int c = 4 * b + j;
+                    int32_t t = rnd.start + cf.v[R] * X(c);
+#pragma unroll
+                    for (int k = 1; k <= R; k++) {
+                        if (SYM) t += cf.v[R + k] * (X(c - 3 * k) + X(c + 3 * k));
+                        else t += cf.v[R - k] * X(c - 3 * k) + cf.v[R + k] * X(c + 3 * k);
+                    }
+                    a[j] = t;
+                }
+                o[b] = rnd.template pack4<MODE>(a[0], a[1], a[2], a[3]);
+            }
+            if (writes) *reinterpret_cast<uint4 *>(out) = make_uint4(o[0], o[1], o[2], o[3]);
+            out += pitch;
+        }
+    }
+}
+
+template <int K, int MODE, bool SYM, int RH>
+__global__ void __launch_bounds__(128, 4) conv_sep_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks, const SepCoef<K> cf,
+                                                       const ConvRound rnd)
+{
+    constexpr int R = K / 2;
+    pdl_trigger();
+    const int wg = blockIdx.x * 4 + (threadIdx.x >> 5);  // warp number along the row: 30 chunks each
+    if (wg * 30 >= (int)nchunks) return;
+    const int chunk = wg * 30 - 1 + (int)(threadIdx.x & 31);
+    const int ys = blockIdx.y * RH;
+    const bool inner = ys >= R && ys + RH + R <= rs.h;
+    const bool edge = wg == 0 || wg * 30 + 30 >= (int)nchunks;
+    if (inner && !edge) conv_sep_body<K, MODE, SYM, RH, true, false>(rs, dst, nchunks, chunk, ys, cf, rnd);
+    else if (inner) conv_sep_body<K, MODE, SYM, RH, true, true>(rs, dst, nchunks, chunk, ys, cf, rnd);
+    else conv_sep_body<K, MODE, SYM, RH, false, true>(rs, dst, nchunks, chunk, ys, cf, rnd);
+}
+
+template <int K>
+static bool rank_one(const int32_t *coef, int32_t (&u)[K], int32_t (&v)[K]);
+
+// returns false when the kernel is not rank 1 with a column factor that fits signed bytes
+template <int K, int RH>
+static bool conv_sep_rh(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef, const ConvRound &rnd,
+                     cudaStream_t s, cudaError_t *err)
+{
+    constexpr int R = K / 2;
+    int32_t u[K], v[K];
+    if (!rank_one<K>(coef, u, v)) return false;
+    SepCoef<K> cf;
+    cf.u_lo = cf.u_hi = 0;
+    bool sym = true;
+    for (int i = 0; i < K; i++) {
+        if (u[i] < -128 || u[i] > 127) return false;
+        const int dy = i - R, bh = dy - (R - 3), bl = dy - (R - 7);
+        if (bh >= 0 && bh < 4) cf.u_hi |= (uint32_t)(uint8_t)(int8_t)u[i] << (8 * bh);
+        else if (bl >= 0 && bl < 4) cf.u_lo |= (uint32_t)(uint8_t)(int8_t)u[i] << (8 * bl);
+        else return false;
+        cf.v[i] = v[i];
+        sym = sym && v[i] == v[K - 1 - i];
+    }
+    const uint32_t nchunks = w * 3 / 16;
+    dim3 grid((nchunks + 119) / 120, (h + RH - 1) / RH);
+    if (grid.y > 65535u) {
+        *err = cudaErrorInvalidValue;
+        return true;
+    }
+#define PPMX_SEP_LAUNCH(MODE, SYM) launch(conv_sep_kernel<K, MODE, SYM, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd)
+    if (sym) {
+        if (rnd.mode == 0) PPMX_SEP_LAUNCH(0, true);
+        else if (rnd.mode == 1) PPMX_SEP_LAUNCH(1, true);
+        else PPMX_SEP_LAUNCH(2, true);
+    } else {
+        if (rnd.mode == 0) PPMX_SEP_LAUNCH(0, false);
+        else if (rnd.mode == 1) PPMX_SEP_LAUNCH(1, false);
+        else PPMX_SEP_LAUNCH(2, false);
+    }
+#undef PPMX_SEP_LAUNCH
+    *err = PPMX_LAUNCHED();
+    return true;
+}
+
+template <int K>
+static bool conv_sep(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef, const ConvRound &rnd,
+                     cudaStream_t s, cudaError_t *err)
+{
+    // rows per strip, 7x7 / 5x5 binomial at 8192^2: 16 -> 0.46 / 0.53 of the HBM roofline, 32 -> 0.45 / 0.52, 64 -> 0.42 / 0.48
+    if (g_variant == 9) return conv_sep_rh<K, 8>(rs, dst, w, h, coef, rnd, s, err);
+    if (g_variant == 10) return conv_sep_rh<K, 32>(rs, dst, w, h, coef, rnd, s, err);
+    return conv_sep_rh<K, 16>(rs, dst, w, h, coef, rnd, s, err);
+}
+
 template <int K>
 static cudaError_t conv_fast(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef,
                              const ConvRound &rnd, cudaStream_t s)
@@ -717,7 +892,13 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         if (k == 9) return conv_box<9>(rs, dst, w, h, bm, bc, s);
         return conv_box<11>(rs, dst, w, h, bm, bc, s);
     }
-    if (s8 && (k == 3 || k == 5 || k == 7) && fast_layout && aligned4(dst) && make_conv_round(sum_abs, div, bias, &rnd)) {
+    const bool rnd_ok = make_conv_round(sum_abs, div, bias, &rnd);
+    if (rnd_ok && fast_layout && (k == 5 || k == 7) && g_variant != 7 && g_variant != 2 && aligned16(dst)) {
+        // rank-1 (only the two factors must be small, not their products): sliding vertical words
+        cudaError_t e = cudaSuccess;
+        if (k == 5 ? conv_sep<5>(rs, dst, w, h, coef, rnd, s, &e) : conv_sep<7>(rs, dst, w, h, coef, rnd, s, &e)) return e;
+    }
+    if (s8 && (k == 3 || k == 5 || k == 7) && fast_layout && aligned4(dst) && rnd_ok) {
         // variant 7 keeps the row-wise (planar dp4a) kernel for 3x3; the strip kernel is the default
         if (k == 3 && g_variant != 7 && aligned16(dst)) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s);
         if (k == 3) return conv_fast<3>(rs, dst, w, h, coef, rnd, s);

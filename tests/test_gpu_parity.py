@@ -227,6 +227,10 @@ KERNELS["gauss7"] = (np.outer([1, 6, 15, 20, 15, 6, 1], [1, 6, 15, 20, 15, 6, 1]
 KERNELS["sep5_signed"] = (np.outer([2, -4, 6, -4, 2], [-1, 3, 5, 3, -1]), 32, 9)                    # rank 1 with signs + gcd
 KERNELS["sobel3"] = (np.outer([1, 2, 1], [-1, 0, 1]), 1, 128)                                        # rank 1, zero column
 KERNELS["box5"] = (np.ones((5, 5), np.int64), 25, 0)                                                  # running-sum box kernel
+KERNELS["sep5_asym"] = (np.outer([1, 2, 3, 2, 1], [-1, -2, 0, 2, 1]), 8, 128)                      # rank 1, v not symmetric (Sobel-like)
+KERNELS["sep7_div3"] = (np.outer([1, 1, 2, 3, 2, 1, 1], [1, 2, 3, 4, 3, 2, 1]), 3, 0)               # rank 1, general divisor, saturates
+KERNELS["sep7_div1_neg"] = (np.outer([0, -1, 2, -3, 2, -1, 0], [1, 0, -2, 3, -2, 0, 1]), 1, 100)    # rank 1, zeros and signs, div 1
+KERNELS["gauss5"] = (np.outer([1, 4, 6, 4, 1], [1, 4, 6, 4, 1]), 256, 0)
 KERNELS["box9"] = (np.ones((9, 9), np.int64), 81, 0)
 KERNELS["box11"] = (np.ones((11, 11), np.int64), 121, 0)
 KERNELS["box11_bias"] = (np.ones((11, 11), np.int64), 121, 3)                                          # constants overflow 32 bits: generic kernel
