@@ -678,12 +678,18 @@ def run_ours(args):
     after = None
     drain = None
     if name == "gray_hist" and dist is not None:
-        # the one real exchange of this path: sum the 256 bins over ranks (NCCL), in stream order after the
-        # step's kernels.  (Issuing it asynchronously on alternating bin buffers so that it overlaps the
-        # next step measured SLOWER at N=2: 0.495 vs 0.399 ms per step -- the NCCL kernel then competes
-        # with the PDL-chained launches -- so it stays in order.)
-        def after():
+        # The one real exchange of this path is the job's FINAL histogram reduction (north star: "NCCL only for the
+        # final histogram reduction"): every rank accumulates the 256 bins of all its rasters on the device (u64) and
+        # one NCCL all-reduce, issued in stream order inside the timed region, sums them over the ranks.
+        # PPMX_BENCH_ALLREDUCE_EVERY_STEP=1 reduces after every step instead (2500 reductions/s: at N=8 the step
+        # grows from 0.39 to 0.45 ms, since the NCCL kernel has to find an SM among 148 resident 1024-thread CTAs
+        # and the ranks then wait for each other every 0.4 ms).
+        def reduce_bins():
             dist.all_reduce(runner.hist, op=dist.ReduceOp.SUM)
+        if os.environ.get("PPMX_BENCH_ALLREDUCE_EVERY_STEP") == "1":
+            after = reduce_bins
+        else:
+            drain = reduce_bins
 
     n0 = g.launch_count()
     with ClockSampler(local) as clk:
@@ -699,7 +705,9 @@ def run_ours(args):
         "config": {"workload": desc, "op": name, "raster": "%dx%d" % (w, h), "rasters_per_step_per_gpu": batch,
                    "l2": "inputs larger than L2 (%d MB per step per GPU)" % (batch * w * h * 3 // 1000000),
                    "sharding": "rasters sharded across ranks, no data-path collective" +
-                               ("; NCCL all-reduce of the 256 histogram bins per step" if after else "")},
+                               ("; NCCL all-reduce of the 256 histogram bins per step" if after else
+                                "; one NCCL all-reduce of the 256 accumulated histogram bins at the end of the timed region"
+                                if drain else "")},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }
