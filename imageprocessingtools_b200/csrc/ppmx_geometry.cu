@@ -268,6 +268,105 @@ __global__ void __launch_bounds__(256, MINB) rotate_transpose64_kernel(const uin
     }
 }
 
+// ---- 90 / 270 degrees through the bulk-copy engine (w % 16 == 0, h % 16 == 0) ------------------
+// One 64 x 64 pixel tile per 128-thread CTA.  The 64 source row pieces (192 B each) come in by cp.async.bulk
+// (global -> shared, completion on an mbarrier) as RAW interleaved bytes, the transposed tile leaves by
+// cp.async.bulk (shared -> global) as 64 destination row pieces of 192 B: no thread issues a global load or store,
+// so the L1 tag stage no longer sees 8..16 partly used lines per instruction (what held the register-path kernel
+// at 0.71), and 8 CTAs per SM keep ~100 KB in flight.  In between, a lane takes ONE source column over 16 rows:
+// the pixel at byte 3x of a row is cut out of two aligned words by a funnel shift whose amount is constant per
+// lane; a warp's 32 lanes read 24 consecutive words of one row (conflict-free), and write three 16-byte vectors
+// each into rows 208 B apart (conflict-free per quarter warp).
+constexpr int XB_PITCH = 208;  // 192 B of pixels + 16 B: rows stay 16-byte aligned and spread over the banks
+
+__device__ __forceinline__ uint32_t xb_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool CW>
+__global__ void __launch_bounds__(128) rotate_bulk64_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t w,
+                                                            uint32_t h)
+{
+    pdl_trigger();
+    __shared__ __align__(128) uint8_t tin[64 * XB_PITCH];
+    __shared__ __align__(128) uint8_t tout[64 * XB_PITCH];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t tid = threadIdx.x, tx0 = blockIdx.x * 64u, ty0 = blockIdx.y * 64u;
+    // tiles at the right / bottom edge of a raster whose sides are multiples of 16 are 16, 32 or 48 pixels wide / tall
+    const uint32_t nc = min(64u, w - tx0), nr = min(64u, h - ty0);
+    const size_t in_pitch = (size_t)w * 3, out_pitch = (size_t)h * 3;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(xb_smem(&bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    if (tid == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xb_smem(&bar)), "r"(nr * nc * 3u) : "memory");
+    // a bulk copy is a per-warp (uniform) instruction, so a warp issues its lanes' copies one after the other:
+    // 16 per warp on all four warps instead of 32 on two halves that latency (0.71 -> 0.82 of the HBM roofline)
+    const uint32_t crow = (tid >> 5) * 16u + (tid & 15u);  // the row piece this thread copies (lanes 0..15 of each warp)
+    if ((tid & 31u) < 16u && crow < nr) {
+        const uint8_t *g = src + (size_t)(ty0 + crow) * in_pitch + (size_t)tx0 * 3;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         xb_smem(tin + crow * XB_PITCH)),
+                     "l"(g), "r"(nc * 3u), "r"(xb_smem(&bar))
+                     : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(xb_smem(&bar)),
+        "r"(0)
+        : "memory");
+
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t x = lane + 32u * (warp & 1u);             // source column inside the tile
+    const uint32_t wcol = (3u * x) >> 2, sh = ((3u * x) & 3u) * 8u;
+    const uint32_t *tin32 = reinterpret_cast<const uint32_t *>(tin);
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        const uint32_t j = (warp >> 1) + 2u * pass;          // 16-row group
+        if (x >= nc || 16u * j >= nr) continue;
+        uint32_t px[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t *rw = tin32 + (16u * j + k) * (XB_PITCH / 4) + wcol;
+            px[k] = __funnelshift_r(rw[0], rw[1], sh);       // r g b x (the word after the last pixel is the row's padding)
+        }
+        uint32_t o[12];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {  // 4 pixels -> 3 words; CW walks the source rows backwards
+            const uint32_t p0 = CW ? px[15 - 4 * i] : px[4 * i], p1 = CW ? px[14 - 4 * i] : px[4 * i + 1];
+            const uint32_t p2 = CW ? px[13 - 4 * i] : px[4 * i + 2], p3 = CW ? px[12 - 4 * i] : px[4 * i + 3];
+            o[3 * i] = __byte_perm(p0, p1, 0x4210);
+            o[3 * i + 1] = __byte_perm(p1, p2, 0x5421);
+            o[3 * i + 2] = __byte_perm(p2, p3, 0x6542);
+        }
+        // CW: out[x][h-1-y] (ref:717): destination row x, its pixels nr-16-16j .. nr-1-16j; else out[w-1-x][y] (ref:725):
+        // destination row nc-1-x, pixels 16j .. 16j+15
+        const uint32_t drow = CW ? x : nc - 1u - x, dbyte = CW ? (nr - 16u - 16u * j) * 3u : 48u * j;
+        uint4 *q = reinterpret_cast<uint4 *>(tout + drow * XB_PITCH + dbyte);
+        q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        q[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the bulk engine must see the tile the threads wrote
+    __syncthreads();
+    if ((tid & 31u) < 16u && crow < nc) {
+        uint8_t *g = CW ? dst + (size_t)(tx0 + crow) * out_pitch + (size_t)(h - ty0 - nr) * 3
+                        : dst + (size_t)(w - tx0 - nc + crow) * out_pitch + (size_t)ty0 * 3;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(xb_smem(tout + crow * XB_PITCH)),
+                     "r"(nr * 3u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may go once it has been read
+    }
+}
+
 cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int angle, cudaStream_t s)
 {
     if (!w || !h) return cudaSuccess;
@@ -284,6 +383,13 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
         return PPMX_LAUNCHED();
     }
     if (angle != 90 && angle != 270) return cudaErrorInvalidValue;
+    if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && (g_variant == 0 || g_variant == 9)) {
+        dim3 grid((w + 63) / 64, (h + 63) / 64);
+        if (grid.y > 65535u) return cudaErrorInvalidValue;
+        if (angle == 90) launch(rotate_bulk64_kernel<true>, grid, dim3(128), 0, s, src, dst, w, h);
+        else launch(rotate_bulk64_kernel<false>, grid, dim3(128), 0, s, src, dst, w, h);
+        return PPMX_LAUNCHED();
+    }
     if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && g_variant != 1) {
         // (numbering the CTAs down bands of 2..16 tile rows, for DRAM page locality on the write side,
         // measured 1-5 % SLOWER than this plain 2-D grid: the index arithmetic costs more than it gains)

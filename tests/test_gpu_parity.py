@@ -63,6 +63,23 @@ def test_pack_pbm_raw_bytes(gpu, orc):
         assert np.array_equal(gpu.pack_pbm(raw), orc.pack_pbm(raw)), (w, h)
 
 
+def test_rotate_orth_bulk_copy_tiles(gpu, orc):
+    """90 / 270 degrees on rasters whose sides are multiples of 16 take the bulk-copy (cp.async.bulk) transposer
+    (64 x 64 tiles, narrower / shorter at the right and bottom edges);
+    the register-path kernel (variant 6) and the generic one (variant 1) must give the same bytes."""
+    try:
+        for (w, h) in [(64, 64), (128, 64), (64, 192), (320, 256), (1024, 576), (16, 16), (80, 48), (144, 208), (48, 400)]:
+            for name in ("lcg", "xramp", "yramp"):
+                img = P.all_patterns(w, h).get(name, P.lcg(w, h, 3))
+                for a in (90, 270):
+                    exp = orc.rotate(img, a)
+                    for v in (0, 6, 1):
+                        gpu.set_tuning("variant", v)
+                        assert np.array_equal(gpu.rotate(img, a), exp), (w, h, name, a, v)
+    finally:
+        gpu.set_tuning("variant", 0)
+
+
 def test_rotate_bicubic_sweep(gpu, orc):
     for (w, h) in [(1, 1), (2, 2), (3, 5), (5, 4), (6, 6), (37, 23), (64, 48), (100, 37)]:
         pats = P.all_patterns(w, h)
