@@ -270,9 +270,13 @@ def test_extension_conv_row_bands(gpu, orc):
     pointers (here: the neighbour band in the same HBM), equals the whole-raster result."""
     import torch
     import imageprocessingtools_b200.ppmx as pp
-    for (w, h, k, cuts) in [(128, 96, 3, [0, 32, 64, 96]), (128, 96, 7, [0, 24, 48, 72, 96]), (64, 50, 5, [0, 7, 13, 50]),
-                            (37, 23, 3, [0, 10, 23]), (256, 40, 7, [0, 3, 6, 40])]:
-        coef, div, bias = (np.ones((k, k), np.int64), k * k, 0) if k != 5 else KERNELS["emboss5"]
+    for (w, h, k, cuts, kname) in [(128, 96, 3, [0, 32, 64, 96], None), (128, 96, 7, [0, 24, 48, 72, 96], None),
+                                   (64, 50, 5, [0, 7, 13, 50], "emboss5"), (37, 23, 3, [0, 10, 23], None),
+                                   (256, 40, 7, [0, 3, 6, 40], None),
+                                   (128, 96, 5, [0, 32, 64, 96], "gauss5"), (256, 40, 7, [0, 3, 6, 40], "gauss7"),   # rank-1 kernel
+                                   (64, 50, 5, [0, 7, 13, 50], "sep5_asym"), (128, 200, 3, [0, 67, 134, 200], "edge3"),
+                                   (128, 96, 5, [0, 24, 48, 72, 96], "box5"), (64, 64, 11, [0, 16, 37, 64], "box11")]:
+        coef, div, bias = (np.ones((k, k), np.int64), k * k, 0) if kname is None else KERNELS[kname]
         img = P.lcg(w, h, 77)
         exp = orc.conv(img, coef, div, bias)
         r = k // 2
