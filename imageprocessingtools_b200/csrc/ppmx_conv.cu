@@ -873,6 +873,12 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
 {
     if (k < 1 || k > CONV_MAXK || !(k & 1) || div < 1) return cudaErrorInvalidValue;
     if (!w || !h) return cudaSuccess;
+    if (band.full_h) {  // a row band: the k/2 rows beyond either cut must be reachable through the halo pointers
+        const uint32_t r = (uint32_t)k / 2;
+        if ((uint64_t)band.y0 + h > band.full_h) return cudaErrorInvalidValue;
+        if (band.y0 > 0 && r > 0 && (!band.top || band.halo < r)) return cudaErrorInvalidValue;
+        if (band.y0 + h < band.full_h && r > 0 && (!band.bottom || band.halo < r)) return cudaErrorInvalidValue;
+    }
     const RowSource rs = make_row_source(src, h, band);
 
     bool s8 = true;

@@ -298,6 +298,14 @@ def test_extension_conv_row_bands(gpu, orc):
         torch.cuda.synchronize()
         got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
         assert np.array_equal(got, exp), (w, h, k)
+    # a band whose halo is thinner than k/2, or missing, is refused instead of read out of bounds
+    mid = torch.zeros((32, 128, 3), dtype=torch.uint8, device=dev)
+    op7 = gpu.conv_op(np.ones((7, 7), np.int64), 49, 0)
+    for bad in (pp.PpmxBand(full_h=96, y0=32, halo=1, d_top=mid.data_ptr(), d_bottom=mid.data_ptr()),
+                pp.PpmxBand(full_h=96, y0=32, halo=3, d_top=mid.data_ptr()),
+                pp.PpmxBand(full_h=40, y0=32, halo=3, d_top=mid.data_ptr())):
+        with pytest.raises(pp.PpmxError):
+            gpu.launch(op7, mid.data_ptr(), 128, 32, pp.LAYOUT_RGB8, mid.data_ptr(), bad)
 
 
 def test_imresize_height_pass_row_bands(gpu, orc):
