@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(256) conv_dp4a_kernel(RowSource rs, uint8_t *_
 // rule at the raster's edge.  Instruction mix per output byte: 3 IDP (fma pipe), ~1.1 PRMT + 0.75..1.5
 // finishing (alu pipe) -- both pipes issue 64 lanes/clk/SM (tools/int_peak.cu), so the kernel is bound by HBM.
 struct Conv3Coef {
-    uint32_t a[3], b[3];  // per tap column dx = -1, 0, +1: the coefficient bytes for the upper / lower row of a pair
+    uint32_t a[3], b[3];    // per tap column dx = -1, 0, +1: the coefficient bytes for the upper / lower row of a pair
+    uint32_t ah[3], bh[3];  // WIDE kernels only: coefficients beyond a signed byte are split c = 128 * hi + lo
 };
 
 template <int MODE>
@@ -289,7 +290,7 @@ __device__ __forceinline__ uint32_t strip_pack4(const ConvRound &rnd, int32_t a0
     return rnd.template pack4<MODE>(a0, a1, a2, a3);
 }
 
-template <int MODE, int RH, int PF, bool INNER>
+template <int MODE, int RH, int PF, bool INNER, bool WIDE>
 __device__ __forceinline__ void conv3_strip_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, uint32_t cx,
                                                  int ys, const Conv3Coef &cf, const ConvRound &rnd)
 {
@@ -360,6 +361,10 @@ __device__ __forceinline__ void conv3_strip_body(const RowSource &rs, uint8_t *_
                     const int c = 4 * b + j + 4;
                     accA[j] = dp4a_u8s8(V[c + 3], cf.a[2], dp4a_u8s8(V[c], cf.a[1], dp4a_u8s8(V[c - 3], cf.a[0], rnd.start)));
                     accB[j] = dp4a_u8s8(V[c + 3], cf.b[2], dp4a_u8s8(V[c], cf.b[1], dp4a_u8s8(V[c - 3], cf.b[0], rnd.start)));
+                    if (WIDE) {  // the high parts of the coefficients: a second dp4a chain, weighted 128
+                        accA[j] += dp4a_u8s8(V[c + 3], cf.ah[2], dp4a_u8s8(V[c], cf.ah[1], dp4a_u8s8(V[c - 3], cf.ah[0], 0))) << 7;
+                        accB[j] += dp4a_u8s8(V[c + 3], cf.bh[2], dp4a_u8s8(V[c], cf.bh[1], dp4a_u8s8(V[c - 3], cf.bh[0], 0))) << 7;
+                    }
                 }
                 oa[b] = strip_pack4<MODE>(rnd, accA[0], accA[1], accA[2], accA[3]);
                 ob[b] = strip_pack4<MODE>(rnd, accB[0], accB[1], accB[2], accB[3]);
@@ -371,7 +376,7 @@ __device__ __forceinline__ void conv3_strip_body(const RowSource &rs, uint8_t *_
     }
 }
 
-template <int MODE, int RH, int PF, int BLOCK>
+template <int MODE, int RH, int PF, int BLOCK, bool WIDE = false>
 __global__ void __launch_bounds__(BLOCK) conv3_strip_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks,
                                                             const Conv3Coef cf, const ConvRound rnd)
 {
@@ -381,8 +386,8 @@ __global__ void __launch_bounds__(BLOCK) conv3_strip_kernel(RowSource rs, uint8_
     const int ys = blockIdx.y * RH;  // first output row of the strip, band-local
     // source rows ys-1 .. ys+RH all inside the own band (all strips but the first and last of a band): plain
     // pointer steps; otherwise every row goes through the mirror / halo resolver
-    if (ys >= 1 && ys + RH + 1 <= rs.h) conv3_strip_body<MODE, RH, PF, true>(rs, dst, nchunks, cx, ys, cf, rnd);
-    else conv3_strip_body<MODE, RH, PF, false>(rs, dst, nchunks, cx, ys, cf, rnd);
+    if (ys >= 1 && ys + RH + 1 <= rs.h) conv3_strip_body<MODE, RH, PF, true, WIDE>(rs, dst, nchunks, cx, ys, cf, rnd);
+    else conv3_strip_body<MODE, RH, PF, false, WIDE>(rs, dst, nchunks, cx, ys, cf, rnd);
 }
 
 static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef,
@@ -393,11 +398,24 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
     // -- three PRMT per four bytes instead of shift + saturating pack -- measured 2 % SLOWER: 0.934 vs 0.953)
     const int mode = rnd.mode;
     Conv3Coef cf;
+    bool wide = false;
     for (int dx = 0; dx < 3; dx++) {
-        const uint32_t t = (uint32_t)(uint8_t)(int8_t)c[dx], m = (uint32_t)(uint8_t)(int8_t)c[3 + dx],
-                       b = (uint32_t)(uint8_t)(int8_t)c[6 + dx];
-        cf.a[dx] = t | m << 8 | b << 16;
-        cf.b[dx] = t << 8 | m << 16 | b << 24;
+        uint32_t lo[3], hi[3];
+        for (int dy = 0; dy < 3; dy++) {  // c = 128 * hi + lo with lo in -64..63; hi == 0 for every byte-sized coefficient
+            const int32_t v = c[3 * dy + dx];
+            int32_t l = v, hpart = 0;
+            if (v < -128 || v > 127) {
+                l = ((v + 64) & 127) - 64;
+                hpart = (v - l) / 128;
+                wide = true;
+            }
+            lo[dy] = (uint32_t)(uint8_t)(int8_t)l;
+            hi[dy] = (uint32_t)(uint8_t)(int8_t)hpart;
+        }
+        cf.a[dx] = lo[0] | lo[1] << 8 | lo[2] << 16;
+        cf.b[dx] = lo[0] << 8 | lo[1] << 16 | lo[2] << 24;
+        cf.ah[dx] = hi[0] | hi[1] << 8 | hi[2] << 16;
+        cf.bh[dx] = hi[0] << 8 | hi[1] << 16 | hi[2] << 24;
     }
     const uint32_t nchunks = w * 3 / 16;
 #define PPMX_CONV3_LAUNCH(MODE, RH, PF, BLOCK)                                                                   \
@@ -416,6 +434,14 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
     // 4/2/128: 0.94 of the HBM roofline, 4/2/256: 0.92, 8/2/128: 0.84, 8/4/128: 0.84, 16/1/128: 0.74, 32/1/128: 0.68 --
     // the flatter the better (all six source rows of a strip are requested before the first dp4a, and the CTAs
     // resident at any moment cover a compact block of rows), as for the colour kernels.
+    if (wide) {  // 6 instead of 3 dp4a per byte: still above what HBM delivers
+        dim3 grid((nchunks + 127) / 128, (h + 3) / 4);
+        if (grid.y > 65535u) return cudaErrorInvalidValue;
+        if (mode == 0) launch(conv3_strip_kernel<0, 4, 2, 128, true>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd);
+        else if (mode == 1) launch(conv3_strip_kernel<1, 4, 2, 128, true>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd);
+        else launch(conv3_strip_kernel<2, 4, 2, 128, true>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd);
+        return PPMX_LAUNCHED();
+    }
     if (g_variant == 9) PPMX_CONV3_MODES(2, 1, 128);
     else if (g_variant == 10) PPMX_CONV3_MODES(4, 2, 256);
     else if (g_variant == 11) PPMX_CONV3_MODES(8, 2, 128);
@@ -903,6 +929,12 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         // rank-1 (only the two factors must be small, not their products): sliding vertical words
         cudaError_t e = cudaSuccess;
         if (k == 5 ? conv_sep<5>(rs, dst, w, h, coef, rnd, s, &e) : conv_sep<7>(rs, dst, w, h, coef, rnd, s, &e)) return e;
+    }
+    if (k == 3 && !s8 && rnd_ok && fast_layout && aligned16(dst) && g_variant != 7) {
+        // coefficients beyond a signed byte (up to +-16320): the strip kernel splits them into two dp4a chains
+        bool splittable = true;
+        for (int i = 0; i < 9; i++) splittable = splittable && coef[i] >= -16320 && coef[i] <= 16320;
+        if (splittable) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s);
     }
     if (s8 && (k == 3 || k == 5 || k == 7) && fast_layout && aligned4(dst) && rnd_ok) {
         // variant 7 keeps the row-wise (planar dp4a) kernel for 3x3; the strip kernel is the default

@@ -248,6 +248,8 @@ KERNELS["sep5_asym"] = (np.outer([1, 2, 3, 2, 1], [-1, -2, 0, 2, 1]), 8, 128)   
 KERNELS["sep7_div3"] = (np.outer([1, 1, 2, 3, 2, 1, 1], [1, 2, 3, 4, 3, 2, 1]), 3, 0)               # rank 1, general divisor, saturates
 KERNELS["sep7_div1_neg"] = (np.outer([0, -1, 2, -3, 2, -1, 0], [1, 0, -2, 3, -2, 0, 1]), 1, 100)    # rank 1, zeros and signs, div 1
 KERNELS["gauss5"] = (np.outer([1, 4, 6, 4, 1], [1, 4, 6, 4, 1]), 256, 0)
+KERNELS["wide3"] = (np.array([[-300, 200, 129], [-129, 5000, -128], [127, 128, -16320]]), 997, 40)   # 3x3 beyond int8: split dp4a chains
+KERNELS["wide3_pow2"] = (np.array([[256, 512, 256], [512, 1024, 512], [256, 512, 256]]), 4096, 0)
 KERNELS["box9"] = (np.ones((9, 9), np.int64), 81, 0)
 KERNELS["box11"] = (np.ones((11, 11), np.int64), 121, 0)
 KERNELS["box11_bias"] = (np.ones((11, 11), np.int64), 121, 3)                                          # constants overflow 32 bits: generic kernel
@@ -484,7 +486,7 @@ def test_extension_conv3_strip_variants(gpu, orc):
     scaled-coefficient byte extraction) and the row-wise planar kernel (variant 7) give the self-oracle's bytes,
     on flat extremes too (saturation at both ends)."""
     imgs = [P.lcg(64, 200, 5), P.const(64, 131, 255), P.const(32, 70, 0), P.all_patterns(48, 133)["checker"]]
-    names = ("blur3", "sharpen3", "edge3", "mix3_div8_biasneg", "sobel3")
+    names = ("blur3", "sharpen3", "edge3", "mix3_div8_biasneg", "sobel3", "wide3", "wide3_pow2")
     exp = {(i, k): orc.conv(img, *KERNELS[k]) for i, img in enumerate(imgs) for k in names}
     exp_big = orc.conv(imgs[0], np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]]) * 4, 64, 0)  # scaled coefficients would pass 127
     try:
