@@ -49,6 +49,7 @@ WORKLOADS = {
     "levels": (4096, 4096, 8, 6.0, "4096x4096 levels (256-entry table on every byte, extension), 8 rasters per step"),
     "conv3": (8192, 8192, 2, 6.0, "8192x8192 3x3 blur (extension, config 3), 2 rasters per step"),
     "conv7": (8192, 8192, 2, 6.0, "8192x8192 7x7 box (extension, config 3), 2 rasters per step"),
+    "conv3_odd": (4090, 4090, 4, 6.0, "4090x4090 3x3 blur (extension): a width that is no multiple of 16 goes through a padded copy, 4 rasters per step"),
     "gauss7": (8192, 8192, 2, 6.0, "8192x8192 7x7 binomial blur (1 6 15 20 15 6 1)^2 / 4096 (extension), 2 rasters per step"),
     "gauss5": (8192, 8192, 2, 6.0, "8192x8192 5x5 binomial blur (1 4 6 4 1)^2 / 256 (extension), 2 rasters per step"),
     "sharpen3": (8192, 8192, 2, 6.0, "8192x8192 3x3 sharpen (0 -1 0; -1 5 -1; 0 -1 0) (extension, config 3), 2 rasters per step"),
@@ -59,7 +60,7 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "gray_hist"
 PER_OP = ["gray", "gray_hist", "mono", "fliph", "flipv", "rot90", "rot180", "gray_16k", "mono_16k", "fliph_16k",
-          "rot90_16k", "levels", "conv3", "conv7", "sharpen3", "edge3", "gauss5", "gauss7", "resize_up", "resize_down", "rot30"]
+          "rot90_16k", "levels", "conv3", "conv7", "sharpen3", "edge3", "gauss5", "gauss7", "conv3_odd", "resize_up", "resize_down", "rot30"]
 
 
 def traffic_for(name):
@@ -183,8 +184,8 @@ class Runner:
             self.ops = [(op, op.new_width, op.new_height, op.new_width * op.new_height * 3)]
         elif name == "levels":
             self.ops = [(g.levels_op(g.levels_lut_linear(16, 235)), w, h, w * h * 3)]
-        elif name in ("conv3", "conv7", "sharpen3", "edge3", "gauss5", "gauss7"):
-            if name == "conv3":
+        elif name in ("conv3", "conv7", "sharpen3", "edge3", "gauss5", "gauss7", "conv3_odd"):
+            if name in ("conv3", "conv3_odd"):
                 coef, div = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], np.int32), 16
             elif name == "sharpen3":
                 coef, div = np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]], np.int32), 1

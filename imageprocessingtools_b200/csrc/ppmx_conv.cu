@@ -894,6 +894,52 @@ static cudaError_t conv_fast(const RowSource &rs, uint8_t *dst, uint32_t w, uint
     return PPMX_LAUNCHED();
 }
 
+// ---- rasters whose width or pointers do not allow 16-byte vectors (w % 16 != 0, odd addresses) ----------------
+// The vector kernels want a row pitch that is a multiple of 16 bytes.  Such a raster is copied into a pool buffer
+// of width wp = roundup(w + k/2, 16) with the columns beyond the right edge filled by the mirror rule (so every real
+// pixel sees exactly the neighbours the border rule gives it), convolved there by the fast kernels, and the real
+// columns are copied out again: two extra passes through the copy engine's 2-D path.
+// The rows themselves move by cudaMemcpy2DAsync (device to device, any pitch); this kernel only fills the
+// wp - w mirrored pixels at the end of every padded row.
+__global__ void __launch_bounds__(64) conv_pad_edge_kernel(uint8_t *__restrict__ padded, uint32_t w, uint32_t wp)
+{
+    PDL_PROLOGUE();
+    const uint32_t t = threadIdx.x, y = blockIdx.x;  // byte t of the mirrored tail of padded row y
+    if (t >= (wp - w) * 3u) return;
+    uint8_t *row = padded + (size_t)y * wp * 3;
+    const uint32_t px = w + t / 3u, ch = t % 3u;
+    row[px * 3u + ch] = row[(uint32_t)mirror_index((int)px, (int)w) * 3u + ch];
+}
+
+cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef, int32_t div,
+                 int32_t bias, const Band &band, cudaStream_t s);
+
+static cudaError_t conv_padded(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef, int32_t div,
+                               int32_t bias, cudaStream_t s)
+{
+    const uint32_t wp = (w + (uint32_t)k / 2 + 15u) & ~15u;
+    const size_t nb_pad = (size_t)wp * h * 3;
+    uint8_t *tin = nullptr, *tout = nullptr;
+    cudaError_t e = cudaMallocAsync(&tin, nb_pad, s);
+    if (e != cudaSuccess) return e;
+    e = cudaMallocAsync(&tout, nb_pad, s);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(tin, s);
+        return e;
+    }
+    // (wp - w <= k/2 + 15 <= 20 pixels = 60 bytes: one 64-thread CTA per row)
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(tin, (size_t)wp * 3, src, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) {
+        launch(conv_pad_edge_kernel, dim3(h), dim3(64), 0, s, tin, w, wp);
+        e = PPMX_LAUNCHED();
+    }
+    if (e == cudaSuccess) e = conv(tin, tout, wp, h, k, coef, div, bias, Band(), s);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(dst, (size_t)w * 3, tout, (size_t)wp * 3, (size_t)w * 3, h, cudaMemcpyDeviceToDevice, s);
+    cudaFreeAsync(tin, s);
+    cudaFreeAsync(tout, s);
+    return e;
+}
+
 cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef, int32_t div,
                  int32_t bias, const Band &band, cudaStream_t s)
 {
@@ -943,6 +989,10 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         if (k == 5) return conv_fast<5>(rs, dst, w, h, coef, rnd, s);
         return conv_fast<7>(rs, dst, w, h, coef, rnd, s);
     }
+    // a whole raster that only lacks the layout for the vector kernels goes through a padded copy (variant 1 = never)
+    const bool layout_only = ((w % 16u) != 0 || !aligned16(src) || !aligned16(dst)) && !band.full_h && g_variant != 1 &&
+                             g_variant != 7 && w >= 16 && k <= 11 && (size_t)w * h >= 4096;
+    if (layout_only) return conv_padded(src, dst, w, h, k, coef, div, bias, s);
     ConvCoefGeneric cf;
     for (int i = 0; i < CONV_MAXK * CONV_MAXK; i++) cf.c[i] = i < k * k ? coef[i] : 0;
     dim3 grid((w + CONV_TW - 1) / CONV_TW, (h + CONV_TH - 1) / CONV_TH);
