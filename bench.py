@@ -46,6 +46,11 @@ WORKLOADS = {
     "mono_16k": (16384, 16384, 2, 3.125, "16384x16384 -> Bayer bilevel P4 bits, two rasters per step"),
     "fliph_16k": (16384, 16384, 2, 6.0, "16384x16384 horizontal flip, two rasters per step"),
     "rot90_16k": (16384, 16384, 2, 6.0, "16384x16384 rotate 90, two rasters per step"),
+    "mono_4090": (4090, 4090, 8, 3.125, "4090x4090 -> Bayer bilevel bits: sides no multiple of 16 (generic kernel), 8 rasters per step"),
+    "fliph_4090": (4090, 4090, 8, 6.0, "4090x4090 horizontal flip: sides no multiple of 16 (generic kernel), 8 rasters per step"),
+    "flipv_4090": (4090, 4090, 8, 6.0, "4090x4090 vertical flip: sides no multiple of 16 (generic kernel), 8 rasters per step"),
+    "rot90_4090": (4090, 4090, 8, 6.0, "4090x4090 rotate 90: sides no multiple of 16 (generic kernel), 8 rasters per step"),
+    "gray_4090": (4090, 4090, 8, 4.0, "4090x4090 RGB->greyscale: sides no multiple of 16, 8 rasters per step"),
     "levels": (4096, 4096, 8, 6.0, "4096x4096 levels (256-entry table on every byte, extension), 8 rasters per step"),
     "conv3": (8192, 8192, 2, 6.0, "8192x8192 3x3 blur (extension, config 3), 2 rasters per step"),
     "conv7": (8192, 8192, 2, 6.0, "8192x8192 7x7 box (extension, config 3), 2 rasters per step"),
@@ -170,6 +175,8 @@ class Runner:
         base = name.split("_16k")[0]
         if name.endswith("_16k"):
             name = base
+        if name.endswith("_4090"):  # same operator on a raster whose sides are no multiple of 16 (generic kernels)
+            name = name[:-5]
         if name in ("gray", "gray_hist"):
             kind = L.OP_GRAY if name == "gray" else L.OP_GRAY_HIST
             self.ops = [(L.PpmxOp(kind=kind), w, h, w * h)]

@@ -87,6 +87,48 @@ __global__ void __launch_bounds__(256) fliph_rgb16_kernel(const uint4 *__restric
     q[2] = make_uint4(o[8], o[9], o[10], o[11]);
 }
 
+// Rows of any length at any alignment (widths that are no multiple of 16, odd pointers): one grid row per raster
+// row, one thread per ALIGNED destination word.  Vertical: the four source bytes come out of two aligned source
+// words by a funnel shift (source and destination rows are misaligned differently); horizontal: four byte loads
+// from the mirrored pixels.  Words cut by the row's ends are written byte by byte.  No 64-bit division anywhere.
+template <bool HFLIP, int BPP>
+__global__ void __launch_bounds__(256) flip_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t w,
+                                                        uint32_t h)
+{
+    PDL_PROLOGUE();
+    const uint32_t y = blockIdx.y, row = w * BPP;
+    uint8_t *D0 = dst + (size_t)y * row;
+    const uint8_t *S0 = src + (size_t)(HFLIP ? y : h - 1u - y) * row;
+    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(D0) & 3u), nwords = (a0 + row + 3u) / 4u;
+    for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < nwords; k += gridDim.x * 256u) {
+        const int b0 = (int)(4u * k) - (int)a0;  // first row byte of this destination word
+        const bool full = b0 >= 0 && (uint32_t)b0 + 4u <= row;
+        if (!HFLIP && full) {
+            const uint8_t *q = S0 + b0;
+            const uint32_t m = (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3u);
+            const uint32_t *base = reinterpret_cast<const uint32_t *>(q - m);
+            const uint32_t w0 = __ldg(base), w1 = m ? __ldg(base + 1) : 0u;
+            *reinterpret_cast<uint32_t *>(D0 + b0) = __funnelshift_r(w0, w1, 8u * m);
+            continue;
+        }
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int b = b0 + j;
+            if (b < 0 || (uint32_t)b >= row) continue;
+            uint32_t sb = (uint32_t)b;
+            if (HFLIP) {
+                const uint32_t x = (uint32_t)b / BPP, c = (uint32_t)b - x * BPP;
+                sb = (w - 1u - x) * BPP + c;
+            }
+            const uint32_t byte = S0[sb];
+            if (full) v |= byte << (8 * j);
+            else D0[b] = (uint8_t)byte;
+        }
+        if (full) *reinterpret_cast<uint32_t *>(D0 + b0) = v;
+    }
+}
+
 cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int bpp, int vertical, cudaStream_t s)
 {
     if (!w || !h) return cudaSuccess;
@@ -100,6 +142,10 @@ cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int b
             size_t n = row / 4 * h;
             launch(flipv_kernel<uint32_t>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
                    reinterpret_cast<const uint32_t *>(src), reinterpret_cast<uint32_t *>(dst), (uint32_t)(row / 4), h, n);
+        } else if (h <= 65535u && g_variant != 1) {
+            const unsigned gx = (unsigned)((row / 4 + 1 + 255) / 256);
+            if (bpp == 3) launch(flip_rows_kernel<false, 3>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
+            else launch(flip_rows_kernel<false, 1>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
         } else {
             launch(flipv_kernel<uint8_t>, dim3((unsigned)((row * h + 255) / 256)), dim3(256), 0, s, src, dst, (uint32_t)row, h,
                    row * h);
@@ -109,6 +155,10 @@ cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int b
             size_t n = (size_t)(w / 16u) * h;
             launch(fliph_rgb16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
                    reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), w / 16u, n);
+        } else if (h <= 65535u && (bpp == 3 || bpp == 1) && g_variant != 1) {
+            const unsigned gx = (unsigned)((row / 4 + 1 + 255) / 256);
+            if (bpp == 3) launch(flip_rows_kernel<true, 3>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
+            else launch(flip_rows_kernel<true, 1>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
         } else {
             launch(fliph_generic_kernel, dim3(wave_grid(row * h, 256, 8)), dim3(256), 0, s, src, dst, w, h, bpp);
         }
