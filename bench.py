@@ -50,6 +50,7 @@ WORKLOADS = {
     "fliph_4090": (4090, 4090, 8, 6.0, "4090x4090 horizontal flip: sides no multiple of 16 (generic kernel), 8 rasters per step"),
     "flipv_4090": (4090, 4090, 8, 6.0, "4090x4090 vertical flip: sides no multiple of 16 (generic kernel), 8 rasters per step"),
     "rot90_4090": (4090, 4090, 8, 6.0, "4090x4090 rotate 90: sides no multiple of 16 (generic kernel), 8 rasters per step"),
+    "rot180_4090": (4090, 4090, 8, 6.0, "4090x4090 rotate 180: sides no multiple of 16 (generic kernel), 8 rasters per step"),
     "gray_4090": (4090, 4090, 8, 4.0, "4090x4090 RGB->greyscale: sides no multiple of 16, 8 rasters per step"),
     "levels": (4096, 4096, 8, 6.0, "4096x4096 levels (256-entry table on every byte, extension), 8 rasters per step"),
     "conv3": (8192, 8192, 2, 6.0, "8192x8192 3x3 blur (extension, config 3), 2 rasters per step"),

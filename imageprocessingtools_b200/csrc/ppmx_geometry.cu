@@ -91,14 +91,14 @@ __global__ void __launch_bounds__(256) fliph_rgb16_kernel(const uint4 *__restric
 // row, one thread per ALIGNED destination word.  Vertical: the four source bytes come out of two aligned source
 // words by a funnel shift (source and destination rows are misaligned differently); horizontal: four byte loads
 // from the mirrored pixels.  Words cut by the row's ends are written byte by byte.  No 64-bit division anywhere.
-template <bool HFLIP, int BPP>
+template <bool HFLIP, int BPP, bool VFLIP = !HFLIP>
 __global__ void __launch_bounds__(256) flip_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t w,
                                                         uint32_t h)
 {
     PDL_PROLOGUE();
     const uint32_t y = blockIdx.y, row = w * BPP;
     uint8_t *D0 = dst + (size_t)y * row;
-    const uint8_t *S0 = src + (size_t)(HFLIP ? y : h - 1u - y) * row;
+    const uint8_t *S0 = src + (size_t)(VFLIP ? h - 1u - y : y) * row;  // (both flips together = 180 degrees, ref:721)
     const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(D0) & 3u), nwords = (a0 + row + 3u) / 4u;
     for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < nwords; k += gridDim.x * 256u) {
         const int b0 = (int)(4u * k) - (int)a0;  // first row byte of this destination word
@@ -461,6 +461,9 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
             if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
             launch(fliph_rgb16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
                    reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), (uint32_t)n, n);
+        } else if (h <= 65535u && g_variant != 1) {  // any layout: mirrored rows taken from the mirrored row
+            const unsigned gx = (unsigned)(((size_t)w * 3 / 4 + 1 + 255) / 256);
+            launch(flip_rows_kernel<true, 3, true>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
         } else {
             launch(reverse_pixels_kernel, dim3(wave_grid(npix * 3, 256, 8)), dim3(256), 0, s, src, dst, npix);
         }
