@@ -991,7 +991,8 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
     }
     // a whole raster that only lacks the layout for the vector kernels goes through a padded copy (variant 1 = never)
     const bool layout_only = ((w % 16u) != 0 || !aligned16(src) || !aligned16(dst)) && !band.full_h && g_variant != 1 &&
-                             g_variant != 7 && w >= 16 && k <= 11 && (size_t)w * h >= 4096;
+                             g_variant != 7 && w >= 16 && (size_t)w * h >= 4096 &&
+                             (k <= 7 || (k <= 11 && box_constants(coef, k, div, bias, &bm, &bc)));  // a vector kernel exists
     if (layout_only) return conv_padded(src, dst, w, h, k, coef, div, bias, s);
     ConvCoefGeneric cf;
     for (int i = 0; i < CONV_MAXK * CONV_MAXK; i++) cf.c[i] = i < k * k ? coef[i] : 0;
