@@ -223,16 +223,30 @@ class Runner:
         self.tabs = [g.tables_upload(o[0]) if o[0].kind == L.OP_IMRESIZE else 0 for o in self.ops]
         self.launches_per_step = batch * len(self.ops)
         self.pixels_per_step = batch * w * h  # input pixels (resize/rotate: also reported per output px)
-
-    def step(self, stream):
-        L = self.pp
-        for b in range(self.batch):
-            src, w, h = self.src[b].data_ptr(), self.w, self.h
+        # The argument lists of every ppmx_gpu_launch of a step are built ONCE: a 4096^2 launch lasts ~12 us on the
+        # device, and slicing tensors + boxing ctypes values per call costs about as much on a slow host core, which
+        # would make the step a measurement of Python, not of the kernels.
+        import ctypes as C
+        hist_ptr = C.c_void_p(self.hist.data_ptr() if self.hist is not None else 0)
+        self._calls = []
+        for b in range(batch):
+            src, cw, chh = self.src[b].data_ptr(), w, h
             for i, (op, ow, oh, nbytes) in enumerate(self.ops):
                 dst = self.dst[i][b].data_ptr()
-                self.g.launch(op, src, w, h, L.LAYOUT_RGB8, dst, None, self.hist.data_ptr() if self.hist is not None else 0,
-                              self.tabs[i], stream)
-                src, w, h = dst, ow, oh
+                self._calls.append((C.byref(op), C.c_void_p(src), cw, chh, L.LAYOUT_RGB8, C.c_void_p(dst), None, hist_ptr,
+                                    C.c_void_p(self.tabs[i])))
+                src, cw, chh = dst, ow, oh
+        self._launch = g.L.ppmx_gpu_launch
+        self._stream = (None, None)
+
+    def step(self, stream):
+        if self._stream[0] != stream:
+            import ctypes as C
+            self._stream = (stream, C.c_void_p(stream))
+        st, fn = self._stream[1], self._launch
+        for a in self._calls:
+            if fn(*a, st) != 0:
+                raise SystemExit("ppmx_gpu_launch failed")
 
     def close(self):
         for t in self.tabs:
