@@ -192,14 +192,14 @@ cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_
     int xo = (int)(nw / 2u) - (int)(w / 2u), yo = (int)(nh / 2u) - (int)(h / 2u);
     dim3 block(32, 8), grid((nw + 31) / 32, (nh + 7) / 8);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
-    if ((w % 4u) == 0 && aligned4(src) && g_variant != 1) {
+    if ((w % 4u) == 0 && aligned4(src) && PPMX_VARIANT != 1) {
         // with the index conversions off the XU pipe (floor_int/floor_both) all 48 byte conversions fit there:
         // measured 56.5 Gpix/s (CONV 0) vs 53.5 (3 of 4 on XU) vs 51.0 (half) vs 47.8 (all on the FP64 pipe)
-        if (g_variant == 2)
+        if (PPMX_VARIANT == 2)
             launch(rotate_bicubic_kernel<true, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
-        else if (g_variant == 3)
+        else if (PPMX_VARIANT == 3)
             launch(rotate_bicubic_kernel<true, 2>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
-        else if (g_variant == 4)
+        else if (PPMX_VARIANT == 4)
             launch(rotate_bicubic_kernel<true, 3>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
         else
             launch(rotate_bicubic_kernel<true, 0>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
@@ -413,13 +413,13 @@ static void launch_colsK(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t 
     for (uint32_t y0 = 0; y0 < h; y0 += 65535u * rows_per_cta) {
         uint32_t rows = min(65535u * rows_per_cta, h - y0);
         dim3 grid((out_w + 127) / 128, (rows + rows_per_cta - 1) / rows_per_cta);
-        if (g_variant == 2)
+        if (PPMX_VARIANT == 2)
             launch(imresize_colsK_kernel<K, 1>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
                    dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
-        else if (g_variant == 3)
+        else if (PPMX_VARIANT == 3)
             launch(imresize_colsK_kernel<K, 0>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
                    dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
-        else if (g_variant == 4)
+        else if (PPMX_VARIANT == 4)
             launch(imresize_colsK_kernel<K, 2>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
                    dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
         else  // three of four byte conversions on the XU pipe: 1-3 % faster than half/half once the first-tap adds are gone
@@ -506,8 +506,8 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
         }
         const bool halo_ok = (!band.top || aligned16(band.top)) && (!band.bottom || aligned16(band.bottom));
         uint32_t row_bytes = w * 3u;
-        if (row_bytes % 16 == 0 && aligned16(src_ptr) && aligned16(dst) && halo_ok && taps <= ROWS16_MAXK && g_variant != 1) {
-            const bool narrow = (g_variant == 6);  // 8 bytes per thread
+        if (row_bytes % 16 == 0 && aligned16(src_ptr) && aligned16(dst) && halo_ok && taps <= ROWS16_MAXK && PPMX_VARIANT != 1) {
+            const bool narrow = (PPMX_VARIANT == 6);  // 8 bytes per thread
             const uint32_t vecs = narrow ? row_bytes / 8 : row_bytes / 16;
             dim3 grid((vecs + 255) / 256, 1);
             for (int y0 = 0; y0 < out_size; y0 += 65535) {
@@ -517,14 +517,14 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
                 const double *w0 = d_weights + (size_t)y0 * taps;
                 const int *i0 = d_indices + (size_t)y0 * taps;
                 if (narrow) launch(imresize_rows16_kernel<2, 2>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else if (g_variant == 2) launch(imresize_rows16_kernel<1, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else if (g_variant == 3) launch(imresize_rows16_kernel<0, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else if (g_variant == 4) launch(imresize_rows16_kernel<2, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else if (taps == 4 && g_variant != 5) launch(imresize_rows16_kernel<3, 4, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else if (taps == 5 && g_variant != 5) launch(imresize_rows16_kernel<3, 4, 5>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else if (taps == 6 && g_variant != 5) launch(imresize_rows16_kernel<3, 4, 6>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else if (taps == 7 && g_variant != 5) launch(imresize_rows16_kernel<3, 4, 7>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else if (taps == 8 && g_variant != 5) launch(imresize_rows16_kernel<3, 4, 8>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (PPMX_VARIANT == 2) launch(imresize_rows16_kernel<1, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (PPMX_VARIANT == 3) launch(imresize_rows16_kernel<0, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (PPMX_VARIANT == 4) launch(imresize_rows16_kernel<2, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 4 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 5 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 5>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 6 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 6>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 7 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 7>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 8 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 8>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else launch(imresize_rows16_kernel<3, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
             }
             return cudaGetLastError();
@@ -550,7 +550,7 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
         return cudaGetLastError();
     }
     const uint8_t *src = src_ptr;
-    if ((w % 4u) == 0 && aligned4(src) && taps >= 4 && taps <= 8 && g_variant != 1) {
+    if ((w % 4u) == 0 && aligned4(src) && taps >= 4 && taps <= 8 && PPMX_VARIANT != 1) {
         switch (taps) {
         case 4: launch_colsK<4>(src, dst, w, h, out_size, d_weights, d_indices, s); break;
         case 5: launch_colsK<5>(src, dst, w, h, out_size, d_weights, d_indices, s); break;

@@ -4,10 +4,13 @@
 
 namespace ppmx {
 
-int g_variant = 0;
-int g_pdl = 1;  // ppmx_gpu_set_tuning("pdl", 0/1)
-unsigned long long g_launches = 0;
-unsigned long long launch_count() { return g_launches; }
+#ifdef PPMX_TUNING
+int g_variant = 0;  // ppmx_gpu_set_tuning("variant", n): only in the tuning build (libppmx_gpu_tuning.so)
+#endif
+std::atomic<int> g_pdl{1};  // ppmx_gpu_set_tuning("pdl", 0/1); process-wide
+std::atomic<unsigned long long> g_launches{0};
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void add_launches(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------
 // gray  (ref:998-1000)  RGB8 -> R8, flat over the raster; optional fused histogram (extension)
@@ -387,9 +390,9 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
     if (npix == 0) return cudaSuccess;
     if (aligned16(src) && (!STORE || aligned16(dst))) {
         size_t ngroups = npix / 16;
-        if (HIST && g_variant != 2 && g_variant != 5) {
+        if (HIST && PPMX_VARIANT != 2 && PPMX_VARIANT != 5) {
             // lane-private columns, RED.shared; one 1024-thread CTA per SM
-            static bool ok[64] = {};
+            static SmemOptIn ok;
             allow_smem(gray_hist_lanes_kernel<STORE>, HL_SMEM, ok);
             size_t want = (ngroups + HL_THREADS - 1) / HL_THREADS, wave = (size_t)sm_count();
             unsigned grid = (unsigned)(want < 1 ? 1 : want < wave ? want : wave);
@@ -397,9 +400,9 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
                    reinterpret_cast<uint4 *>(dst), ngroups, npix, d_hist);
             return PPMX_LAUNCHED();
         }
-        if (HIST && g_variant == 5) {
+        if (HIST && PPMX_VARIANT == 5) {
             // thread-private byte counters: <= 15 groups per thread between folds, 3 CTAs per SM
-            static bool ok[64] = {};
+            static SmemOptIn ok;
             allow_smem(gray_hist_private_kernel<STORE>, HP_SMEM, ok);
             size_t wave = (size_t)sm_count() * 3 * HP_THREADS;
             size_t per = (ngroups + wave - 1) / wave;
@@ -412,9 +415,9 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
                    reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), ngroups, npix, (uint32_t)per, d_hist);
             return PPMX_LAUNCHED();
         }
-        if (!HIST && g_variant != 1 && g_variant != 4) {  // default: one group per thread, no loop
-            if (g_variant == 6 || g_variant == 7) {  // smaller CTAs: shorter tail, more CTA launches
-                const unsigned blk = g_variant == 6 ? 128u : 64u;
+        if (!HIST && PPMX_VARIANT != 1 && PPMX_VARIANT != 4) {  // default: one group per thread, no loop
+            if (PPMX_VARIANT == 6 || PPMX_VARIANT == 7) {  // smaller CTAs: shorter tail, more CTA launches
+                const unsigned blk = PPMX_VARIANT == 6 ? 128u : 64u;
                 unsigned grid = (unsigned)((ngroups + blk - 1) / blk);
                 if (blk == 128) launch(gray_flat_kernel<128>, dim3(grid ? grid : 1), dim3(128), 0, s,
                                        reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), ngroups, npix);
@@ -427,8 +430,8 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
                    reinterpret_cast<uint4 *>(dst), ngroups, npix);
             return PPMX_LAUNCHED();
         }
-        if (!HIST && g_variant == 4) {
-            static bool ok[64] = {};
+        if (!HIST && PPMX_VARIANT == 4) {
+            static SmemOptIn ok;
             allow_smem(gray_tma_kernel, GT_SMEM, ok);
             size_t ntiles = (ngroups + GT_TILE_GROUPS - 1) / GT_TILE_GROUPS;
             unsigned grid = (unsigned)(ntiles < (size_t)sm_count() * 4 ? (ntiles ? ntiles : 1) : (size_t)sm_count() * 4);
@@ -696,8 +699,8 @@ cudaError_t levels(const uint8_t *src, uint8_t *dst, size_t nbytes, const uint8_
     LevelsLut l;
     for (int i = 0; i < 64; i++)
         l.w[i] = (uint32_t)lut[4 * i] | (uint32_t)lut[4 * i + 1] << 8 | (uint32_t)lut[4 * i + 2] << 16 | (uint32_t)lut[4 * i + 3] << 24;
-    if (aligned16(src) && aligned16(dst) && nbytes >= (size_t)1 << 20 && g_variant != 1) {
-        static bool ok[64] = {};
+    if (aligned16(src) && aligned16(dst) && nbytes >= (size_t)1 << 20 && PPMX_VARIANT != 1) {
+        static SmemOptIn ok;
         allow_smem(levels_lanes_kernel, LV_SMEM, ok);
         const size_t nvec = nbytes / 16, want = (nvec + LV_THREADS - 1) / LV_THREADS, wave = (size_t)sm_count();
         launch(levels_lanes_kernel, dim3((unsigned)(want < wave ? want : wave)), dim3(LV_THREADS), LV_SMEM, s,

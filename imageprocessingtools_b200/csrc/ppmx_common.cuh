@@ -12,20 +12,25 @@
 
 #include <cuda.h>
 
+#include <atomic>
+
 namespace ppmx {
 
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
 
-static int g_sm_count = 0;
+// SM count of the CURRENT device, cached per device (a racing first call stores the same value twice)
 static inline int sm_count()
 {
-    if (!g_sm_count) {  // every device a process sees in this pool is the same B200 part
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
-            g_sm_count = 148;
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (!n) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return g_sm_count;
+    return n;
 }
 
 #define PPMX_LAUNCHED() (cudaGetLastError())
@@ -42,14 +47,21 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
     } while (0)
 
 // opt in to > 48 KB dynamic shared memory once per (kernel, device)
+struct SmemOptIn {
+    std::atomic<bool> done[64];
+};
 template <typename K>
-static void allow_smem(K kernel, size_t bytes, bool (&done)[64])
+static void allow_smem(K kernel, size_t bytes, SmemOptIn &once)
 {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || done[dev]) return;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    done[dev] = true;
+    if (dev < 0 || dev >= 64) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        return;
+    }
+    if (once.done[dev].load(std::memory_order_acquire)) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);  // idempotent: a race repeats it
+    once.done[dev].store(true, std::memory_order_release);
 }
 
 template <typename... KArgs, typename... Args>
@@ -62,10 +74,10 @@ static cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    ++g_launches;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -120,8 +132,9 @@ __device__ __forceinline__ uint4 gray16(uint4 p, uint4 q, uint4 r)
     return o;
 }
 
-// Bayer thresholds of ref:954 times 255 (all exact), in the reference's own index order
-// (x%4)*4 + (y%4), ref:967.  bit = grey < threshold  <=>  !(grey >= matrix*255).
+// ceil(matrix * 255) for the Bayer matrix of ref:954 (the products are NOT all integers: 0.125 * 255 = 31.875), in the
+// reference's own index order (x%4)*4 + (y%4), ref:967.  Equivalent for an INTEGER grey: grey >= 31.875 <=> grey >= 32,
+// so bit = grey < c_bayer  <=>  !(grey >= matrix*255)  (checked for all 256 x 16 cases in tests/test_host_logic.py).
 static __constant__ uint8_t c_bayer[16] = {32, 255, 48, 208, 160, 96, 176, 112, 64, 224, 16, 240, 192, 128, 144, 80};
 
 // thresholds for 4 consecutive pixels starting at x % 4 == 0 on row y, packed like gray4's result
@@ -152,16 +165,18 @@ __host__ __device__ __forceinline__ int mirror_index(int i, int n)
 struct RowSource {
     const uint8_t *own, *top, *bottom;
     int y0, h, halo, full_h;
+    int lo, hi;  // rows [lo, hi) of the whole raster are readable: the band plus the halo rows that exist
     __device__ __forceinline__ const uint8_t *row(int gy, size_t pitch) const
     {
         gy = mirror_index(gy, full_h);
-        if (gy >= y0 && gy < y0 + h) return own + (size_t)(gy - y0) * pitch;
-        if (gy < y0) return top + (size_t)(gy - (y0 - halo)) * pitch;
-        return bottom + (size_t)(gy - (y0 + h)) * pitch;
+        return row_plain(gy, pitch);
     }
-    // the same without the mirror step, for row numbers that are already inside the raster
+    // the same without the mirror step, for row numbers that are already inside the raster.  Rows a strip or tile
+    // prefetches but never uses (a band whose height is no multiple of the strip height) are clamped to the readable
+    // range, so nothing outside [lo, hi) -- possibly a neighbour's HBM -- is ever touched.
     __device__ __forceinline__ const uint8_t *row_plain(int gy, size_t pitch) const
     {
+        gy = max(lo, min(gy, hi - 1));
         if (gy >= y0 && gy < y0 + h) return own + (size_t)(gy - y0) * pitch;
         if (gy < y0) return top + (size_t)(gy - (y0 - halo)) * pitch;
         return bottom + (size_t)(gy - (y0 + h)) * pitch;
@@ -178,6 +193,10 @@ static inline RowSource make_row_source(const uint8_t *src, uint32_t h, const Ba
     rs.h = (int)h;
     rs.halo = (int)band.halo;
     rs.full_h = band.full_h ? (int)band.full_h : (int)h;
+    rs.lo = band.top ? rs.y0 - rs.halo : rs.y0;
+    rs.hi = band.bottom ? rs.y0 + rs.h + rs.halo : rs.y0 + rs.h;
+    if (rs.lo < 0) rs.lo = 0;
+    if (rs.hi > rs.full_h) rs.hi = rs.full_h;
     return rs;
 }
 

@@ -442,11 +442,11 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
         else launch(conv3_strip_kernel<2, 4, 2, 128, true>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd);
         return PPMX_LAUNCHED();
     }
-    if (g_variant == 9) PPMX_CONV3_MODES(2, 1, 128);
-    else if (g_variant == 10) PPMX_CONV3_MODES(4, 2, 256);
-    else if (g_variant == 11) PPMX_CONV3_MODES(8, 2, 128);
-    else if (g_variant == 12) PPMX_CONV3_MODES(16, 1, 128);
-    else if (g_variant == 13) PPMX_CONV3_MODES(4, 2, 64);
+    if (PPMX_VARIANT == 9) PPMX_CONV3_MODES(2, 1, 128);
+    else if (PPMX_VARIANT == 10) PPMX_CONV3_MODES(4, 2, 256);
+    else if (PPMX_VARIANT == 11) PPMX_CONV3_MODES(8, 2, 128);
+    else if (PPMX_VARIANT == 12) PPMX_CONV3_MODES(16, 1, 128);
+    else if (PPMX_VARIANT == 13) PPMX_CONV3_MODES(4, 2, 64);
     else PPMX_CONV3_MODES(4, 2, 128);
 #undef PPMX_CONV3_MODES
 #undef PPMX_CONV3_LAUNCH
@@ -643,8 +643,8 @@ static cudaError_t conv_box(const RowSource &rs, uint8_t *dst, uint32_t w, uint3
         if (grid.y > 65535u) return cudaErrorInvalidValue;                                    \
         launch(conv_box_kernel<K, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, M, C);        \
     } while (0)
-    if (g_variant == 10) PPMX_BOX_LAUNCH(32);
-    else if (g_variant == 11) PPMX_BOX_LAUNCH(64);
+    if (PPMX_VARIANT == 10) PPMX_BOX_LAUNCH(32);
+    else if (PPMX_VARIANT == 11) PPMX_BOX_LAUNCH(64);
     else PPMX_BOX_LAUNCH(16);
 #undef PPMX_BOX_LAUNCH
     return PPMX_LAUNCHED();
@@ -849,8 +849,8 @@ static bool conv_sep(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, 
                      cudaStream_t s, cudaError_t *err)
 {
     // rows per strip, 7x7 / 5x5 binomial at 8192^2: 16 -> 0.46 / 0.53 of the HBM roofline, 32 -> 0.45 / 0.52, 64 -> 0.42 / 0.48
-    if (g_variant == 9) return conv_sep_rh<K, 8>(rs, dst, w, h, coef, rnd, s, err);
-    if (g_variant == 10) return conv_sep_rh<K, 32>(rs, dst, w, h, coef, rnd, s, err);
+    if (PPMX_VARIANT == 9) return conv_sep_rh<K, 8>(rs, dst, w, h, coef, rnd, s, err);
+    if (PPMX_VARIANT == 10) return conv_sep_rh<K, 32>(rs, dst, w, h, coef, rnd, s, err);
     return conv_sep_rh<K, 16>(rs, dst, w, h, coef, rnd, s, err);
 }
 
@@ -861,7 +861,7 @@ static cudaError_t conv_fast(const RowSource &rs, uint8_t *dst, uint32_t w, uint
     ConvCoefPacked<K> cf;
     int32_t u[K], v[K];
     // 3x3: the direct form measured faster (0.51 vs 0.49 of the HBM roofline); 5x5 and 7x7: separable wins
-    const bool sep = g_variant != 2 && K >= 5 && rank_one<K>(coef, u, v);
+    const bool sep = PPMX_VARIANT != 2 && K >= 5 && rank_one<K>(coef, u, v);
     for (int dy = 0; dy < K; dy++) {
         cf.u[dy] = sep ? u[dy] : 0;
         for (int j = 0; j < 4; j++)
@@ -961,9 +961,9 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
     }
     ConvRound rnd;
     const bool fast_layout = (w % 16u) == 0 && aligned16(src) && (!band.top || aligned16(band.top)) &&
-                             (!band.bottom || aligned16(band.bottom)) && g_variant != 1;
+                             (!band.bottom || aligned16(band.bottom)) && PPMX_VARIANT != 1;
     uint32_t bm, bc;
-    if (fast_layout && k >= 5 && k <= 11 && g_variant != 7 && aligned16(dst) && box_constants(coef, k, div, bias, &bm, &bc)) {
+    if (fast_layout && k >= 5 && k <= 11 && PPMX_VARIANT != 7 && aligned16(dst) && box_constants(coef, k, div, bias, &bm, &bc)) {
         // running sums: the cost does not depend on k (3R <= 15 halo columns come from one neighbouring lane)
         if (k == 5) return conv_box<5>(rs, dst, w, h, bm, bc, s);
         if (k == 7) return conv_box<7>(rs, dst, w, h, bm, bc, s);
@@ -971,12 +971,12 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         return conv_box<11>(rs, dst, w, h, bm, bc, s);
     }
     const bool rnd_ok = make_conv_round(sum_abs, div, bias, &rnd);
-    if (rnd_ok && fast_layout && (k == 5 || k == 7) && g_variant != 7 && g_variant != 2 && aligned16(dst)) {
+    if (rnd_ok && fast_layout && (k == 5 || k == 7) && PPMX_VARIANT != 7 && PPMX_VARIANT != 2 && aligned16(dst)) {
         // rank-1 (only the two factors must be small, not their products): sliding vertical words
         cudaError_t e = cudaSuccess;
         if (k == 5 ? conv_sep<5>(rs, dst, w, h, coef, rnd, s, &e) : conv_sep<7>(rs, dst, w, h, coef, rnd, s, &e)) return e;
     }
-    if (k == 3 && !s8 && rnd_ok && fast_layout && aligned16(dst) && g_variant != 7) {
+    if (k == 3 && !s8 && rnd_ok && fast_layout && aligned16(dst) && PPMX_VARIANT != 7) {
         // coefficients beyond a signed byte (up to +-16320): the strip kernel splits them into two dp4a chains
         bool splittable = true;
         for (int i = 0; i < 9; i++) splittable = splittable && coef[i] >= -16320 && coef[i] <= 16320;
@@ -984,14 +984,14 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
     }
     if (s8 && (k == 3 || k == 5 || k == 7) && fast_layout && aligned4(dst) && rnd_ok) {
         // variant 7 keeps the row-wise (planar dp4a) kernel for 3x3; the strip kernel is the default
-        if (k == 3 && g_variant != 7 && aligned16(dst)) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s);
+        if (k == 3 && PPMX_VARIANT != 7 && aligned16(dst)) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s);
         if (k == 3) return conv_fast<3>(rs, dst, w, h, coef, rnd, s);
         if (k == 5) return conv_fast<5>(rs, dst, w, h, coef, rnd, s);
         return conv_fast<7>(rs, dst, w, h, coef, rnd, s);
     }
     // a whole raster that only lacks the layout for the vector kernels goes through a padded copy (variant 1 = never)
-    const bool layout_only = ((w % 16u) != 0 || !aligned16(src) || !aligned16(dst)) && !band.full_h && g_variant != 1 &&
-                             g_variant != 7 && w >= 16 && (size_t)w * h >= 4096 &&
+    const bool layout_only = ((w % 16u) != 0 || !aligned16(src) || !aligned16(dst)) && !band.full_h && PPMX_VARIANT != 1 &&
+                             PPMX_VARIANT != 7 && w >= 16 && (size_t)w * h >= 4096 &&
                              (k <= 7 || (k <= 11 && box_constants(coef, k, div, bias, &bm, &bc)));  // a vector kernel exists
     if (layout_only) return conv_padded(src, dst, w, h, k, coef, div, bias, s);
     ConvCoefGeneric cf;

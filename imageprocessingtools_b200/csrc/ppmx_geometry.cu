@@ -142,7 +142,7 @@ cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int b
             size_t n = row / 4 * h;
             launch(flipv_kernel<uint32_t>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
                    reinterpret_cast<const uint32_t *>(src), reinterpret_cast<uint32_t *>(dst), (uint32_t)(row / 4), h, n);
-        } else if (h <= 65535u && g_variant != 1) {
+        } else if (h <= 65535u && PPMX_VARIANT != 1) {
             const unsigned gx = (unsigned)((row / 4 + 1 + 255) / 256);
             if (bpp == 3) launch(flip_rows_kernel<false, 3>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
             else launch(flip_rows_kernel<false, 1>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
@@ -155,7 +155,7 @@ cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int b
             size_t n = (size_t)(w / 16u) * h;
             launch(fliph_rgb16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
                    reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), w / 16u, n);
-        } else if (h <= 65535u && (bpp == 3 || bpp == 1) && g_variant != 1) {
+        } else if (h <= 65535u && (bpp == 3 || bpp == 1) && PPMX_VARIANT != 1) {
             const unsigned gx = (unsigned)((row / 4 + 1 + 255) / 256);
             if (bpp == 3) launch(flip_rows_kernel<true, 3>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
             else launch(flip_rows_kernel<true, 1>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
@@ -461,7 +461,7 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
             if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
             launch(fliph_rgb16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
                    reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), (uint32_t)n, n);
-        } else if (h <= 65535u && g_variant != 1) {  // any layout: mirrored rows taken from the mirrored row
+        } else if (h <= 65535u && PPMX_VARIANT != 1) {  // any layout: mirrored rows taken from the mirrored row
             const unsigned gx = (unsigned)(((size_t)w * 3 / 4 + 1 + 255) / 256);
             launch(flip_rows_kernel<true, 3, true>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
         } else {
@@ -470,28 +470,28 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
         return PPMX_LAUNCHED();
     }
     if (angle != 90 && angle != 270) return cudaErrorInvalidValue;
-    if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && (g_variant == 0 || g_variant == 9)) {
+    if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && (PPMX_VARIANT == 0 || PPMX_VARIANT == 9)) {
         dim3 grid((w + 63) / 64, (h + 63) / 64);
         if (grid.y > 65535u) return cudaErrorInvalidValue;
         if (angle == 90) launch(rotate_bulk64_kernel<true>, grid, dim3(128), 0, s, src, dst, w, h);
         else launch(rotate_bulk64_kernel<false>, grid, dim3(128), 0, s, src, dst, w, h);
         return PPMX_LAUNCHED();
     }
-    if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && g_variant != 1) {
+    if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && PPMX_VARIANT != 1) {
         // (numbering the CTAs down bands of 2..16 tile rows, for DRAM page locality on the write side,
         // measured 1-5 % SLOWER than this plain 2-D grid: the index arithmetic costs more than it gains)
         // two tiles per CTA at <= 40 registers (6 CTAs per SM) measured best: 0.725 / 0.828 of the HBM
         // roofline at 4096^2 / 16384^2; one tile per CTA (variant 6): 0.723 / 0.753
-        const int nt = (g_variant == 6) ? 1 : 2;
+        const int nt = (PPMX_VARIANT == 6) ? 1 : 2;
         dim3 g64((w + XT * nt - 1) / (XT * nt), (h + XT - 1) / XT);
         if (g64.y > 65535u) return cudaErrorInvalidValue;
-        if (g_variant == 6) {
+        if (PPMX_VARIANT == 6) {
             if (angle == 90) launch(rotate_transpose64_kernel<true, 1, 1, 0>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
             else launch(rotate_transpose64_kernel<false, 1, 1, 0>, dim3(g64), dim3(256), 0, s, src, dst, w, h);
-        } else if (g_variant == 7 || g_variant == 8) {
-            const unsigned band = g_variant == 7 ? 8u : 4u;
+        } else if (PPMX_VARIANT == 7 || PPMX_VARIANT == 8) {
+            const unsigned band = PPMX_VARIANT == 7 ? 8u : 4u;
             dim3 gb(g64.x * band, (g64.y + band - 1) / band);
-            if (g_variant == 7) {
+            if (PPMX_VARIANT == 7) {
                 if (angle == 90) launch(rotate_transpose64_kernel<true, 2, 6, 8>, gb, dim3(256), 0, s, src, dst, w, h);
                 else launch(rotate_transpose64_kernel<false, 2, 6, 8>, gb, dim3(256), 0, s, src, dst, w, h);
             } else {
@@ -504,7 +504,7 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
         }
         return PPMX_LAUNCHED();
     }
-    if (g_variant != 1) {
+    if (PPMX_VARIANT != 1) {
         dim3 ga((w + RA - 1) / RA, (h + RA - 1) / RA);
         if (ga.y > 65535u) return cudaErrorInvalidValue;
         if (angle == 90) launch(rotate_transpose_any_kernel<true>, ga, dim3(256), 0, s, src, dst, w, h);

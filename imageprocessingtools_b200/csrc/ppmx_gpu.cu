@@ -1,64 +1,33 @@
-// ppmx_gpu.cu -- implementation of the C ABI declared in include/ppmx_gpu.h.
-//
-// Owns: one CUDA device per context, a small set of streams ("lanes") with stream-ordered
-// device allocations, the buff/new_buff hand-over rules of the reference's op chain
-// (ref:1084-1155 = /root/reference/ppmx-edward.c), and the pinned upload/download path.
-// All arithmetic lives in ppmx_kernels.cu.  There is no CPU fallback anywhere in this file.
-#include "../../include/ppmx_gpu.h"
-#include "ppmx_kernels.h"
+// ppmx_gpu.cu -- the C ABI of include/ppmx_gpu.h: contexts, rasters in HBM, single operators, raw launches, CUDA
+// graphs and IPC.  The op chain (ref:1084-1155 = /root/reference/ppmx-edward.c), its row parts and the multi-device
+// split live in ppmx_chain.cu; all arithmetic lives in ppmx_{color,geometry,bicubic,conv}.cu.  There is no CPU
+// fallback anywhere in this library.
+#include "ppmx_ctx.h"
 
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
-#include <vector>
 
 using ppmx::Band;
+using ppmx::DeviceTables;
+using ppmx::fail;
+using ppmx::image_alloc_on;
+using ppmx::image_free_on;
+using ppmx::kLanes;
+using ppmx::launch_op;
+using ppmx::primary;
+using ppmx::upload_tables;
 
-#define PPMX_VERSION "ppmx-b200 0.1 (sm_100a)"
+#define PPMX_VERSION "ppmx-b200 0.2 (sm_100a)"
+#define CK PPMX_CK
 
-namespace {
-
-constexpr int kLanes = 3;  // upload / compute / download of consecutive rasters overlap
-
-// the reference reports failures with one printf line on stdout (CHECK_ERROR, ref:31-36)
-int fail(const char *what, cudaError_t e = cudaSuccess)
+int ppmx::fail(const char *what, cudaError_t e)
 {
     if (e != cudaSuccess) printf("ppmx_gpu error: %s: %s\n", what, cudaGetErrorString(e));
     else printf("ppmx_gpu error: %s\n", what);
     fflush(stdout);
     return PPMX_ERROR;
 }
-
-#define CK(call, what)                                         \
-    do {                                                       \
-        cudaError_t e__ = (call);                              \
-        if (e__ != cudaSuccess) return fail(what, e__);        \
-    } while (0)
-
-struct DeviceTables {  // imresize tables of one op, resident in HBM
-    double *weights = nullptr;
-    int *indices = nullptr;
-    void *base = nullptr;
-};
-
-}  // namespace
-
-struct ppmx_gpu_image {
-    uint8_t *d = nullptr;
-    uint32_t w = 0, h = 0;
-    int layout = PPMX_LAYOUT_RGB8;
-    size_t bytes = 0;
-    int lane = 0;
-};
-
-struct ppmx_gpu_ctx {
-    int device = 0;
-    cudaStream_t lane[kLanes] = {};
-    cudaEvent_t tables_ready = nullptr;
-    unsigned long long *d_hist = nullptr;   // 256 bins
-    unsigned long long *h_hist = nullptr;   // pinned copy
-};
 
 extern "C" size_t ppmx_gpu_layout_bytes(uint32_t w, uint32_t h, int layout)
 {
@@ -72,23 +41,35 @@ extern "C" size_t ppmx_gpu_layout_bytes(uint32_t w, uint32_t h, int layout)
 
 extern "C" int ppmx_gpu_set_tuning(const char *key, int value)
 {
-    if (key && !strcmp(key, "variant")) ppmx::g_variant = value;
-    else if (key && !strcmp(key, "pdl")) ppmx::g_pdl = value ? 1 : 0;
+    if (key && !strcmp(key, "variant")) {
+#ifdef PPMX_TUNING
+        ppmx::g_variant = value;
+#else
+        // the release library carries the default (best measured) kernels only; the alternative implementations
+        // live in libppmx_gpu_tuning.so (same sources, -DPPMX_TUNING), which tools/sweep.py and the variant tests load
+        if (value != 0) return PPMX_ERROR;
+#endif
+    } else if (key && !strcmp(key, "pdl")) ppmx::g_pdl.store(value ? 1 : 0);
     else return PPMX_ERROR;
     return PPMX_OK;
 }
 
-extern "C" const char *ppmx_gpu_version(void) { return PPMX_VERSION; }
+extern "C" const char *ppmx_gpu_version(void)
+{
+#ifdef PPMX_TUNING
+    return PPMX_VERSION " tuning";
+#else
+    return PPMX_VERSION;
+#endif
+}
 extern "C" uint64_t ppmx_gpu_launch_count(void) { return ppmx::launch_count(); }
 
 // ---------------------------------------------------------------------------------------------
 // lifetime
 // ---------------------------------------------------------------------------------------------
 
-extern "C" int ppmx_gpu_init(ppmx_gpu_ctx **out, int device)
+static int init_one(ppmx_gpu_ctx *c, int device)
 {
-    if (!out) return fail("ppmx_gpu_init: null ctx pointer");
-    *out = nullptr;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) return fail("no CUDA device (this library has no CPU fallback)", e);
@@ -97,47 +78,99 @@ extern "C" int ppmx_gpu_init(ppmx_gpu_ctx **out, int device)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
     if (prop.major != 10) return fail("this build carries sm_100a code only and needs a B200-class device");
-
-    ppmx_gpu_ctx *c = new (std::nothrow) ppmx_gpu_ctx();
-    if (!c) return fail("out of host memory");
     c->device = device;
-    for (int i = 0; i < kLanes; i++) CK(cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int i = 0; i < kLanes; i++) {
+        CK(cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking), "cudaStreamCreate");
+        CK(cudaEventCreateWithFlags(&c->lane_done[i], cudaEventDisableTiming), "cudaEventCreate");
+    }
     CK(cudaEventCreateWithFlags(&c->tables_ready, cudaEventDisableTiming), "cudaEventCreate");
     CK(cudaMalloc(&c->d_hist, 256 * sizeof(unsigned long long)), "cudaMalloc hist");
-    CK(cudaMallocHost(&c->h_hist, 256 * sizeof(unsigned long long)), "cudaMallocHost hist");
-    // keep freed rasters cached in the stream-ordered pool instead of returning them to the driver
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    CK(cudaHostAlloc(&c->h_hist, 256 * sizeof(unsigned long long), cudaHostAllocPortable), "cudaHostAlloc hist");
+    // a pool of the context's own (freed rasters stay cached in it; the device's default pool is left alone)
+    cudaMemPoolProps pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    CK(cudaMemPoolCreate(&c->pool, &pp), "cudaMemPoolCreate");
+    unsigned long long keep = ~0ull;
+    CK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep), "cudaMemPoolSetAttribute");
+    return PPMX_OK;
+}
+
+extern "C" int ppmx_gpu_init(ppmx_gpu_ctx **out, int device)
+{
+    if (!out) return fail("ppmx_gpu_init: null ctx pointer");
+    *out = nullptr;
+    ppmx_gpu_ctx *c = new (std::nothrow) ppmx_gpu_ctx();
+    if (!c) return fail("out of host memory");
+    if (init_one(c, device) != PPMX_OK) {
+        ppmx_gpu_free(c);  // whatever was created so far
+        return PPMX_ERROR;
     }
     *out = c;
     return PPMX_OK;
 }
 
+extern "C" int ppmx_gpu_init_multi(ppmx_gpu_ctx **out, const int *devices, int ndev)
+{
+    if (!out) return fail("ppmx_gpu_init_multi: null ctx pointer");
+    *out = nullptr;
+    if (ndev < 0 || ndev > 64 || (ndev > 0 && !devices)) return fail("ppmx_gpu_init_multi: bad device list");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return fail("no CUDA device (this library has no CPU fallback)", e);
+    if (ndev == 0) ndev = n;  // every visible device
+    ppmx_gpu_ctx *m = new (std::nothrow) ppmx_gpu_ctx();
+    if (!m) return fail("out of host memory");
+    for (int i = 0; i < ndev; i++) {
+        ppmx_gpu_ctx *c = nullptr;
+        if (ppmx_gpu_init(&c, devices ? devices[i] : i) != PPMX_OK) {
+            ppmx_gpu_free(m);
+            return PPMX_ERROR;
+        }
+        m->children.push_back(c);
+    }
+    m->device = m->children[0]->device;
+    *out = m;
+    return PPMX_OK;
+}
+
+extern "C" int ppmx_gpu_device_count(const ppmx_gpu_ctx *c)
+{
+    if (!c) return 0;
+    return c->children.empty() ? 1 : (int)c->children.size();
+}
+
 extern "C" void ppmx_gpu_free(ppmx_gpu_ctx *c)
 {
     if (!c) return;
-    cudaSetDevice(c->device);
-    for (int i = 0; i < kLanes; i++)
-        if (c->lane[i]) {
-            cudaStreamSynchronize(c->lane[i]);
-            cudaStreamDestroy(c->lane[i]);
+    for (ppmx_gpu_ctx *k : c->children) ppmx_gpu_free(k);
+    if (c->children.empty()) {
+        cudaSetDevice(c->device);
+        for (int i = 0; i < kLanes; i++) {
+            if (c->lane[i]) {
+                cudaStreamSynchronize(c->lane[i]);
+                cudaStreamDestroy(c->lane[i]);
+            }
+            if (c->lane_done[i]) cudaEventDestroy(c->lane_done[i]);
         }
-    if (c->tables_ready) cudaEventDestroy(c->tables_ready);
-    cudaMemPool_t pool;  // hand the cached rasters back to the driver
-    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    if (c->d_hist) cudaFree(c->d_hist);
-    if (c->h_hist) cudaFreeHost(c->h_hist);
+        if (c->tables_ready) cudaEventDestroy(c->tables_ready);
+        if (c->pool) cudaMemPoolDestroy(c->pool);  // hands the cached rasters back to the driver
+        if (c->d_hist) cudaFree(c->d_hist);
+        if (c->h_hist) cudaFreeHost(c->h_hist);
+    }
     delete c;
 }
 
 extern "C" void *ppmx_gpu_host_alloc(ppmx_gpu_ctx *c, size_t bytes)
 {
     void *p = nullptr;
-    if (c) cudaSetDevice(c->device);
-    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
-        fail("cudaMallocHost");
+    if (c) cudaSetDevice(primary(c)->device);
+    // portable: a multi-device context copies to and from the same host raster on every device
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        fail("cudaHostAlloc");
         return nullptr;
     }
     return p;
@@ -149,9 +182,31 @@ extern "C" void ppmx_gpu_host_free(ppmx_gpu_ctx *c, void *p)
     if (p) cudaFreeHost(p);
 }
 
+extern "C" int ppmx_gpu_host_register(ppmx_gpu_ctx *c, void *p, size_t bytes)
+{
+    if (!p || !bytes) return fail("ppmx_gpu_host_register: null argument");
+    if (c) cudaSetDevice(primary(c)->device);
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable), "cudaHostRegister");
+    return PPMX_OK;
+}
+
+extern "C" int ppmx_gpu_host_unregister(ppmx_gpu_ctx *c, void *p)
+{
+    (void)c;
+    if (!p) return fail("ppmx_gpu_host_unregister: null argument");
+    CK(cudaHostUnregister(p), "cudaHostUnregister");
+    return PPMX_OK;
+}
+
 extern "C" int ppmx_gpu_sync(ppmx_gpu_ctx *c)
 {
     if (!c) return fail("null ctx");
+    if (!c->children.empty()) {
+        for (ppmx_gpu_ctx *k : c->children)
+            if (ppmx_gpu_sync(k) != PPMX_OK) return PPMX_ERROR;
+        return PPMX_OK;
+    }
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
     for (int i = 0; i < kLanes; i++) CK(cudaStreamSynchronize(c->lane[i]), "cudaStreamSynchronize");
     return PPMX_OK;
 }
@@ -160,7 +215,12 @@ extern "C" int ppmx_gpu_sync(ppmx_gpu_ctx *c)
 // rasters in HBM
 // ---------------------------------------------------------------------------------------------
 
-static int image_alloc_on(ppmx_gpu_ctx *c, int lane, uint32_t w, uint32_t h, int layout, ppmx_gpu_image **out)
+cudaError_t ppmx::pool_alloc(ppmx_gpu_ctx *c, void **p, size_t bytes, cudaStream_t s)
+{
+    return cudaMallocFromPoolAsync(p, bytes ? bytes : 16, c->pool, s);
+}
+
+int ppmx::image_alloc_on(ppmx_gpu_ctx *c, int lane, uint32_t w, uint32_t h, int layout, ppmx_gpu_image **out)
 {
     size_t bytes = ppmx_gpu_layout_bytes(w, h, layout);
     ppmx_gpu_image *im = new (std::nothrow) ppmx_gpu_image();
@@ -171,7 +231,7 @@ static int image_alloc_on(ppmx_gpu_ctx *c, int lane, uint32_t w, uint32_t h, int
     im->bytes = bytes;
     im->lane = lane;
     // +16: vector kernels never read past `bytes`, the slack only keeps zero-sized rasters valid
-    cudaError_t e = cudaMallocAsync((void **)&im->d, bytes + 16, c->lane[lane]);
+    cudaError_t e = pool_alloc(c, (void **)&im->d, bytes + 16, c->lane[lane]);
     if (e != cudaSuccess) {
         delete im;
         return fail("can not allocate image buff in HBM", e);  // wording of ref:926
@@ -180,7 +240,7 @@ static int image_alloc_on(ppmx_gpu_ctx *c, int lane, uint32_t w, uint32_t h, int
     return PPMX_OK;
 }
 
-static void image_free_on(ppmx_gpu_ctx *c, ppmx_gpu_image *im)
+void ppmx::image_free_on(ppmx_gpu_ctx *c, ppmx_gpu_image *im)
 {
     if (!im) return;
     if (im->d) cudaFreeAsync(im->d, c->lane[im->lane]);
@@ -190,6 +250,7 @@ static void image_free_on(ppmx_gpu_ctx *c, ppmx_gpu_image *im)
 extern "C" int ppmx_gpu_image_alloc(ppmx_gpu_ctx *c, uint32_t w, uint32_t h, int layout, ppmx_gpu_image **img)
 {
     if (!c || !img) return fail("ppmx_gpu_image_alloc: null argument");
+    c = primary(c);
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     return image_alloc_on(c, 0, w, h, layout, img);
 }
@@ -197,6 +258,7 @@ extern "C" int ppmx_gpu_image_alloc(ppmx_gpu_ctx *c, uint32_t w, uint32_t h, int
 extern "C" void ppmx_gpu_image_free(ppmx_gpu_ctx *c, ppmx_gpu_image *img)
 {
     if (!c) return;
+    c = primary(c);
     cudaSetDevice(c->device);
     image_free_on(c, img);
 }
@@ -213,20 +275,24 @@ extern "C" int ppmx_gpu_image_info(const ppmx_gpu_image *img, uint32_t *w, uint3
     return PPMX_OK;
 }
 
-static int upload_on(ppmx_gpu_ctx *c, int lane, const uint8_t *src, uint32_t w, uint32_t h, int layout,
-                     ppmx_gpu_image **img)
-{
-    if (image_alloc_on(c, lane, w, h, layout, img) != PPMX_OK) return PPMX_ERROR;
-    if ((*img)->bytes) CK(cudaMemcpyAsync((*img)->d, src, (*img)->bytes, cudaMemcpyHostToDevice, c->lane[lane]), "upload");
-    return PPMX_OK;
-}
-
 extern "C" int ppmx_gpu_upload(ppmx_gpu_ctx *c, const uint8_t *src, uint32_t w, uint32_t h, int layout,
                                ppmx_gpu_image **img)
 {
     if (!c || !img || (!src && w && h)) return fail("ppmx_gpu_upload: null argument");
+    c = primary(c);
     CK(cudaSetDevice(c->device), "cudaSetDevice");
-    return upload_on(c, 0, src, w, h, layout, img);
+    *img = nullptr;
+    ppmx_gpu_image *im = nullptr;
+    if (image_alloc_on(c, 0, w, h, layout, &im) != PPMX_OK) return PPMX_ERROR;
+    if (im->bytes) {
+        cudaError_t e = cudaMemcpyAsync(im->d, src, im->bytes, cudaMemcpyHostToDevice, c->lane[0]);
+        if (e != cudaSuccess) {
+            image_free_on(c, im);
+            return fail("upload", e);
+        }
+    }
+    *img = im;
+    return PPMX_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -289,22 +355,28 @@ extern "C" int ppmx_gpu_op_output(const ppmx_op *op, uint32_t w, uint32_t h, int
     return PPMX_OK;
 }
 
-static int upload_tables(const ppmx_op *op, DeviceTables *t, cudaStream_t s, bool async_pool)
+int ppmx::upload_tables(ppmx_gpu_ctx *c, const ppmx_op *op, DeviceTables *t, cudaStream_t s)
 {
     if (op->out_size < 1 || op->weights_sz < 1 || !op->weights || !op->indices) return fail("imresize: bad tables");
     size_t n = (size_t)op->out_size * op->weights_sz;
     size_t wbytes = n * sizeof(double), ibytes = n * sizeof(int);
-    if (async_pool) CK(cudaMallocAsync(&t->base, wbytes + ibytes, s), "cudaMallocAsync tables");
+    if (c) CK(pool_alloc(c, &t->base, wbytes + ibytes, s), "pool alloc (tables)");
     else CK(cudaMalloc(&t->base, wbytes + ibytes), "cudaMalloc tables");
     t->weights = (double *)t->base;
     t->indices = (int *)((uint8_t *)t->base + wbytes);
-    CK(cudaMemcpyAsync(t->weights, op->weights, wbytes, cudaMemcpyHostToDevice, s), "upload weights");
-    CK(cudaMemcpyAsync(t->indices, op->indices, ibytes, cudaMemcpyHostToDevice, s), "upload indices");
+    cudaError_t e = cudaMemcpyAsync(t->weights, op->weights, wbytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->indices, op->indices, ibytes, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+        if (c) cudaFreeAsync(t->base, s);
+        else cudaFree(t->base);
+        *t = DeviceTables();
+        return fail("upload tables", e);
+    }
     return PPMX_OK;
 }
 
 // launches the kernel(s) of one operator on raw device pointers
-static int launch_op(const ppmx_op *op, const uint8_t *d_src, uint32_t w, uint32_t h, int layout, uint8_t *d_dst,
+int ppmx::launch_op(const ppmx_op *op, const uint8_t *d_src, uint32_t w, uint32_t h, int layout, uint8_t *d_dst,
                      const Band &band, unsigned long long *d_hist, const DeviceTables *tables, cudaStream_t s)
 {
     const size_t npix = (size_t)w * h;
@@ -365,7 +437,7 @@ static int launch_op(const ppmx_op *op, const uint8_t *d_src, uint32_t w, uint32
 }
 
 static int op_on(ppmx_gpu_ctx *c, int lane, const ppmx_op *op, const ppmx_gpu_image *src, ppmx_gpu_image **dst,
-                 const DeviceTables *shared_tables, unsigned long long *d_hist)
+                 unsigned long long *d_hist)
 {
     uint32_t ow, oh;
     int ol;
@@ -376,17 +448,13 @@ static int op_on(ppmx_gpu_ctx *c, int lane, const ppmx_op *op, const ppmx_gpu_im
     if (op->kind != PPMX_OP_HIST_GRAY && image_alloc_on(c, lane, ow, oh, ol, &out) != PPMX_OK) return PPMX_ERROR;
 
     DeviceTables local;
-    const DeviceTables *tables = shared_tables;
-    if (op->kind == PPMX_OP_IMRESIZE && !tables) {
-        if (upload_tables(op, &local, s, true) != PPMX_OK) {
-            image_free_on(c, out);
-            return PPMX_ERROR;
-        }
-        tables = &local;
-    }
-    if (d_hist) CK(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), s), "clear hist");
+    int rc = PPMX_OK;
+    if (op->kind == PPMX_OP_IMRESIZE) rc = upload_tables(c, op, &local, s);
+    if (rc == PPMX_OK && d_hist && cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), s) != cudaSuccess)
+        rc = fail("clear hist");
     // rotate's uncovered pixels are written as 0 by the kernel itself (ref:727); no memset needed
-    int rc = launch_op(op, src->d, src->w, src->h, src->layout, out ? out->d : nullptr, Band(), d_hist, tables, s);
+    if (rc == PPMX_OK)
+        rc = launch_op(op, src->d, src->w, src->h, src->layout, out ? out->d : nullptr, Band(), d_hist, &local, s);
     if (local.base) cudaFreeAsync(local.base, s);
     if (rc != PPMX_OK) {
         image_free_on(c, out);
@@ -400,16 +468,22 @@ extern "C" int ppmx_gpu_op(ppmx_gpu_ctx *c, const ppmx_op *op, const ppmx_gpu_im
                            uint64_t *hist_out)
 {
     if (!c || !op || !src || !dst) return fail("ppmx_gpu_op: null argument");
+    c = primary(c);
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     *dst = nullptr;
     const bool hist = (op->kind == PPMX_OP_HIST_GRAY || op->kind == PPMX_OP_GRAY_HIST);
     if (hist && !hist_out) return fail("histogram operator needs hist_out");
-    int rc = op_on(c, src->lane, op, src, dst, nullptr, hist ? c->d_hist : nullptr);
+    int rc = op_on(c, src->lane, op, src, dst, hist ? c->d_hist : nullptr);
     if (rc != PPMX_OK) return rc;
     if (hist) {
         cudaStream_t s = c->lane[src->lane];
-        CK(cudaMemcpyAsync(c->h_hist, c->d_hist, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s), "hist D2H");
-        CK(cudaStreamSynchronize(s), "sync");
+        cudaError_t e = cudaMemcpyAsync(c->h_hist, c->d_hist, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            image_free_on(c, *dst);
+            *dst = nullptr;
+            return fail("hist D2H", e);
+        }
         for (int i = 0; i < 256; i++) hist_out[i] = c->h_hist[i];
     }
     return PPMX_OK;
@@ -435,7 +509,7 @@ static int download_on(ppmx_gpu_ctx *c, int lane, const ppmx_gpu_image *img, int
         cv.kind = -1;
     }
     if (cv.kind >= 0) {
-        if (op_on(c, lane, &cv, img, tmp, nullptr, nullptr) != PPMX_OK) return PPMX_ERROR;
+        if (op_on(c, lane, &cv, img, tmp, nullptr) != PPMX_OK) return PPMX_ERROR;
         from = *tmp;
     }
     if (from->bytes > cap) return fail("destination buffer too small");
@@ -448,193 +522,15 @@ extern "C" int ppmx_gpu_download(ppmx_gpu_ctx *c, const ppmx_gpu_image *img, int
                                  size_t *nbytes)
 {
     if (!c || !img || (!dst && cap)) return fail("ppmx_gpu_download: null argument");
+    c = primary(c);
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     ppmx_gpu_image *tmp = nullptr;
     int rc = download_on(c, img->lane, img, file_type, dst, cap, nbytes, &tmp);
     image_free_on(c, tmp);
+    cudaError_t e = cudaStreamSynchronize(c->lane[img->lane]);  // also after a failure: nothing may still write to dst
     if (rc != PPMX_OK) return rc;
-    CK(cudaStreamSynchronize(c->lane[img->lane]), "sync");
+    if (e != cudaSuccess) return fail("sync", e);
     return PPMX_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// the op chain (ref:1084-1155): buff / new_buff hand-over, then the writer's raster (ref:263-291)
-// ---------------------------------------------------------------------------------------------
-
-struct Chain {
-    ppmx_gpu_ctx *c;
-    int lane;
-    ppmx_gpu_image *buff = nullptr, *newb = nullptr;  // newb may alias buff (flip, rotate 0)
-    int file_type = PPMX_FILETYPE_PPM;
-    int index = 0;  // position of this raster in a batch
-
-    void drop_new()
-    {  // the reference leaks a superseded new_buff; here it goes back to the pool
-        if (newb && newb != buff) image_free_on(c, newb);
-        newb = nullptr;
-    }
-    void renew()
-    {  // renewBuffer, ref:1019-1026
-        if (!newb) return;
-        if (newb != buff) image_free_on(c, buff);
-        buff = newb;
-        newb = nullptr;
-    }
-    void release()
-    {
-        if (newb && newb != buff) image_free_on(c, newb);
-        image_free_on(c, buff);
-        buff = newb = nullptr;
-    }
-};
-
-static int run_chain(Chain &ch, const ppmx_op *ops, int nops, const std::vector<DeviceTables> &tables)
-{
-    ppmx_gpu_ctx *c = ch.c;
-    for (int i = 0; i < nops; i++) {
-        ppmx_op op = ops[i];
-        if (op.renew_before) ch.renew();
-        ppmx_gpu_image *out = nullptr;
-        const DeviceTables *t = (op.kind == PPMX_OP_IMRESIZE) ? &tables[i] : nullptr;
-        switch (op.kind) {
-        case PPMX_OP_MONO:
-            // a bilevel result nothing else touches goes straight to packed bits (mono + ref:268-284)
-            if (i == nops - 1) op.kind = PPMX_OP_MONO_BITS;
-            /* fall through */
-        case PPMX_OP_GRAY:
-            if (op_on(c, ch.lane, &op, ch.buff, &out, nullptr, nullptr) != PPMX_OK) return PPMX_ERROR;
-            ch.drop_new();
-            ch.newb = out;
-            ch.file_type = (op.kind == PPMX_OP_GRAY) ? PPMX_FILETYPE_PGM : PPMX_FILETYPE_PBM;  // ref:991, 956
-            break;
-        case PPMX_OP_GRAY_HIST: {  // extension: gray (ref:998-1000) + its 256-bin histogram in one pass
-            if (!op.hist_out) return fail("gray+hist in a chain needs op.hist_out");
-            unsigned long long *dh = nullptr;
-            cudaStream_t s = c->lane[ch.lane];
-            CK(cudaMallocAsync((void **)&dh, 256 * sizeof(unsigned long long), s), "cudaMallocAsync hist");
-            int rc = op_on(c, ch.lane, &op, ch.buff, &out, nullptr, dh);
-            if (rc == PPMX_OK)
-                rc = cudaMemcpyAsync(op.hist_out + 256 * (size_t)ch.index, dh, 256 * sizeof(unsigned long long),
-                                     cudaMemcpyDeviceToHost, s) == cudaSuccess ? PPMX_OK : fail("hist D2H");
-            cudaFreeAsync(dh, s);
-            if (rc != PPMX_OK) return rc;
-            ch.drop_new();
-            ch.newb = out;
-            ch.file_type = PPMX_FILETYPE_PGM;
-            break;
-        }
-        case PPMX_OP_FLIP:
-            // ref:896: works on buff itself and aliases new_buff to it
-            if (op_on(c, ch.lane, &op, ch.buff, &out, nullptr, nullptr) != PPMX_OK) return PPMX_ERROR;
-            ch.drop_new();
-            image_free_on(c, ch.buff);
-            ch.buff = ch.newb = out;
-            break;
-        case PPMX_OP_ROTATE:
-            if (op.angle_deg == 0) {  // ref:701-705
-                ch.drop_new();
-                ch.newb = ch.buff;
-                break;
-            }
-            /* fall through */
-        case PPMX_OP_IMRESIZE:
-        case PPMX_OP_CONV:
-        case PPMX_OP_LEVELS:
-            if (op_on(c, ch.lane, &op, ch.buff, &out, t, nullptr) != PPMX_OK) return PPMX_ERROR;
-            ch.drop_new();
-            ch.newb = out;
-            break;
-        default:
-            return fail("operator not allowed in a chain");
-        }
-    }
-    if (!ch.newb) return fail("Error: no data to write");  // ref:235
-    return PPMX_OK;
-}
-
-static int prepare_tables(ppmx_gpu_ctx *c, const ppmx_op *ops, int nops, std::vector<DeviceTables> &tables)
-{
-    tables.assign(nops, DeviceTables());
-    bool any = false;
-    for (int i = 0; i < nops; i++)
-        if (ops[i].kind == PPMX_OP_IMRESIZE) {
-            if (upload_tables(&ops[i], &tables[i], c->lane[0], true) != PPMX_OK) return PPMX_ERROR;
-            any = true;
-        }
-    if (any) {
-        CK(cudaEventRecord(c->tables_ready, c->lane[0]), "event record");
-        for (int l = 1; l < kLanes; l++) CK(cudaStreamWaitEvent(c->lane[l], c->tables_ready, 0), "event wait");
-    }
-    return PPMX_OK;
-}
-
-static void release_tables(ppmx_gpu_ctx *c, std::vector<DeviceTables> &tables)
-{
-    // every lane has been synchronised by the caller
-    for (auto &t : tables)
-        if (t.base) cudaFreeAsync(t.base, c->lane[0]);
-    tables.clear();
-}
-
-extern "C" int ppmx_gpu_apply_batch(ppmx_gpu_ctx *c, const ppmx_op *ops, int nops, const uint8_t *src, uint32_t w,
-                                    uint32_t h, int count, uint8_t *dst, size_t dst_stride, size_t *dst_bytes_each,
-                                    uint32_t *out_w, uint32_t *out_h, int *out_file_type)
-{
-    if (!c || !ops || nops < 1 || !src || !dst || count < 1) return fail("ppmx_gpu_apply: bad argument");
-    CK(cudaSetDevice(c->device), "cudaSetDevice");
-    std::vector<DeviceTables> tables;
-    if (prepare_tables(c, ops, nops, tables) != PPMX_OK) return PPMX_ERROR;
-
-    const size_t in_bytes = (size_t)w * h * 3;
-    int rc = PPMX_OK;
-    size_t each = 0;
-    uint32_t ow = 0, oh = 0;
-    int ft = PPMX_FILETYPE_PPM;
-    // at most kInFlight rasters per lane are enqueued ahead of the GPU, so the stream-ordered pool
-    // holds a bounded number of rasters however long the batch is
-    constexpr int kInFlight = 4;
-    cudaEvent_t done[kLanes][kInFlight] = {};
-    for (int i = 0; i < count && rc == PPMX_OK; i++) {
-        Chain ch;
-        ch.c = c;
-        ch.lane = i % kLanes;
-        ch.index = i;
-        const int slot = (i / kLanes) % kInFlight;
-        if (done[ch.lane][slot]) CK(cudaEventSynchronize(done[ch.lane][slot]), "event sync");
-        else CK(cudaEventCreateWithFlags(&done[ch.lane][slot], cudaEventDisableTiming), "event create");
-        rc = upload_on(c, ch.lane, src + (size_t)i * in_bytes, w, h, PPMX_LAYOUT_RGB8, &ch.buff);
-        if (rc == PPMX_OK) rc = run_chain(ch, ops, nops, tables);
-        if (rc == PPMX_OK) {
-            ppmx_gpu_image *tmp = nullptr;
-            rc = download_on(c, ch.lane, ch.newb, ch.file_type, dst + (size_t)i * dst_stride, dst_stride, &each, &tmp);
-            image_free_on(c, tmp);
-            ow = ch.newb->w;
-            oh = ch.newb->h;
-            ft = ch.file_type;
-        }
-        ch.release();
-        cudaEventRecord(done[ch.lane][slot], c->lane[ch.lane]);
-    }
-    for (int l = 0; l < kLanes; l++) {
-        cudaError_t e = cudaStreamSynchronize(c->lane[l]);
-        if (e != cudaSuccess && rc == PPMX_OK) rc = fail("stream sync", e);
-        for (int k = 0; k < kInFlight; k++)
-            if (done[l][k]) cudaEventDestroy(done[l][k]);
-    }
-    release_tables(c, tables);
-    if (rc != PPMX_OK) return rc;
-    if (dst_bytes_each) *dst_bytes_each = each;
-    if (out_w) *out_w = ow;
-    if (out_h) *out_h = oh;
-    if (out_file_type) *out_file_type = ft;
-    return PPMX_OK;
-}
-
-extern "C" int ppmx_gpu_apply(ppmx_gpu_ctx *c, const ppmx_op *ops, int nops, const uint8_t *src, uint32_t w, uint32_t h,
-                              uint8_t *dst, size_t dst_cap, size_t *dst_bytes, uint32_t *out_w, uint32_t *out_h,
-                              int *out_file_type)
-{
-    return ppmx_gpu_apply_batch(c, ops, nops, src, w, h, 1, dst, dst_cap, dst_bytes, out_w, out_h, out_file_type);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -645,8 +541,12 @@ extern "C" int ppmx_gpu_tables_upload(const ppmx_op *op, void **d_tables)
 {
     if (!op || !d_tables) return fail("ppmx_gpu_tables_upload: null argument");
     DeviceTables t;
-    if (upload_tables(op, &t, 0, false) != PPMX_OK) return PPMX_ERROR;
-    CK(cudaStreamSynchronize(0), "sync");
+    if (upload_tables(nullptr, op, &t, 0) != PPMX_OK) return PPMX_ERROR;
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) {
+        cudaFree(t.base);
+        return fail("sync", e);
+    }
     *d_tables = t.base;
     return PPMX_OK;
 }
@@ -683,26 +583,90 @@ extern "C" int ppmx_gpu_launch(const ppmx_op *op, const void *d_src, uint32_t w,
 }
 
 // ---------------------------------------------------------------------------------------------
+// CUDA graphs: a sequence of ppmx_gpu_launch calls (they only enqueue kernels) recorded once and replayed with ONE
+// driver call per step, so the host's launch cost is off the device's critical path
+// ---------------------------------------------------------------------------------------------
+
+struct ppmx_gpu_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long kernels = 0;
+};
+
+extern "C" int ppmx_gpu_graph_begin(void *stream)
+{
+    CK(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+    return PPMX_OK;
+}
+
+extern "C" int ppmx_gpu_graph_end(void *stream, ppmx_gpu_graph **out, uint64_t *kernel_nodes)
+{
+    if (!out) return fail("ppmx_gpu_graph_end: null argument");
+    *out = nullptr;
+    ppmx_gpu_graph *g = new (std::nothrow) ppmx_gpu_graph();
+    if (!g) return fail("out of host memory");
+    cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &g->graph);
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e == cudaSuccess) {
+        size_t n = 0;
+        e = cudaGraphGetNodes(g->graph, nullptr, &n);
+        if (e == cudaSuccess && n) {
+            std::vector<cudaGraphNode_t> nodes(n);
+            e = cudaGraphGetNodes(g->graph, nodes.data(), &n);
+            for (size_t i = 0; e == cudaSuccess && i < n; i++) {
+                cudaGraphNodeType t;
+                e = cudaGraphNodeGetType(nodes[i], &t);
+                if (e == cudaSuccess && t == cudaGraphNodeTypeKernel) g->kernels++;
+            }
+        }
+    }
+    if (e != cudaSuccess) {
+        ppmx_gpu_graph_free(g);
+        return fail("graph capture", e);
+    }
+    if (kernel_nodes) *kernel_nodes = g->kernels;
+    *out = g;
+    return PPMX_OK;
+}
+
+extern "C" int ppmx_gpu_graph_launch(ppmx_gpu_graph *g, void *stream)
+{
+    if (!g || !g->exec) return fail("ppmx_gpu_graph_launch: null graph");
+    CK(cudaGraphLaunch(g->exec, (cudaStream_t)stream), "cudaGraphLaunch");
+    ppmx::add_launches(g->kernels);
+    return PPMX_OK;
+}
+
+extern "C" void ppmx_gpu_graph_free(ppmx_gpu_graph *g)
+{
+    if (!g) return;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+}
+
+// ---------------------------------------------------------------------------------------------
 // multi-GPU: CUDA IPC so that one process per GPU can read a neighbour's band over NVLink
 // ---------------------------------------------------------------------------------------------
 
 extern "C" int ppmx_gpu_device_alloc(ppmx_gpu_ctx *c, size_t bytes, void **device_ptr)
 {
     if (!c || !device_ptr) return fail("ppmx_gpu_device_alloc: null argument");
-    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    CK(cudaSetDevice(primary(c)->device), "cudaSetDevice");
     CK(cudaMalloc(device_ptr, bytes ? bytes : 16), "cudaMalloc");  // plain cudaMalloc: IPC-exportable
     return PPMX_OK;
 }
 
 extern "C" void ppmx_gpu_device_free(ppmx_gpu_ctx *c, void *device_ptr)
 {
-    if (c) cudaSetDevice(c->device);
+    if (c) cudaSetDevice(primary(c)->device);
     if (device_ptr) cudaFree(device_ptr);
 }
 
 extern "C" int ppmx_gpu_copy(ppmx_gpu_ctx *c, void *dst, const void *src, size_t bytes, int kind)
 {
     if (!c || (bytes && (!dst || !src))) return fail("ppmx_gpu_copy: null argument");
+    c = primary(c);
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, k, c->lane[0]), "cudaMemcpyAsync");
@@ -714,7 +678,7 @@ extern "C" int ppmx_gpu_ipc_export(ppmx_gpu_ctx *c, const void *device_ptr, uint
 {
     if (!c || !device_ptr || !handle) return fail("ppmx_gpu_ipc_export: null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    CK(cudaSetDevice(primary(c)->device), "cudaSetDevice");
     cudaIpcMemHandle_t hd;
     CK(cudaIpcGetMemHandle(&hd, const_cast<void *>(device_ptr)), "cudaIpcGetMemHandle");
     memcpy(handle, &hd, 64);
@@ -724,7 +688,7 @@ extern "C" int ppmx_gpu_ipc_export(ppmx_gpu_ctx *c, const void *device_ptr, uint
 extern "C" int ppmx_gpu_ipc_open(ppmx_gpu_ctx *c, const uint8_t handle[64], void **device_ptr)
 {
     if (!c || !device_ptr || !handle) return fail("ppmx_gpu_ipc_open: null argument");
-    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    CK(cudaSetDevice(primary(c)->device), "cudaSetDevice");
     cudaIpcMemHandle_t hd;
     memcpy(&hd, handle, 64);
     CK(cudaIpcOpenMemHandle(device_ptr, hd, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
@@ -734,7 +698,7 @@ extern "C" int ppmx_gpu_ipc_open(ppmx_gpu_ctx *c, const uint8_t handle[64], void
 extern "C" int ppmx_gpu_ipc_close(ppmx_gpu_ctx *c, void *device_ptr)
 {
     if (!c || !device_ptr) return fail("ppmx_gpu_ipc_close: null argument");
-    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    CK(cudaSetDevice(primary(c)->device), "cudaSetDevice");
     CK(cudaIpcCloseMemHandle(device_ptr), "cudaIpcCloseMemHandle");
     return PPMX_OK;
 }

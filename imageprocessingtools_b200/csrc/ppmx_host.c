@@ -298,6 +298,10 @@ int ppmx_plan_chain_ext2(const ppmx_args_flag *f, unsigned int output_width_size
     int renew = f->resize_enable || f->rotate_enable;
     int n = 0;
     memset(plan, 0, sizeof(*plan));
+    /* the reference's command line refuses these pairs (ref:130, 135, 166, 171); a caller of the C planner gets
+     * the same answer instead of a chain the reference can not express (and the op array stays within its bound) */
+    if ((f->gray_enable && f->mono_enable) || (f->flipv_enable && f->fliph_enable))
+        BAIL("Error: Conflicting options not allowed\n");
 
     if (f->resize_enable) { /* ref:1084-1130 */
         double scale[2];
@@ -374,6 +378,10 @@ int ppmx_plan_chain_ext2(const ppmx_args_flag *f, unsigned int output_width_size
         plan->ops[n].flip_direction = 0;
         plan->ops[n++].renew_before = renew;
     }
+    if (n > PPMX_PLAN_MAX_OPS) { /* can not happen with the stages above (7 at most); guards future additions */
+        printf("Error: op chain too long\n");
+        goto bad;
+    }
     plan->nops = n;
     return PPMX_OK;
 bad:
@@ -407,6 +415,31 @@ int ppmx_band_plan(unsigned int full_h, int nranks, int rank, unsigned int align
     *y0 = a;
     *rows = b - a;
     return PPMX_OK;
+}
+
+/* ------------------------------------------------------------------ synthetic rasters */
+
+/* The benchmark's input generator: s = s * 1664525 + 1013904223 mod 2^32, one step per pixel,
+ * r = s >> 24, g = s >> 16, b = s >> 8.  Fills pixels [first, first + npix) of the sequence that starts from `seed`,
+ * so every rank of a multi-process job can produce its own rows of ONE raster: the state after `first` steps comes
+ * from the affine map of a jump, composed by squaring (a k-step jump is s -> A s + C mod 2^32). */
+void ppmx_synth_lcg(unsigned char *rgb, size_t first, size_t npix, uint32_t seed)
+{
+    uint32_t A = 1664525u, Cc = 1013904223u, ja = 1u, jc = 0u, s = seed;
+    size_t k = first, i;
+    while (k) { /* (ja, jc) := jump by the bits of `first` */
+        if (k & 1u) { ja = ja * A; jc = jc * A + Cc; }
+        Cc = Cc * A + Cc; /* doubling: s -> A (A s + C) + C */
+        A = A * A;
+        k >>= 1;
+    }
+    s = ja * s + jc;
+    for (i = 0; i < npix; i++) {
+        s = s * 1664525u + 1013904223u;
+        rgb[3 * i] = (unsigned char)(s >> 24);
+        rgb[3 * i + 1] = (unsigned char)(s >> 16);
+        rgb[3 * i + 2] = (unsigned char)(s >> 8);
+    }
 }
 
 /* ------------------------------------------------------------------ P6 in, P6/P5/P4 out */

@@ -6,6 +6,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace ppmx {
 
 // Row-band context for operators whose result depends on the absolute row (Bayer phase,
@@ -19,9 +21,16 @@ struct Band {
     uint32_t out_y0 = 0, out_rows = 0;  // imresize height pass: the slice of output rows this band produces
 };
 
-// which implementation of an operator to launch; 0 = the default (best measured)
+// Which implementation of an operator to launch; 0 = the default (best measured).  Only the tuning build
+// (-DPPMX_TUNING, libppmx_gpu_tuning.so) has the switch: in the release library PPMX_VARIANT is the constant 0, so the
+// alternative kernels are never instantiated and do not ship.
+#ifdef PPMX_TUNING
 extern int g_variant;
-extern int g_pdl;  // programmatic dependent launch on/off
+#define PPMX_VARIANT (::ppmx::g_variant)
+#else
+#define PPMX_VARIANT 0
+#endif
+extern std::atomic<int> g_pdl;  // programmatic dependent launch on/off (process-wide)
 
 cudaError_t gray(const uint8_t *src, uint8_t *dst, size_t npix, unsigned long long *d_hist, cudaStream_t s);
 cudaError_t hist_gray(const uint8_t *src, size_t npix, unsigned long long *d_hist, cudaStream_t s);
@@ -44,5 +53,6 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
 cudaError_t levels(const uint8_t *src, uint8_t *dst, size_t nbytes, const uint8_t *lut /*host*/, cudaStream_t s);
 
 unsigned long long launch_count();
+void add_launches(unsigned long long n);  // kernels replayed by a CUDA graph launch
 
 }  // namespace ppmx

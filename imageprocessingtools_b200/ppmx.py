@@ -14,6 +14,7 @@ import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 GPU_SO = os.path.join(PKG, "libppmx_gpu.so")
+TUNING_SO = os.path.join(PKG, "libppmx_gpu_tuning.so")  # same sources, -DPPMX_TUNING: alternative kernel variants
 HOST_SO = os.path.join(PKG, "libppmx_host.so")
 CLI = os.path.join(PKG, "ppmx-b200")
 
@@ -58,23 +59,53 @@ class _Contrib(C.Structure):
     _fields_ = [("weights", _dblp), ("indices", _i32p), ("weights_sz", C.c_int), ("out_size", C.c_int)]
 
 
+PLAN_MAX_OPS = 12  # PPMX_PLAN_MAX_OPS of include/ppmx_host.h
+
+
 class _Plan(C.Structure):
-    _fields_ = [("ops", PpmxOp * 8), ("nops", C.c_int), ("contrib", _Contrib * 2), ("levels_lut", C.c_uint8 * 256)]
+    _fields_ = [("ops", PpmxOp * PLAN_MAX_OPS), ("nops", C.c_int), ("contrib", _Contrib * 2), ("levels_lut", C.c_uint8 * 256)]
 
 
 _gpu = None
+_tuning = None
 _host = None
 
 
-def gpu_lib() -> C.CDLL:
-    """libppmx_gpu.so; raises if it has not been built (no fallback)."""
-    global _gpu
+def gpu_lib(tuning: bool = False) -> C.CDLL:
+    """libppmx_gpu.so (or the tuning build); raises if it has not been built (no fallback)."""
+    global _gpu, _tuning
+    if tuning:
+        if _tuning is None:
+            if not os.path.exists(TUNING_SO):
+                raise PpmxError("libppmx_gpu_tuning.so is not built")
+            _tuning = _declare(C.CDLL(TUNING_SO, mode=C.RTLD_LOCAL))
+        return _tuning
     if _gpu is None:
         if not os.path.exists(GPU_SO):
             raise PpmxError("libppmx_gpu.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
-        L = C.CDLL(GPU_SO, mode=C.RTLD_GLOBAL)
+        _gpu = _declare(C.CDLL(GPU_SO, mode=C.RTLD_GLOBAL))
+    return _gpu
+
+
+def _declare(L: C.CDLL) -> C.CDLL:
+    if True:
         vp = C.c_void_p
         L.ppmx_gpu_init.argtypes = [C.POINTER(vp), C.c_int]
+        L.ppmx_gpu_init_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+        L.ppmx_gpu_device_count.argtypes = [vp]
+        L.ppmx_gpu_host_register.argtypes = [vp, vp, C.c_size_t]
+        L.ppmx_gpu_host_unregister.argtypes = [vp, vp]
+        L.ppmx_gpu_apply_band.argtypes = [vp, C.POINTER(PpmxOp), C.c_int, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp,
+                                          C.c_size_t, C.POINTER(C.c_size_t), _u32p, _u32p, C.POINTER(C.c_int), _u32p, _u32p]
+        L.ppmx_gpu_chain_info.argtypes = [C.POINTER(PpmxOp), C.c_int, C.c_uint32, C.c_uint32, _u32p, _u32p,
+                                          C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ppmx_gpu_band_rows.argtypes = [C.POINTER(PpmxOp), C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u32p, _u32p,
+                                         _u32p, _u32p]
+        L.ppmx_gpu_graph_begin.argtypes = [vp]
+        L.ppmx_gpu_graph_end.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+        L.ppmx_gpu_graph_launch.argtypes = [vp, vp]
+        L.ppmx_gpu_graph_free.argtypes = [vp]
+        L.ppmx_gpu_graph_free.restype = None
         L.ppmx_gpu_free.argtypes = [vp]
         L.ppmx_gpu_free.restype = None
         L.ppmx_gpu_host_alloc.argtypes = [vp, C.c_size_t]
@@ -112,8 +143,7 @@ def gpu_lib() -> C.CDLL:
         L.ppmx_gpu_set_tuning.argtypes = [C.c_char_p, C.c_int]
         L.ppmx_gpu_launch_count.restype = C.c_uint64
         L.ppmx_gpu_version.restype = C.c_char_p
-        _gpu = L
-    return _gpu
+    return L
 
 
 def host_lib() -> C.CDLL:
@@ -144,6 +174,8 @@ def host_lib() -> C.CDLL:
         H.ppmx_band_plan.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, _u32p, _u32p]
         H.ppmx_parse_header.argtypes = [C.c_char_p, C.c_size_t, _u32p, _u32p, _u32p, C.POINTER(C.c_size_t)]
         H.ppmx_format_header.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_uint]
+        H.ppmx_synth_lcg.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32]
+        H.ppmx_synth_lcg.restype = None
         _host = H
     return _host
 
@@ -196,6 +228,34 @@ def band_plan(full_h: int, nranks: int, rank: int, align: int = 1) -> Tuple[int,
     return y0.value, rows.value
 
 
+def synth_lcg(w: int, rows: int, seed: int, y0: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Rows [y0, y0 + rows) of the w-wide LCG raster of SURVEY.md 8d (ppmx_synth_lcg, host C)."""
+    if out is None:
+        out = np.empty((rows, w, 3), np.uint8)
+    assert out.size == rows * w * 3 and out.flags["C_CONTIGUOUS"]
+    host_lib().ppmx_synth_lcg(C.c_void_p(out.ctypes.data), y0 * w, rows * w, seed & 0xFFFFFFFF)
+    return out
+
+
+def chain_info(ops, w: int, h: int):
+    """ppmx_gpu_chain_info (no device work): (out_w, out_h, file_type, out_bytes, splittable, kernels_per_part)."""
+    arr = (PpmxOp * len(ops))(*ops)
+    ow, oh, ft, nb, sp, k = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_size_t(), C.c_int(), C.c_int()
+    if gpu_lib().ppmx_gpu_chain_info(arr, len(ops), w, h, C.byref(ow), C.byref(oh), C.byref(ft), C.byref(nb), C.byref(sp),
+                                     C.byref(k)) != 0:
+        raise PpmxError("ppmx_gpu_chain_info failed")
+    return ow.value, oh.value, ft.value, nb.value, bool(sp.value), k.value
+
+
+def band_rows(ops, w: int, h: int, band: int, nbands: int):
+    """ppmx_gpu_band_rows (no device work): (out_y0, out_rows, src_y0, src_rows) of one band of ppmx_gpu_apply_band."""
+    arr = (PpmxOp * len(ops))(*ops)
+    v = [C.c_uint32() for _ in range(4)]
+    if gpu_lib().ppmx_gpu_band_rows(arr, len(ops), w, h, band, nbands, *[C.byref(x) for x in v]) != 0:
+        raise PpmxError("ppmx_gpu_band_rows failed")
+    return tuple(x.value for x in v)
+
+
 def parse_header(data: bytes):
     w, h, m = C.c_uint32(), C.c_uint32(), C.c_uint32()
     off = C.c_size_t()
@@ -232,12 +292,24 @@ class _PlanHolder:
 class Ppmx:
     """One ppmx_gpu_ctx.  Every method goes through the C ABI; rasters are numpy (h, w, 3) uint8."""
 
-    def __init__(self, device: int = 0):
-        self.L = gpu_lib()
+    def __init__(self, device=0, tuning: bool = False):
+        """device: an int (one GPU), or a list of device numbers / "all" for a multi-device context
+        (ppmx_gpu_init_multi).  tuning=True loads libppmx_gpu_tuning.so (kernel variants for sweeps)."""
+        self.L = gpu_lib(tuning)
         self.ctx = C.c_void_p()
-        if self.L.ppmx_gpu_init(C.byref(self.ctx), device) != 0:
+        if isinstance(device, int):
+            rc = self.L.ppmx_gpu_init(C.byref(self.ctx), device)
+        elif device == "all":
+            rc = self.L.ppmx_gpu_init_multi(C.byref(self.ctx), None, 0)
+        else:
+            devs = (C.c_int * len(device))(*device)
+            rc = self.L.ppmx_gpu_init_multi(C.byref(self.ctx), devs, len(device))
+        if rc != 0:
             raise PpmxError("ppmx_gpu_init failed (no B200 visible?) -- there is no CPU fallback")
         self.device = device
+
+    def device_count(self) -> int:
+        return int(self.L.ppmx_gpu_device_count(self.ctx))
 
     def close(self):
         if self.ctx:
@@ -403,6 +475,45 @@ class Ppmx:
         if rc != 0:
             raise PpmxError("ppmx_gpu_apply_batch failed")
         return out[:, :each.value].copy(), rw.value, rh.value, ft.value
+
+    def apply_band(self, img, ops, band: int, nbands: int, out: Optional[np.ndarray] = None):
+        """ppmx_gpu_apply_band: the rows of row band `band` of `nbands` of the chain's output, written into `out`
+        (the WHOLE output, shared by all bands).  Returns (out, out_w, out_h, file_type, band_y0, band_rows)."""
+        img = _img(img)
+        h, w, _ = img.shape
+        arr = (PpmxOp * len(ops))(*ops)
+        ow, oh, ft, nb = self.chain_info(ops, w, h)[:4]
+        if out is None:
+            out = np.zeros(nb, np.uint8)
+        n = C.c_size_t()
+        rw, rh, rft, y0, rows = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_uint32(), C.c_uint32()
+        rc = self.L.ppmx_gpu_apply_band(self.ctx, arr, len(ops), _vp(img), w, h, band, nbands, _vp(out), out.size,
+                                        C.byref(n), C.byref(rw), C.byref(rh), C.byref(rft), C.byref(y0), C.byref(rows))
+        if rc != 0:
+            raise PpmxError("ppmx_gpu_apply_band failed")
+        return out, rw.value, rh.value, rft.value, y0.value, rows.value
+
+    @staticmethod
+    def chain_info(ops, w: int, h: int):
+        return chain_info(ops, w, h)
+
+    # -- CUDA graphs over raw launches ---------------------------------------------------------
+    def graph_begin(self, stream: int) -> None:
+        if self.L.ppmx_gpu_graph_begin(C.c_void_p(stream)) != 0:
+            raise PpmxError("ppmx_gpu_graph_begin failed")
+
+    def graph_end(self, stream: int):
+        g, n = C.c_void_p(), C.c_uint64()
+        if self.L.ppmx_gpu_graph_end(C.c_void_p(stream), C.byref(g), C.byref(n)) != 0:
+            raise PpmxError("ppmx_gpu_graph_end failed")
+        return g, int(n.value)
+
+    def graph_launch(self, graph, stream: int) -> None:
+        if self.L.ppmx_gpu_graph_launch(graph, C.c_void_p(stream)) != 0:
+            raise PpmxError("ppmx_gpu_graph_launch failed")
+
+    def graph_free(self, graph) -> None:
+        self.L.ppmx_gpu_graph_free(graph)
 
     @staticmethod
     def header(file_type: int, w: int, h: int, maxval: int = 255) -> bytes:

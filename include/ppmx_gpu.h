@@ -84,20 +84,33 @@ typedef struct ppmx_op {
     const uint8_t *levels_lut;
 } ppmx_op;
 
-typedef struct ppmx_gpu_ctx ppmx_gpu_ctx;     /* one CUDA device, one stream, buffer pool   */
+typedef struct ppmx_gpu_ctx ppmx_gpu_ctx;     /* one CUDA device (or several), streams, a private buffer pool */
 typedef struct ppmx_gpu_image ppmx_gpu_image; /* a raster resident in HBM                   */
+typedef struct ppmx_gpu_graph ppmx_gpu_graph; /* a recorded sequence of raw launches        */
 
 /* ---- lifetime ------------------------------------------------------------------------ */
 
-/* Binds a context to CUDA device `device`, creates its stream and staging pool.  Replaces
- * nothing in the reference (it has no state beyond the handler on main's stack, ref:119). */
+/* Binds a context to CUDA device `device`, creates its streams and a stream-ordered pool of its
+ * own (the device's default pool is not touched).  Replaces nothing in the reference (it has no
+ * state beyond the handler on main's stack, ref:119). */
 int ppmx_gpu_init(ppmx_gpu_ctx **ctx, int device);
+/* One context over several devices of this process (devices == NULL or ndev == 0: every visible
+ * device).  ppmx_gpu_apply on such a context cuts ONE large raster into row bands, one per device
+ * (BASELINE config 4: halo rows are uploaded with each band straight from the host raster);
+ * ppmx_gpu_apply_batch deals whole rasters round-robin (config 5, image-parallel).  Everything
+ * else (upload, op, download, raw memory) runs on the first device. */
+int ppmx_gpu_init_multi(ppmx_gpu_ctx **ctx, const int *devices, int ndev);
+int ppmx_gpu_device_count(const ppmx_gpu_ctx *ctx);
 void ppmx_gpu_free(ppmx_gpu_ctx *ctx);
 
-/* Pinned host memory for rasters, so upload/download run at PCIe speed.  Replaces the
- * per-row mallocs of getImageInfo / image_buff_alloc (ref:440-449, 922-934). */
+/* Pinned host memory for rasters, so upload/download run at PCIe speed (portable: usable from
+ * every device of a multi-device context).  Replaces the per-row mallocs of getImageInfo /
+ * image_buff_alloc (ref:440-449, 922-934).  host_register pins memory the caller already owns
+ * (e.g. a shared mapping that several ranks of a job read their bands from). */
 void *ppmx_gpu_host_alloc(ppmx_gpu_ctx *ctx, size_t bytes);
 void ppmx_gpu_host_free(ppmx_gpu_ctx *ctx, void *p);
+int ppmx_gpu_host_register(ppmx_gpu_ctx *ctx, void *p, size_t bytes);
+int ppmx_gpu_host_unregister(ppmx_gpu_ctx *ctx, void *p);
 
 /* ---- the reference-facing call: one op chain, host raster in, host raster out ------- */
 
@@ -105,7 +118,11 @@ void ppmx_gpu_host_free(ppmx_gpu_ctx *ctx, void *p);
  * follow a P6 header, ref:316-318) with the reference's buff/new_buff hand-over rules
  * (ref:1084-1155, driven by ops[i].renew_before) and writes to `dst` exactly the bytes
  * putImageToFile emits after its header (ref:263-291): RGB triples, or .r bytes for PGM, or
- * packed bits for PBM.  Upload, kernels and download are issued on the context's stream. */
+ * packed bits for PBM.  Operators whose result the reference computes but never writes (the
+ * leaked grey raster of "-gray -fh") are not computed; the bytes are the same.
+ * A large raster is cut into row parts that go round-robin over the context's streams, so the
+ * upload of one part, the kernels of the previous and the download of the one before overlap;
+ * on a multi-device context the parts are spread over the devices as row bands. */
 int ppmx_gpu_apply(ppmx_gpu_ctx *ctx, const ppmx_op *ops, int nops,
                    const uint8_t *src_rgb, uint32_t w, uint32_t h,
                    uint8_t *dst, size_t dst_cap, size_t *dst_bytes,
@@ -118,6 +135,30 @@ int ppmx_gpu_apply_batch(ppmx_gpu_ctx *ctx, const ppmx_op *ops, int nops,
                          const uint8_t *src_rgb, uint32_t w, uint32_t h, int count,
                          uint8_t *dst, size_t dst_stride, size_t *dst_bytes_each,
                          uint32_t *out_w, uint32_t *out_h, int *out_file_type);
+
+/* One rank of a multi-process job (one process per GPU): the same as ppmx_gpu_apply, but only the
+ * output rows of row band `band` of `nbands` are produced (cuts as ppmx_band_plan with align 4,
+ * returned in band_y0 / band_rows).  src is the WHOLE w x h raster on the host -- only the rows the
+ * band needs (its own plus halo rows: k/2 for a convolution, the table's reach for a resize height
+ * pass, the mirrored band for a vertical flip) are read -- and dst the WHOLE output, of which only
+ * the band's rows are written; typically both are one shared pinned mapping.  Chains holding a
+ * 90 / 270 degree or free rotation can not be cut (nbands must be 1 for them). */
+int ppmx_gpu_apply_band(ppmx_gpu_ctx *ctx, const ppmx_op *ops, int nops,
+                        const uint8_t *src_rgb, uint32_t w, uint32_t h, int band, int nbands,
+                        uint8_t *dst, size_t dst_cap, size_t *dst_bytes,
+                        uint32_t *out_w, uint32_t *out_h, int *out_file_type,
+                        uint32_t *band_y0, uint32_t *band_rows);
+
+/* The rows ppmx_gpu_apply_band touches for band `band` of `nbands`: output rows [out_y0, out_y0 +
+ * out_rows) are written, source rows [src_y0, src_y0 + src_rows) are read.  No device work. */
+int ppmx_gpu_band_rows(const ppmx_op *ops, int nops, uint32_t w, uint32_t h, int band, int nbands,
+                       uint32_t *out_y0, uint32_t *out_rows, uint32_t *src_y0, uint32_t *src_rows);
+
+/* What a chain will produce for a w x h raster, without running it: geometry, writer's file type,
+ * bytes, whether it can be cut into row bands, and the number of kernels one part launches. */
+int ppmx_gpu_chain_info(const ppmx_op *ops, int nops, uint32_t w, uint32_t h, uint32_t *out_w,
+                        uint32_t *out_h, int *out_file_type, size_t *out_bytes, int *splittable,
+                        int *kernels);
 
 /* ---- device-resident rasters: one operator per call ---------------------------------- */
 
@@ -164,6 +205,15 @@ typedef struct ppmx_band {
 int ppmx_gpu_launch(const ppmx_op *op, const void *d_src, uint32_t w, uint32_t h, int src_layout,
                     void *d_dst, const ppmx_band *band, void *d_hist, void *d_tables, void *stream);
 
+/* A sequence of ppmx_gpu_launch calls recorded into a CUDA graph and replayed with one driver call:
+ * begin puts `stream` into capture mode, the launches issued on it (and on streams forked from it
+ * with events) are recorded instead of run, end instantiates the graph (*kernel_nodes = kernels in
+ * it).  graph_launch enqueues the whole recording on a stream. */
+int ppmx_gpu_graph_begin(void *stream);
+int ppmx_gpu_graph_end(void *stream, ppmx_gpu_graph **graph, uint64_t *kernel_nodes);
+int ppmx_gpu_graph_launch(ppmx_gpu_graph *graph, void *stream);
+void ppmx_gpu_graph_free(ppmx_gpu_graph *graph);
+
 /* Device-side copy of an imresize table pair for ppmx_gpu_launch (d_tables): returns a
  * device allocation holding weights then indices; release with ppmx_gpu_tables_free. */
 int ppmx_gpu_tables_upload(const ppmx_op *op, void **d_tables);
@@ -188,9 +238,11 @@ int ppmx_gpu_ipc_export(ppmx_gpu_ctx *ctx, const void *device_ptr, uint8_t handl
 int ppmx_gpu_ipc_open(ppmx_gpu_ctx *ctx, const uint8_t handle[64], void **device_ptr);
 int ppmx_gpu_ipc_close(ppmx_gpu_ctx *ctx, void *device_ptr);
 
-/* Experiment switches for benchmarking (not needed for correct results): key "variant" selects
- * an alternative kernel implementation (0 = default), key "pdl" turns programmatic dependent
- * launch on (1, default) or off (0).  Returns 0, or -1 for an unknown key. */
+/* Switches for benchmarking (not needed for correct results): key "pdl" turns programmatic
+ * dependent launch on (1, default) or off (0), process-wide.  Key "variant" selects an alternative
+ * kernel implementation (0 = default) in the TUNING build only (libppmx_gpu_tuning.so, the same
+ * sources with -DPPMX_TUNING, loaded by tools/sweep.py and the variant tests); the release library
+ * carries no alternatives and answers -1 to any variant but 0.  Returns 0, or -1. */
 int ppmx_gpu_set_tuning(const char *key, int value);
 
 /* number of kernel launches issued through this library since load (bench: gpu_launches) */

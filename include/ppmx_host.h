@@ -83,8 +83,9 @@ void ppmx_renewBuffer(ppmx_image_handler *handler);                  /* ref:1019
 
 /* A ready-to-run op chain for ppmx_gpu_apply: the flag order and renewBuffer conditions of
  * ref:1084-1155, with rotate geometry and resize tables already computed on the host. */
+#define PPMX_PLAN_MAX_OPS 12 /* resize 2 + rotate + conv + levels + gray/mono + one flip = 7 at most today */
 typedef struct ppmx_plan {
-    ppmx_op ops[8];
+    ppmx_op ops[PPMX_PLAN_MAX_OPS];
     int nops;
     ppmx_contributions contrib[2]; /* owned tables of the two resize passes */
     unsigned char levels_lut[256]; /* table of the extension levels stage, if any */
@@ -129,6 +130,11 @@ int ppmx_format_header(char *dst, size_t cap, int file_type, unsigned int width,
  * trailing ranks may get 0 rows when full_h is small.  No reference counterpart. */
 int ppmx_band_plan(unsigned int full_h, int nranks, int rank, unsigned int align, unsigned int *y0,
                    unsigned int *rows);
+
+/* Synthetic raster for benchmarks and tests (no reference counterpart): the LCG
+ * s = s * 1664525 + 1013904223 (mod 2^32), one step per pixel, r = s >> 24, g = s >> 16, b = s >> 8.
+ * Writes pixels [first, first + npix) of the sequence started from `seed` (a rank fills only its rows). */
+void ppmx_synth_lcg(unsigned char *rgb, size_t first, size_t npix, uint32_t seed);
 
 int ppmx_getImageInfo(ppmx_image_handler *handler);   /* ref:409-456: parse + upload        */
 int ppmx_putImageToFile(ppmx_image_handler *handler); /* ref:221-301: download + one fwrite */

@@ -27,6 +27,17 @@ def gpu():
     g.close()
 
 
+@pytest.fixture(scope="module")
+def gpu_tuning():
+    """The tuning build of the same sources (-DPPMX_TUNING): the kernel variants the release library leaves out."""
+    import imageprocessingtools_b200 as ip
+    g = ip.Ppmx(0, tuning=True)
+    yield g
+    g.set_tuning("variant", 0)
+    g.set_tuning("pdl", 1)
+    g.close()
+
+
 def test_native_library_is_the_one_running(gpu):
     import imageprocessingtools_b200.ppmx as pp
     assert os.path.exists(pp.GPU_SO)
@@ -63,7 +74,8 @@ def test_pack_pbm_raw_bytes(gpu, orc):
         assert np.array_equal(gpu.pack_pbm(raw), orc.pack_pbm(raw)), (w, h)
 
 
-def test_rotate_orth_bulk_copy_tiles(gpu, orc):
+def test_rotate_orth_bulk_copy_tiles(gpu_tuning, orc):
+    gpu = gpu_tuning
     """90 / 270 degrees on rasters whose sides are multiples of 16 take the bulk-copy (cp.async.bulk) transposer
     (64 x 64 tiles, narrower / shorter at the right and bottom edges);
     the register-path kernel (variant 6) and the generic one (variant 1) must give the same bytes."""
@@ -457,8 +469,9 @@ def test_full_size_bicubic_4096(gpu, orc):
     assert np.array_equal(gpu.rotate(flat, 77), orc.rotate(flat, 77))
 
 
-def test_tuning_variants_are_bit_identical(gpu, orc):
+def test_tuning_variants_are_bit_identical(gpu_tuning, orc):
     """Every alternative kernel kept for benchmarking must give the default's bytes."""
+    gpu = gpu_tuning
     img = P.lcg(256, 192, 31)
     wt, ix = gpu.calc_contributions(192, 288, 1.5)
     wt2, ix2 = gpu.calc_contributions(256, 128, 0.5)
@@ -481,10 +494,11 @@ def test_tuning_variants_are_bit_identical(gpu, orc):
         gpu.set_tuning("pdl", 1)
 
 
-def test_extension_conv3_strip_variants(gpu, orc):
+def test_extension_conv3_strip_variants(gpu_tuning, orc):
     """3x3: the strip kernel (default; other strip heights / CTA sizes = variants 9-13; variant 8 = without the
     scaled-coefficient byte extraction) and the row-wise planar kernel (variant 7) give the self-oracle's bytes,
     on flat extremes too (saturation at both ends)."""
+    gpu = gpu_tuning
     imgs = [P.lcg(64, 200, 5), P.const(64, 131, 255), P.const(32, 70, 0), P.all_patterns(48, 133)["checker"]]
     names = ("blur3", "sharpen3", "edge3", "mix3_div8_biasneg", "sobel3", "wide3", "wide3_pow2")
     exp = {(i, k): orc.conv(img, *KERNELS[k]) for i, img in enumerate(imgs) for k in names}
@@ -623,3 +637,174 @@ def test_operator_level_host_api_stepwise(gpu, tmp_path):
         if os.path.exists(oracle.REF_CLI):
             rc, _ = oracle.ref_cli(args, c)
             assert rc == 0 and open(c + ".out", "rb").read() == open(a + ".out", "rb").read(), args
+
+
+# ---- round 2: row parts, row bands, several devices, CUDA graphs ------------------------------------------
+
+PART_CHAINS = [dict(conv_preset=1), dict(conv_preset=2, mono=True, flipv=True), dict(resize_w=300, gray=True),
+               dict(resize_w=97, conv_preset=4, fliph=True), dict(flipv=True), dict(angle=180, levels=(16, 235)),
+               dict(gray=True, flipv=True), dict(mono=True), dict(resize_w=201, angle=180, conv_preset=3, mono=True, flipv=True),
+               dict(angle=90, gray=True), dict(angle=33)]
+
+
+def _orc_chain(orc, img, resize_w=None, angle=None, gray=False, mono=False, flipv=False, fliph=False, conv_preset=0,
+               levels=None):
+    """The oracle's chain with the extension stages where ppmx_plan_chain_ext2 puts them (after resize / rotate,
+    before gray / mono / flip); chains without -w/-r and with an extension stage behave as if renewBuffer ran."""
+    cur = img
+    if resize_w is not None:
+        cur = orc.resize(cur, resize_w)
+    if angle is not None:
+        cur = orc.rotate(cur, angle)
+    if conv_preset:
+        coef, div = {1: (KERNELS["blur3"][0], 16), 2: (np.ones((7, 7), np.int64), 49), 3: (KERNELS["sharpen3"][0], 1),
+                     4: (KERNELS["edge3"][0], 1)}[conv_preset]
+        cur = orc.conv(cur, coef, div, 0)
+    if levels is not None:
+        cur = orc.levels(cur, orc.levels_lut_linear(*levels))
+    renewed = resize_w is not None or angle is not None or conv_preset or levels is not None
+    if renewed:
+        return orc.process(cur, angle=0, gray=gray, mono=mono, flipv=flipv, fliph=fliph) if (gray or mono or flipv or fliph) \
+            else (cur.reshape(-1), cur.shape[1], cur.shape[0], 0)
+    return orc.process(cur, gray=gray, mono=mono, flipv=flipv, fliph=fliph)
+
+
+def test_row_parts_equal_whole_raster(gpu, orc, monkeypatch):
+    """ppmx_gpu_apply cuts a raster into row parts that overlap upload / kernels / download; with PPMX_PART_BYTES
+    small rasters are cut into many uneven parts: same bytes as the oracle's whole-raster chain."""
+    for part_bytes in ("3000", "20000"):
+        monkeypatch.setenv("PPMX_PART_BYTES", part_bytes)
+        for (w, h) in [(64, 200), (48, 131), (37, 90)]:
+            img = P.lcg(w, h, 900 + w)
+            for kw in PART_CHAINS:
+                if kw.get("resize_w") and kw["resize_w"] > 4 * w:
+                    continue
+                exp, ew, eh, eft = _orc_chain(orc, img, **kw)
+                got, gw, gh, gft = gpu.process(img, **kw)
+                assert (gw, gh, gft) == (ew, eh, eft), (part_bytes, w, h, kw)
+                assert np.array_equal(got, exp), (part_bytes, w, h, kw)
+    monkeypatch.delenv("PPMX_PART_BYTES")
+    img = P.lcg(2048, 1500, 77)  # 9.2 MB: cut by the default part size
+    got, gw, gh, gft = gpu.process(img, conv_preset=1, gray=True)
+    exp = orc.process(orc.conv(img, KERNELS["blur3"][0], 16, 0), angle=0, gray=True)
+    assert (gw, gh, gft) == exp[1:] and np.array_equal(got, exp[0])
+
+
+def test_apply_band_stitches_to_whole(gpu, orc):
+    """ppmx_gpu_apply_band: every band writes its rows of ONE shared output; all bands together = the whole result.
+    Each call gets a virtual whole-raster pointer behind which only the rows ppmx_gpu_band_rows names exist."""
+    import ctypes as C
+    import imageprocessingtools_b200.ppmx as pp
+    w, h = 64, 150
+    img = P.lcg(w, h, 4711)
+    for kw in [dict(conv_preset=1), dict(conv_preset=2, mono=True, flipv=True), dict(resize_w=96, gray=True), dict(flipv=True),
+               dict(angle=180), dict(gray=True), dict(resize_w=40, conv_preset=4)]:
+        ph = pp._PlanHolder(w=w, h=h, **kw)
+        ops = [ph.plan.ops[i] for i in range(ph.plan.nops)]
+        exp, ew, eh, eft = _orc_chain(orc, img, **kw)
+        for nb in (1, 2, 3, 5, 8):
+            ow, oh, ft, nbytes, split, _ = pp.chain_info(ops, w, h)
+            assert split and (ow, oh, ft) == (ew, eh, eft)
+            out = np.zeros(nbytes, np.uint8)
+            row_bytes = nbytes // oh
+            arr = (pp.PpmxOp * len(ops))(*ops)
+            for b in range(nb):
+                oy0, orows, sy0, srows = pp.band_rows(ops, w, h, b, nb)
+                src = img[sy0:sy0 + srows].copy()  # nothing else of the raster exists for this call
+                n, rw, rh, rft, y0, rows = C.c_size_t(), C.c_uint32(), C.c_uint32(), C.c_int(), C.c_uint32(), C.c_uint32()
+                rc = gpu.L.ppmx_gpu_apply_band(gpu.ctx, arr, len(ops), C.c_void_p(src.ctypes.data - sy0 * w * 3), w, h, b, nb,
+                                               C.c_void_p(out.ctypes.data), out.size, C.byref(n), C.byref(rw), C.byref(rh),
+                                               C.byref(rft), C.byref(y0), C.byref(rows))
+                assert rc == 0 and (y0.value, rows.value) == (oy0, orows)
+            assert np.array_equal(out, exp), (kw, nb)
+        ph.close()
+    # a chain with a 90 degree rotation can not be cut into bands: refused, not computed wrongly
+    ph = pp._PlanHolder(w=w, h=h, angle=90)
+    ops = [ph.plan.ops[i] for i in range(ph.plan.nops)]
+    assert pp.chain_info(ops, w, h)[4] is False
+    with pytest.raises(pp.PpmxError):
+        gpu.apply_band(img, ops, 0, 2)
+    ph.close()
+
+
+def test_multi_device_context_row_bands(orc):
+    """ppmx_gpu_init_multi: ONE raster over all visible GPUs as row bands (config 4), a batch image-parallel."""
+    import torch
+    import imageprocessingtools_b200 as ip
+    import imageprocessingtools_b200.ppmx as pp
+    n = torch.cuda.device_count()
+    devs = list(range(n)) if n > 1 else [0, 0]  # one GPU: two contexts on it still exercise the split
+    g = ip.Ppmx(devs)
+    try:
+        assert g.device_count() == len(devs)
+        img = P.lcg(256, 301, 8)
+        for kw in [dict(conv_preset=2), dict(conv_preset=1, mono=True, flipv=True), dict(resize_w=384, gray=True), dict(angle=90)]:
+            exp, ew, eh, eft = _orc_chain(orc, img, **kw)
+            got, gw, gh, gft = g.process(img, **kw)
+            assert (gw, gh, gft) == (ew, eh, eft) and np.array_equal(got, exp), kw
+        imgs = np.stack([P.lcg(96, 40, 300 + i) for i in range(9)])
+        bins = np.zeros((9, 256), np.uint64)
+        import ctypes as C
+        op = pp.PpmxOp(kind=pp.OP_GRAY_HIST, hist_out=bins.ctypes.data_as(C.POINTER(C.c_uint64)))
+        out, w, h, ft = g.apply_ops(imgs, [op])
+        for i in range(9):
+            assert np.array_equal(out[i].reshape(40, 96), orc.gray(imgs[i])) and np.array_equal(bins[i], orc.hist_gray(imgs[i]))
+        big = P.lcg(1024, 515, 9)
+        bins1 = np.zeros(256, np.uint64)
+        op = pp.PpmxOp(kind=pp.OP_GRAY_HIST, hist_out=bins1.ctypes.data_as(C.POINTER(C.c_uint64)))
+        out, w, h, ft = g.apply_ops(big[None], [op])  # one raster: bands over the devices, bins summed on the host
+        assert np.array_equal(out[0].reshape(515, 1024), orc.gray(big)) and np.array_equal(bins1, orc.hist_gray(big))
+    finally:
+        g.close()
+
+
+def test_full_size_bands_16384(gpu, orc):
+    """BASELINE config 4 size: a 16384-wide raster; N bands == whole raster for the convolutions (property), gray /
+    mono / flips of a 16384 x 2048 slice against the oracle directly."""
+    import imageprocessingtools_b200.ppmx as pp
+    w, h = 16384, 2048
+    img = pp.synth_lcg(w, h, 0xC0FFEE ^ 4)
+    assert np.array_equal(gpu.gray(img), orc.gray(img))
+    assert np.array_equal(gpu.mono_bits(img), orc.pack_pbm(orc.mono(img)))
+    assert np.array_equal(gpu.flip(img, 1), img[::-1])
+    assert np.array_equal(gpu.rotate(img, 180), img[::-1, ::-1])
+    for kname in ("blur3", "box7"):
+        coef, div, bias = KERNELS[kname]
+        op = gpu.conv_op(coef, div, bias)
+        whole = gpu.conv(img, coef, div, bias)
+        out = np.zeros(w * h * 3, np.uint8)
+        for b in range(8):
+            gpu.apply_band(img, [op], b, 8, out)
+        assert np.array_equal(out.reshape(h, w, 3), whole), kname
+        sl = slice(1000, 1040)  # a slice of it against the oracle (rows far from the raster's edges)
+        r = coef.shape[0] // 2
+        exp = orc.conv(img[sl.start - r:sl.stop + r], coef, div, bias)[r:-r]
+        assert np.array_equal(whole[sl], exp), kname
+
+
+def test_cuda_graph_replays_launches(gpu, orc):
+    """ppmx_gpu_graph_*: launches recorded once and replayed give the bytes of direct launches."""
+    import torch
+    import imageprocessingtools_b200.ppmx as pp
+    dev = torch.device("cuda", 0)
+    img = P.lcg(256, 128, 5)
+    src = torch.from_numpy(img).to(dev)
+    mid = torch.zeros_like(src)
+    out = torch.zeros((128, 256), dtype=torch.uint8, device=dev)
+    coef, div, bias = KERNELS["blur3"]
+    op1, op2 = gpu.conv_op(coef, div, bias), pp.PpmxOp(kind=pp.OP_GRAY)
+    s = torch.cuda.Stream()
+    n0 = gpu.launch_count()
+    with torch.cuda.stream(s):
+        gpu.graph_begin(s.cuda_stream)
+        gpu.launch(op1, src.data_ptr(), 256, 128, pp.LAYOUT_RGB8, mid.data_ptr(), None, 0, 0, s.cuda_stream)
+        gpu.launch(op2, mid.data_ptr(), 256, 128, pp.LAYOUT_RGB8, out.data_ptr(), None, 0, 0, s.cuda_stream)
+        graph, nodes = gpu.graph_end(s.cuda_stream)
+        assert nodes == 2
+        assert int(out.sum().item()) == 0  # recording runs nothing
+        gpu.graph_launch(graph, s.cuda_stream)
+        gpu.graph_launch(graph, s.cuda_stream)
+        s.synchronize()
+    assert gpu.launch_count() - n0 == 2 + 4
+    gpu.graph_free(graph)
+    assert np.array_equal(out.cpu().numpy(), orc.gray(orc.conv(img, coef, div, bias)))

@@ -185,3 +185,84 @@ def test_conv_rounding_magic():
         assert all(int(a) == int(b) // d for a, b in zip(q[::37], ns[::37]))
         exp = (ns // np.uint64(d)).astype(object)
         assert (q == exp).all(), div
+
+
+# ---- round 2 ---------------------------------------------------------------------------------------------
+
+def test_bayer_thresholds_are_ceil_of_matrix_times_255():
+    """c_bayer (ppmx_common.cuh) holds ceil(matrix * 255); for an integer grey, g < c_bayer <=> !(g >= matrix * 255)
+    (ref:954, 967) -- all 256 x 16 cases."""
+    src = open(os.path.join(ROOT, "imageprocessingtools_b200", "csrc", "ppmx_common.cuh")).read()
+    thr = [int(x) for x in re.search(r"c_bayer\[16\] = \{([^}]*)\}", src).group(1).split(",")]
+    matrix = [.125, 1, .1875, .8125, .625, .375, .6875, .4375, .25, .875, .0625, .9375, .75, .5, .5625, .3125]  # ref:954
+    assert thr == [int(np.ceil(m * 255)) for m in matrix]
+    for i in range(16):
+        for gv in range(256):
+            assert (gv < thr[i]) == (not (gv >= matrix[i] * 255.0))
+
+
+def test_planner_refuses_conflicting_flags_and_stays_in_bounds(pp):
+    """ref:130,135,166,171: -gray x -mono and -fv x -fh are refused; every accepted flag set fits PPMX_PLAN_MAX_OPS."""
+    for kw in (dict(gray=True, mono=True), dict(flipv=True, fliph=True),
+               dict(resize_w=10, angle=30, gray=True, mono=True, flipv=True, fliph=True, conv_preset=1, levels=(1, 200))):
+        with pytest.raises(pp.PpmxError):
+            pp._PlanHolder(w=16, h=16, **kw)
+    ph = pp._PlanHolder(w=16, h=16, resize_w=10, angle=30, mono=True, flipv=True, conv_preset=1, levels=(1, 200))
+    assert ph.plan.nops == 7 <= pp.PLAN_MAX_OPS
+    ph.close()
+
+
+def test_chain_linearisation_and_band_rows(pp):
+    """ppmx_gpu_chain_info / ppmx_gpu_band_rows need no device: the chain is reduced to the operators that feed the
+    writer (ref:1084-1155 hand-over rules) and every band knows which source rows it reads."""
+    def ops_of(**kw):
+        ph = pp._PlanHolder(w=64, h=40, **kw)
+        return ph, [ph.plan.ops[i] for i in range(ph.plan.nops)]
+    ph, ops = ops_of(gray=True, fliph=True)         # the leaked grey raster (SURVEY.md 3.1): flip + .r extraction only
+    assert pp.chain_info(ops, 64, 40) == (64, 40, pp.FT_PGM, 64 * 40, True, 2)
+    ph.close()
+    ph, ops = ops_of(mono=True)                      # mono + P4 packer in one kernel
+    assert pp.chain_info(ops, 64, 40) == (64, 40, pp.FT_PBM, 8 * 40, True, 1)
+    ph.close()
+    ph, ops = ops_of(angle=90, mono=True, fliph=True)
+    assert pp.chain_info(ops, 64, 40)[:5] == (40, 64, pp.FT_PBM, 5 * 64, False)
+    with pytest.raises(pp.PpmxError):
+        pp.band_rows(ops, 64, 40, 0, 2)
+    ph.close()
+    ph, ops = ops_of(conv_preset=2)                  # 7x7: three halo rows on either side, none beyond the raster
+    cover = []
+    for b in range(3):
+        oy0, orows, sy0, srows = pp.band_rows(ops, 64, 40, b, 3)
+        assert sy0 == max(0, oy0 - 3) and sy0 + srows == min(40, oy0 + orows + 3)
+        cover += list(range(oy0, oy0 + orows))
+    assert cover == list(range(40))
+    ph.close()
+    ph, ops = ops_of(flipv=True)                     # the mirrored band (SURVEY.md 8e), no halo
+    for b in range(4):
+        oy0, orows, sy0, srows = pp.band_rows(ops, 64, 40, b, 4)
+        assert (sy0, srows) == (40 - oy0 - orows, orows)
+    ph.close()
+    ph, ops = ops_of(resize_w=96)                    # x1.5: the height pass reads the rows its table names
+    wt, ix = pp.calc_contributions(40, 60, 1.5)
+    for b in range(3):
+        oy0, orows, sy0, srows = pp.band_rows(ops, 64, 40, b, 3)
+        need = ix[oy0:oy0 + orows]
+        assert (sy0, sy0 + srows) == (int(need.min()), int(need.max()) + 1)
+    ph.close()
+
+
+def test_synthetic_lcg_rows(pp):
+    """ppmx_synth_lcg: any row range of the LCG raster equals the same rows of the whole raster (jump-ahead)."""
+    whole = pp.synth_lcg(37, 23, 0xC0FFEE)
+    assert np.array_equal(whole, P.lcg(37, 23, 0xC0FFEE))
+    for y0, rows in [(0, 1), (5, 7), (22, 1), (11, 12)]:
+        assert np.array_equal(pp.synth_lcg(37, rows, 0xC0FFEE, y0=y0), whole[y0:y0 + rows])
+
+
+def test_release_library_carries_no_tuning_variants(pp):
+    """The alternative kernel variants live in libppmx_gpu_tuning.so only."""
+    L = pp.gpu_lib()
+    assert L.ppmx_gpu_set_tuning(b"variant", 0) == 0 and L.ppmx_gpu_set_tuning(b"variant", 3) != 0
+    assert L.ppmx_gpu_set_tuning(b"pdl", 1) == 0
+    T = pp.gpu_lib(tuning=True)
+    assert T.ppmx_gpu_set_tuning(b"variant", 3) == 0 and T.ppmx_gpu_set_tuning(b"variant", 0) == 0

@@ -28,7 +28,7 @@ def main():
     import imageprocessingtools_b200 as ip
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
-    g = ip.Ppmx(0)
+    g = ip.Ppmx(0, tuning=True)  # libppmx_gpu_tuning.so: the release library carries the default kernels only
     peak, _ = bench.peaks()
     rows = []
     for op in args.ops.split(","):
