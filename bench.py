@@ -1251,7 +1251,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-band", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from the host instead of replaying a CUDA graph")
-    ap.add_argument("--lanes", type=int, default=1, help="streams the launches of a step go round-robin over")
+    ap.add_argument("--lanes", type=int, default=3,
+                    help="streams the launches of a step go round-robin over (independent rasters: ramps and tails overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

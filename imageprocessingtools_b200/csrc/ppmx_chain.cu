@@ -25,8 +25,11 @@ using namespace ppmx;
 
 namespace {
 
+constexpr int kFusedKind = 1000;  // internal stage kind: geometry + pointwise tail in one kernel (ppmx_fused.cu)
+
 struct Stage {
     ppmx_op op;
+    GeomOp go = {};     // kFusedKind only
     int op_index = -1;  // position in the caller's op list (device tables); -1: the writer's conversion
     uint32_t in_w = 0, in_h = 0, out_w = 0, out_h = 0;
     int in_layout = PPMX_LAYOUT_RGB8, out_layout = PPMX_LAYOUT_RGB8;
@@ -52,6 +55,7 @@ bool stage_splits(const Stage &s)
 {
     switch (s.op.kind) {
     case PPMX_OP_ROTATE: return s.op.angle_deg == 180;  // 90 / 270: a transpose; other angles: a slanted source strip
+    case kFusedKind: return !s.go.transpose;
     default: return true;
     }
 }
@@ -63,8 +67,145 @@ bool stage_row_exact(const Stage &s)
     case PPMX_OP_CONV: return s.op.conv_k <= 1;
     case PPMX_OP_IMRESIZE: return s.op.dim != 0;
     case PPMX_OP_ROTATE: return s.op.angle_deg == 180;
+    case kFusedKind: return !s.go.transpose;
     default: return true;
     }
+}
+
+// ---- fusion: runs of flips / right-angle rotations / grey / mono / the writer's conversions become ONE stage ----
+
+// where a pixel of the group's source raster sits after the geometric stages seen so far:
+// cx = sx * (swap ? y : x) + tx,  cy = sy * (swap ? x : y) + ty   (a signed permutation: the 8 orientations)
+struct Aff {
+    bool swap = false;
+    int sx = 1, sy = 1;
+    long tx = 0, ty = 0;
+    uint32_t cw = 0, ch = 0;
+    void fliph() { sx = -sx; tx = (long)cw - 1 - tx; }                 // ref:906-911
+    void flipv() { sy = -sy; ty = (long)ch - 1 - ty; }                 // ref:899-904
+    void rot90()                                                        // new[x][newW-1-y] = old[y][x], ref:717
+    {
+        const int nsx = -sy, nsy = sx;
+        const long ntx = (long)ch - 1 - ty, nty = tx;
+        swap = !swap; sx = nsx; sy = nsy; tx = ntx; ty = nty;
+        const uint32_t t = cw; cw = ch; ch = t;
+    }
+    void rot270()                                                       // new[newH-1-y][x] = old[x][y], ref:725
+    {
+        const int nsx = sy, nsy = -sx;
+        const long ntx = ty, nty = (long)cw - 1 - tx;
+        swap = !swap; sx = nsx; sy = nsy; tx = ntx; ty = nty;
+        const uint32_t t = cw; cw = ch; ch = t;
+    }
+};
+
+bool fusable_kind(const Stage &s)
+{
+    switch (s.op.kind) {
+    case PPMX_OP_FLIP:
+    case PPMX_OP_GRAY:
+    case PPMX_OP_MONO:
+    case PPMX_OP_MONO_BITS:
+    case PPMX_OP_EXTRACT_R:
+    case PPMX_OP_PACK_PBM: return !s.passthrough;
+    case PPMX_OP_ROTATE: return s.op.angle_deg == 90 || s.op.angle_deg == 180 || s.op.angle_deg == 270;
+    default: return false;
+    }
+}
+
+// tries to replace stages [i0, i1) by one fused stage; false = leave them as they are
+bool fuse_run(const std::vector<Stage> &st, size_t i0, size_t i1, Stage *out)
+{
+    if (st[i0].in_layout != PPMX_LAYOUT_RGB8) return false;
+    Aff cur, at_mono;
+    cur.cw = st[i0].in_w;
+    cur.ch = st[i0].in_h;
+    int point = 0;  // 0 rgb, 1 grey, 2 red, 3 mono (bits pending), 4 mono packed
+    for (size_t i = i0; i < i1; i++) {
+        const ppmx_op &op = st[i].op;
+        switch (op.kind) {
+        case PPMX_OP_FLIP:
+            if (op.flip_direction) cur.flipv();
+            else cur.fliph();
+            break;
+        case PPMX_OP_ROTATE:
+            if (op.angle_deg == 90) cur.rot90();
+            else if (op.angle_deg == 270) cur.rot270();
+            else { cur.fliph(); cur.flipv(); }  // ref:721
+            break;
+        case PPMX_OP_GRAY:
+            if (point) return false;
+            point = 1;
+            break;
+        case PPMX_OP_EXTRACT_R:
+            if (point) return false;
+            point = 2;
+            break;
+        case PPMX_OP_MONO:
+        case PPMX_OP_MONO_BITS:
+            if (point) return false;
+            point = op.kind == PPMX_OP_MONO ? 3 : 4;
+            at_mono = cur;
+            break;
+        case PPMX_OP_PACK_PBM:
+            if (point != 3) return false;  // the packer on raw .r bytes (the "-mono -fh" quirk) keeps its own kernel
+            point = 4;
+            break;
+        default: return false;
+        }
+    }
+    if (point == 3) return false;  // a 0/1 plane that is not packed inside the run
+    Stage f = st[i0];
+    memset(&f.op, 0, sizeof(f.op));
+    f.op.kind = kFusedKind;
+    f.op_index = -1;
+    f.out_w = st[i1 - 1].out_w;
+    f.out_h = st[i1 - 1].out_h;
+    f.out_layout = st[i1 - 1].out_layout;
+    GeomOp &g = f.go;
+    g.transpose = cur.swap ? 1 : 0;
+    g.rev_x = cur.sx < 0;
+    g.rev_y = cur.sy < 0;
+    g.point = point == 4 ? 3 : point;
+    if (point == 4) {
+        g.mx_from_y = at_mono.swap ? 1 : 0;
+        g.mx_neg = at_mono.sx < 0;
+        g.my_neg = at_mono.sy < 0;
+        g.mx_add = (int)(((at_mono.tx % 4) + 4) % 4);
+        g.my_add = (int)(((at_mono.ty % 4) + 4) % 4);
+    }
+    if (!geom_point_supported(f.in_w, f.in_h, g)) return false;
+    *out = f;
+    return true;
+}
+
+void fuse_pipeline(std::vector<Stage> &st)
+{
+    if (getenv("PPMX_NO_FUSE")) return;  // (tests compare the fused chain with the stage-by-stage one)
+    std::vector<Stage> out;
+    for (size_t i = 0; i < st.size();) {
+        size_t j = i;
+        while (j < st.size() && fusable_kind(st[j])) j++;
+        bool done = false;
+        // the longest fusable run that starts here; a single stage keeps its own (faster) kernel unless it is a
+        // 90 / 270 degree rotation of a raster the bulk-copy transposer can not take (sides not multiples of 16)
+        for (size_t e = j; e > i && !done; e--) {
+            const bool lone = e - i == 1;
+            if (lone) {
+                const ppmx_op &op = st[i].op;
+                const bool odd_transpose = op.kind == PPMX_OP_ROTATE && op.angle_deg != 180 && ((st[i].in_w | st[i].in_h) & 15u);
+                if (!odd_transpose) break;
+            }
+            Stage f;
+            if (fuse_run(st, i, e, &f)) {
+                out.push_back(f);
+                i = e;
+                done = true;
+            }
+        }
+        if (!done) out.push_back(st[i++]);
+    }
+    st.swap(out);
 }
 
 int build_pipeline(const ppmx_op *ops, int nops, uint32_t w, uint32_t h, Pipeline *P)
@@ -191,6 +332,7 @@ int build_pipeline(const ppmx_op *ops, int nops, uint32_t w, uint32_t h, Pipelin
     P->out_w = cw;
     P->out_h = ch;
     P->out_layout = cl;
+    fuse_pipeline(P->st);
 
     P->splittable = true;
     for (size_t i = 0; i < P->st.size(); i++) {
@@ -218,6 +360,9 @@ Rows stage_in_rows(const Stage &s, uint32_t a, uint32_t b)
 {
     const uint32_t H = s.in_h;
     switch (s.op.kind) {
+    case kFusedKind:
+        if (s.go.transpose) return Rows{0, H};
+        return s.go.rev_y ? Rows{H - b, H - a} : Rows{a, b};
     case PPMX_OP_FLIP:
         if (s.op.flip_direction) return Rows{H - b, H - a};  // ref:899-904
         return Rows{a, b};
@@ -257,6 +402,23 @@ int launch_stage(const Stage &s, const uint8_t *S, Rows in, uint8_t *D, uint32_t
     const bool whole = a == 0 && b == s.out_h && in.lo == 0 && in.hi == s.in_h;
     Band band;
     switch (s.op.kind) {
+    case kFusedKind: {
+        GeomOp go = s.go;
+        cudaError_t e;
+        if (go.transpose) {
+            if (!whole) return fail("internal: a transposing stage needs the whole raster");
+            e = geom_point(S, D, s.in_w, s.in_h, 0, go, stream);
+        } else {
+            const uint32_t first = go.rev_y ? s.in_h - b : a;  // first source row of this part
+            // mono's Bayer phase is counted in whole-raster rows: shift it by the part's first source row
+            const int shift = (int)(first & 3u);
+            if (go.mx_from_y) go.mx_add = (go.mx_add + (go.mx_neg ? 4 - shift : shift)) & 3;
+            else go.my_add = (go.my_add + (go.my_neg ? 4 - shift : shift)) & 3;
+            e = geom_point(S + (size_t)(first - in.lo) * pitch, D, s.in_w, b - a, 0, go, stream);
+        }
+        if (e != cudaSuccess) return fail("fused geometry stage", e);
+        return PPMX_OK;
+    }
     case PPMX_OP_ROTATE:
         if (s.op.angle_deg == 180) {
             ppmx_op op = s.op;  // the mirrored rows, turned as a raster of their own

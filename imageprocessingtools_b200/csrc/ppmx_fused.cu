@@ -1,0 +1,388 @@
+// ppmx_fused.cu -- one kernel for "geometry + pointwise tail": any of the eight orientations a chain of flips (ref:898-911)
+// and 90/180/270 degree rotations (ref:714-725) composes to, followed by nothing, grey (ref:998-1000), the writer's .r
+// extraction (ref:263-267) or mono with the P4 packer (ref:964-969 + 268-284) -- one read of the source, one write of
+// what the writer emits, at ANY raster size and pointer alignment.  "ref:N" = /root/reference/ppmx-edward.c line N.
+//
+// A CTA moves one 64 x 64 pixel tile:
+//   1. the tile's source rows come into shared memory as raw interleaved bytes -- by the bulk-copy engine
+//      (cp.async.bulk + mbarrier) when rows are 16-byte aligned, else as aligned 32-bit words whose leading 0..3
+//      bytes of misalignment are kept in the staged row and undone when pixels are cut out;
+//   2. a thread takes 16 pixels -- down one source COLUMN for the four transposing orientations, along one source
+//      ROW for the others --, applies the pointwise tail and writes them where they belong in an output tile in
+//      shared memory (reversed when the orientation mirrors that axis);
+//   3. the output tile's rows leave by the bulk-copy engine (16-byte aligned destination rows), as 8-byte vectors
+//      (8-byte aligned, e.g. a 1080-pixel-wide result), or as aligned words assembled by a funnel shift with the
+//      row ends written byte by byte (anything else).
+// The Bayer index of mono, (x%4)*4 + (y%4) (ref:967), is taken in the coordinates of the stage where mono sits in
+// the chain; the host passes that stage's coordinates as a signed permutation of the source coordinates.
+#include "ppmx_common.cuh"
+
+namespace ppmx {
+
+constexpr int GI_PITCH = 208;  // staged source row: 192 B of pixels + up to 3 B of misalignment, 52 words (rows spread over banks)
+constexpr int GO_PITCH = 240;  // output tile row (RGB): 192 B + up to 45 B of front pad; 60 words: 16-byte stores of 8 rows never collide
+constexpr int GO_PITCH_R8 = 80;
+constexpr int GO_PITCH_BITS = 16;
+
+enum { GP_RGB = 0, GP_GRAY = 1, GP_RED = 2, GP_MONO = 3 };
+enum { GL_BULK = 0, GL_WORDS = 1 };
+enum { GS_BULK = 0, GS_VEC8 = 1, GS_SHIFT = 2 };
+
+__device__ __forceinline__ uint32_t gs_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int POINT>
+struct GeomOut {
+    static constexpr int pitch = POINT == GP_RGB ? GO_PITCH : POINT == GP_MONO ? GO_PITCH_BITS : GO_PITCH_R8;
+};
+
+// a row piece of `nbytes` bytes from shared memory (16-byte aligned row, piece at byte `soff`) to any global address
+template <int STORE>
+__device__ __forceinline__ void store_piece(uint8_t *g, const uint8_t *srow, uint32_t soff, uint32_t nbytes, uint32_t lane)
+{
+    if (STORE == GS_VEC8) {  // g, soff and nbytes are multiples of 8
+        const uint2 *s = reinterpret_cast<const uint2 *>(srow + soff);
+        for (uint32_t k = lane; k < nbytes / 8u; k += 32u) reinterpret_cast<uint2 *>(g)[k] = s[k];
+        return;
+    }
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u), nwords = (a + nbytes + 3u) >> 2;
+    uint32_t *gw = reinterpret_cast<uint32_t *>(g - a);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(srow);
+    for (uint32_t k = lane; k < nwords; k += 32u) {
+        const int p = (int)(4u * k) - (int)a;  // position in the piece of this destination word's first byte
+        if (p >= 0 && (uint32_t)p + 4u <= nbytes) {
+            const uint32_t q = soff + (uint32_t)p, w0 = sw[q >> 2], w1 = (q & 3u) ? sw[(q >> 2) + 1] : 0u;
+            gw[k] = __funnelshift_r(w0, w1, 8u * (q & 3u));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int q = p + j;
+                if (q >= 0 && (uint32_t)q < nbytes) (reinterpret_cast<uint8_t *>(gw))[4u * k + j] = srow[soff + q];
+            }
+        }
+    }
+}
+
+// TRANSPOSE 1: out row <- source column x (REV_Y: row w-1-x), out pixel <- source row y (REV_X: pixel h-1-y)
+//           0: out row <- source row y    (REV_Y: row h-1-y), out pixel <- source column x (REV_X: pixel w-1-x)
+template <int TRANSPOSE, bool REV_X, int POINT, int LOAD, int STORE>
+__global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t w,
+                                                   uint32_t h, uint32_t in_pitch, uint32_t out_pitch, const GeomOp go)
+{
+    pdl_trigger();
+    constexpr int OP = GeomOut<POINT>::pitch;
+    __shared__ __align__(128) uint8_t tin[64 * GI_PITCH];
+    __shared__ __align__(128) uint8_t tout[64 * OP];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tx0 = blockIdx.x * 64u, ty0 = blockIdx.y * 64u;
+    const uint32_t nc = min(64u, w - tx0), nr = min(64u, h - ty0);
+    const uintptr_t g0 = reinterpret_cast<uintptr_t>(src) + (size_t)ty0 * in_pitch + (size_t)tx0 * 3;
+    const uint32_t a0 = LOAD == GL_BULK ? 0u : (uint32_t)(g0 & 3u), ap = LOAD == GL_BULK ? 0u : (in_pitch & 3u);
+
+    // ---- 1. the tile's source rows -> tin ------------------------------------------------------------------
+    if (LOAD == GL_BULK) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs_smem(&bar)), "r"(1) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        pdl_wait();
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs_smem(&bar)), "r"(nr * nc * 3u) : "memory");
+        const uint32_t crow = warp * 16u + (lane & 15u);  // a bulk copy is issued per warp: 16 per warp on all four warps
+        if (lane < 16u && crow < nr)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             gs_smem(tin + crow * GI_PITCH)),
+                         "l"(g0 + (size_t)crow * in_pitch), "r"(nc * 3u), "r"(gs_smem(&bar))
+                         : "memory");
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"(gs_smem(&bar)),
+            "r"(0)
+            : "memory");
+    } else {
+        pdl_wait();
+        // aligned words covering [g, g + 3 nc): the row's 0..3 bytes of misalignment stay in front of it in tin
+#pragma unroll 1
+        for (uint32_t r4 = 0; r4 < 16u; r4 += 4u) {
+            uint32_t v[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t r = warp * 16u + r4 + u;
+                const uintptr_t g = g0 + (size_t)r * in_pitch;
+                const uint32_t a = (uint32_t)(g & 3u), nwords = r < nr ? (a + nc * 3u + 3u) >> 2 : 0u;
+                const uint32_t *gw = reinterpret_cast<const uint32_t *>(g - a);
+                v[u][0] = lane < nwords ? __ldg(gw + lane) : 0u;
+                v[u][1] = lane + 32u < nwords ? __ldg(gw + lane + 32u) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                uint32_t *trow = reinterpret_cast<uint32_t *>(tin + (warp * 16u + r4 + u) * GI_PITCH);
+                trow[lane] = v[u][0];
+                if (lane < 20u) trow[lane + 32u] = v[u][1];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- 2. 16 pixels per thread, pointwise tail, into the output tile --------------------------------------
+    // the piece of an output row this tile holds starts `pad` pixels into the tout row when the pixel axis is mirrored
+    // and the tile is ragged, so that the 16-pixel blocks of a thread never start before the row
+    const uint32_t npx = TRANSPOSE ? nr : nc;  // pixels per output row piece
+    const uint32_t pad = REV_X ? (16u - (npx & 15u)) & 15u : 0u;
+    const uint32_t *tin32 = reinterpret_cast<const uint32_t *>(tin);
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        // TRANSPOSE: lane = source column, 16-row group j.   else: source row, 16-pixel group j.
+        const uint32_t fix = TRANSPOSE ? lane + 32u * (warp & 1u) : (tid >> 2) + 32u * pass;
+        const uint32_t j = TRANSPOSE ? (warp >> 1) + 2u * pass : (tid & 3u);
+        if (TRANSPOSE ? (fix >= nc || 16u * j >= nr) : (fix >= nr || 16u * j >= nc)) continue;
+        uint32_t px[16];  // r g b x per pixel (TRANSPOSE) ...
+        uint32_t rw12[12];  // ... or 16 packed pixels (row-wise)
+        if (TRANSPOSE) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t r = 16u * j + k, off = ((a0 + r * ap) & 3u) + 3u * fix;
+                const uint32_t *p = tin32 + r * (GI_PITCH / 4) + (off >> 2);
+                px[k] = __funnelshift_r(p[0], p[1], (off & 3u) * 8u);
+            }
+        } else {
+            const uint32_t off = (a0 + fix * ap) & 3u;
+            const uint32_t *p = tin32 + fix * (GI_PITCH / 4) + 12u * j;
+#pragma unroll
+            for (int i = 0; i < 12; i++) rw12[i] = __funnelshift_r(p[i], p[i + 1], off * 8u);
+        }
+        // where the 16 pixels go: tout row `orow`, pixel block `oblk` of that row's piece (+ pad)
+        const uint32_t orow = fix;
+        const uint32_t oblk = REV_X ? (npx + pad) - 16u - 16u * j : 16u * j;
+        if (POINT == GP_RGB) {
+            uint32_t o[12];
+            if (TRANSPOSE) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {  // 4 pixels -> 3 words
+                    const uint32_t p0 = REV_X ? px[15 - 4 * i] : px[4 * i], p1 = REV_X ? px[14 - 4 * i] : px[4 * i + 1];
+                    const uint32_t p2 = REV_X ? px[13 - 4 * i] : px[4 * i + 2], p3 = REV_X ? px[12 - 4 * i] : px[4 * i + 3];
+                    o[3 * i] = __byte_perm(p0, p1, 0x4210);
+                    o[3 * i + 1] = __byte_perm(p1, p2, 0x5421);
+                    o[3 * i + 2] = __byte_perm(p2, p3, 0x6542);
+                }
+            } else if (REV_X) {
+#pragma unroll
+                for (int kk = 0; kk < 12; kk++) {  // reverse the order of 16 packed pixels
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int ob = 4 * kk + b, ib = 3 * (15 - ob / 3) + (ob % 3);
+                        v |= ((rw12[ib >> 2] >> (8 * (ib & 3))) & 0xFFu) << (8 * b);
+                    }
+                    o[kk] = v;
+                }
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 12; kk++) o[kk] = rw12[kk];
+            }
+            uint8_t *q = tout + orow * OP + oblk * 3u;  // 48-byte blocks: 16-byte aligned whenever pad * 3 is
+            if (((pad * 3u) & 15u) == 0u) {
+                uint4 *q4 = reinterpret_cast<uint4 *>(q);
+                q4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                q4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                q4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+            } else if (((pad * 3u) & 3u) == 0u) {
+#pragma unroll
+                for (int kk = 0; kk < 12; kk++) reinterpret_cast<uint32_t *>(q)[kk] = o[kk];
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 12; kk++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) q[4 * kk + b] = (uint8_t)(o[kk] >> (8 * b));
+            }
+        } else {
+            // grey / red / Bayer bit of the 16 pixels, in SOURCE order along the thread's run
+            uint32_t val[16];
+            int thr3[4] = {0, 0, 0, 0};
+            if (POINT == GP_MONO) {
+                // run coordinate u = 16 j' + i has u % 4 == i % 4 (tiles start at multiples of 64); the other one is `fix`
+                const uint32_t run0 = TRANSPOSE ? ty0 : tx0, fixc = (TRANSPOSE ? tx0 : ty0) + fix;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t sx = TRANSPOSE ? fixc : run0 + i, sy = TRANSPOSE ? run0 + i : fixc;  // source x, y (mod 4 is all that counts)
+                    const uint32_t cx = go.mx_from_y ? sy : sx, cy = go.mx_from_y ? sx : sy;
+                    const uint32_t xm = ((go.mx_neg ? 0u - cx : cx) + (uint32_t)go.mx_add) & 3u;
+                    const uint32_t ym = ((go.my_neg ? 0u - cy : cy) + (uint32_t)go.my_add) & 3u;
+                    thr3[i] = -3 * (int)c_bayer[xm * 4u + ym];
+                }
+            }
+            if (TRANSPOSE) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if (POINT == GP_GRAY) val[k] = div3(__dp4a(px[k], 0x00010101u, 0u));
+                    else if (POINT == GP_RED) val[k] = px[k] & 0xFFu;
+                    else val[k] = ((int)__dp4a(px[k], 0x00010101u, (uint32_t)thr3[k & 3]) < 0) ? 1u : 0u;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {  // 4 pixels in 3 words
+                    const uint32_t a = rw12[3 * i], b = rw12[3 * i + 1], c = rw12[3 * i + 2];
+                    const uint32_t t0 = POINT == GP_MONO ? (uint32_t)thr3[0] : 0u, t1 = POINT == GP_MONO ? (uint32_t)thr3[1] : 0u;
+                    const uint32_t t2 = POINT == GP_MONO ? (uint32_t)thr3[2] : 0u, t3 = POINT == GP_MONO ? (uint32_t)thr3[3] : 0u;
+                    if (POINT == GP_RED) {
+                        val[4 * i] = a & 0xFFu;
+                        val[4 * i + 1] = a >> 24;
+                        val[4 * i + 2] = (b >> 16) & 0xFFu;
+                        val[4 * i + 3] = (c >> 8) & 0xFFu;
+                    } else {
+                        const uint32_t s0 = __dp4a(a, 0x00010101u, t0), s1 = __dp4a(a, 0x01000000u, __dp4a(b, 0x00000101u, t1));
+                        const uint32_t s2 = __dp4a(b, 0x01010000u, __dp4a(c, 0x00000001u, t2)), s3 = __dp4a(c, 0x01010100u, t3);
+                        if (POINT == GP_GRAY) {
+                            val[4 * i] = div3(s0);
+                            val[4 * i + 1] = div3(s1);
+                            val[4 * i + 2] = div3(s2);
+                            val[4 * i + 3] = div3(s3);
+                        } else {
+                            val[4 * i] = s0 >> 31;
+                            val[4 * i + 1] = s1 >> 31;
+                            val[4 * i + 2] = s2 >> 31;
+                            val[4 * i + 3] = s3 >> 31;
+                        }
+                    }
+                }
+            }
+            if (POINT == GP_MONO) {
+                uint32_t bits = 0;  // first OUTPUT pixel in the most significant bit (ref:273)
+#pragma unroll
+                for (int k = 0; k < 16; k++) bits |= val[REV_X ? 15 - k : k] << (15 - k);
+                // pixels of this block beyond the raster's edge (a ragged last tile) are pad bits: zero (ref:268-284)
+                const uint32_t valid = min(16u, npx - 16u * j);
+                if (valid < 16u) bits &= REV_X ? (0xFFFFu >> (16u - valid)) : (0xFFFFu << (16u - valid));
+                uint8_t *q = tout + orow * OP + (oblk >> 3);
+                q[0] = (uint8_t)(bits >> 8);
+                q[1] = (uint8_t)bits;
+            } else {
+                uint32_t o[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const int i0 = REV_X ? 15 - 4 * kk : 4 * kk, st = REV_X ? -1 : 1;
+                    o[kk] = val[i0] | (val[i0 + st] << 8) | (val[i0 + 2 * st] << 16) | (val[i0 + 3 * st] << 24);
+                }
+                uint8_t *q = tout + orow * OP + oblk;
+                if ((pad & 15u) == 0u) *reinterpret_cast<uint4 *>(q) = make_uint4(o[0], o[1], o[2], o[3]);
+                else if ((pad & 3u) == 0u) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) reinterpret_cast<uint32_t *>(q)[kk] = o[kk];
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) q[4 * kk + b] = (uint8_t)(o[kk] >> (8 * b));
+                }
+            }
+        }
+    }
+    if (STORE == GS_BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the bulk engine must see the tile
+    __syncthreads();
+
+    // ---- 3. the output tile's rows -> dst -----------------------------------------------------------------------
+    const uint32_t nrows_out = TRANSPOSE ? nc : nr;                       // rows of the output tile
+    const uint32_t out_w = TRANSPOSE ? h : w, run0 = TRANSPOSE ? ty0 : tx0;
+    const uint32_t xs = REV_X ? out_w - run0 - npx : run0;                // first output pixel of every row piece
+    const uint32_t row0 = TRANSPOSE ? tx0 : ty0, out_h = TRANSPOSE ? w : h;
+    uint32_t pbytes, soff;
+    size_t goff;
+    if (POINT == GP_RGB) {
+        pbytes = npx * 3u, soff = pad * 3u, goff = (size_t)xs * 3;
+    } else if (POINT == GP_MONO) {
+        pbytes = (npx + 7u) >> 3, soff = pad >> 3, goff = xs >> 3;
+    } else {
+        pbytes = npx, soff = pad, goff = xs;
+    }
+    if (STORE == GS_BULK) {
+        const uint32_t crow = warp * 16u + (lane & 15u);
+        if (lane < 16u && crow < nrows_out) {
+            const uint32_t y = go.rev_y ? out_h - 1u - (row0 + crow) : row0 + crow;
+            uint8_t *g = dst + (size_t)y * out_pitch + goff;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(gs_smem(tout + crow * OP + soff)),
+                         "r"(pbytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may go once it has been read
+        }
+    } else {
+#pragma unroll 1
+        for (uint32_t rr = 0; rr < 16u; rr++) {
+            const uint32_t crow = warp * 16u + rr;
+            if (crow >= nrows_out) break;
+            const uint32_t y = go.rev_y ? out_h - 1u - (row0 + crow) : row0 + crow;
+            store_piece<STORE>(dst + (size_t)y * out_pitch + goff, tout + crow * OP, soff, pbytes, lane);
+        }
+    }
+}
+
+template <int TRANSPOSE, bool REV_X, int POINT>
+static cudaError_t geom_launch(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t in_pitch, uint32_t out_pitch,
+                               const GeomOp &go, cudaStream_t s)
+{
+    const uint32_t out_w = TRANSPOSE ? h : w;
+    const bool bulk_in = aligned16(src) && (in_pitch % 16u) == 0 && (w % 16u) == 0;
+    int store = GS_SHIFT;
+    if (POINT == GP_RGB) {
+        if (aligned16(dst) && (out_pitch % 16u) == 0 && (out_w % 16u) == 0) store = GS_BULK;
+        else if ((reinterpret_cast<uintptr_t>(dst) & 7u) == 0 && (out_pitch % 8u) == 0 && (out_w % 8u) == 0) store = GS_VEC8;
+    } else if (POINT != GP_MONO && aligned16(dst) && (out_pitch % 16u) == 0 && (out_w % 16u) == 0) {
+        store = GS_BULK;
+    }
+    dim3 grid((w + 63) / 64, (h + 63) / 64);
+    if (grid.y > 65535u) return cudaErrorInvalidValue;
+#define PPMX_GEOM(L, S) launch(geom_kernel<TRANSPOSE, REV_X, POINT, L, S>, grid, dim3(128), 0, s, src, dst, w, h, in_pitch, out_pitch, go)
+    if (bulk_in) {
+        if (store == GS_BULK) PPMX_GEOM(GL_BULK, GS_BULK);
+        else if (store == GS_VEC8) PPMX_GEOM(GL_BULK, GS_VEC8);
+        else PPMX_GEOM(GL_BULK, GS_SHIFT);
+    } else {
+        if (store == GS_BULK) PPMX_GEOM(GL_WORDS, GS_BULK);
+        else if (store == GS_VEC8) PPMX_GEOM(GL_WORDS, GS_VEC8);
+        else PPMX_GEOM(GL_WORDS, GS_SHIFT);
+    }
+#undef PPMX_GEOM
+    return PPMX_LAUNCHED();
+}
+
+bool geom_point_supported(uint32_t w, uint32_t h, const GeomOp &go)
+{
+    if (go.point == GP_MONO) {
+        // packed bits: a mirrored pixel axis must start on a byte boundary of the output row
+        const uint32_t out_w = go.transpose ? h : w;
+        if (go.rev_x && (out_w % 8u) != 0) return false;
+    }
+    return w > 0 && h > 0;
+}
+
+cudaError_t geom_point(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t in_pitch, const GeomOp &go, cudaStream_t s)
+{
+    if (!w || !h) return cudaSuccess;
+    if (!geom_point_supported(w, h, go)) return cudaErrorInvalidValue;
+    const uint32_t out_w = go.transpose ? h : w;
+    const uint32_t out_pitch = go.point == GP_RGB ? out_w * 3u : go.point == GP_MONO ? (out_w + 7u) / 8u : out_w;
+    if (!in_pitch) in_pitch = w * 3u;
+#define PPMX_GEOM_P(T, R)                                                                          \
+    switch (go.point) {                                                                            \
+    case GP_RGB: return geom_launch<T, R, GP_RGB>(src, dst, w, h, in_pitch, out_pitch, go, s);     \
+    case GP_GRAY: return geom_launch<T, R, GP_GRAY>(src, dst, w, h, in_pitch, out_pitch, go, s);   \
+    case GP_RED: return geom_launch<T, R, GP_RED>(src, dst, w, h, in_pitch, out_pitch, go, s);     \
+    case GP_MONO: return geom_launch<T, R, GP_MONO>(src, dst, w, h, in_pitch, out_pitch, go, s);   \
+    default: return cudaErrorInvalidValue;                                                         \
+    }
+    if (go.transpose) {
+        if (go.rev_x) { PPMX_GEOM_P(1, true) } else { PPMX_GEOM_P(1, false) }
+    } else {
+        if (go.rev_x) { PPMX_GEOM_P(0, true) } else { PPMX_GEOM_P(0, false) }
+    }
+#undef PPMX_GEOM_P
+}
+
+}  // namespace ppmx

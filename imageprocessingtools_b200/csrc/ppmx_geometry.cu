@@ -504,6 +504,15 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
         }
         return PPMX_LAUNCHED();
     }
+    if (PPMX_VARIANT == 0) {
+        // any size, any alignment (1920 x 1080 frames: height no multiple of 16): the tile kernel of ppmx_fused.cu, rows in
+        // by bulk copy or aligned words, out as 8-byte vectors or shifted words
+        GeomOp go = {};
+        go.transpose = 1;
+        go.rev_x = angle == 90;   // out[x][h-1-y] = in[y][x], ref:717
+        go.rev_y = angle == 270;  // out[w-1-x][y] = in[y][x], ref:725
+        return geom_point(src, dst, w, h, 0, go, s);
+    }
     if (PPMX_VARIANT != 1) {
         dim3 ga((w + RA - 1) / RA, (h + RA - 1) / RA);
         if (ga.y > 65535u) return cudaErrorInvalidValue;

@@ -519,6 +519,96 @@ int ppmx_parse_header(const unsigned char *file, size_t filesize, unsigned int *
     return PPMX_OK;
 }
 
+/* ------------------------------------------------------------------ EXTENSION: P3 and 16-bit input
+ * The reference reads binary P6 with one byte per sample only (ref:386 accepts the word "P6" alone, ref:453 demands
+ * width * height * 3 bytes after the header).  The two other PPM encodings are decoded here, on the host, into the
+ * same packed 8-bit raster; no reference counterpart, no oracle beyond tests/test_host_logic.py.
+ *   P3           ASCII decimal samples separated by white space, '#' comments run to the end of the line
+ *   maxval > 255 two bytes per sample, most significant first (P6), or larger decimals (P3)
+ * Samples above maxval are clamped to it.  maxval <= 255: bytes are taken as they are and the header's maxval is
+ * written back unchanged, exactly like the reference treats P6 (ref:259).  maxval > 255: samples are scaled to
+ * 0..255 with the reference's round() (floor(x + 0.5), ref:27) in integers and the result is written as maxval 255. */
+
+static int pnm_skip_space(const unsigned char *f, size_t n, size_t *i)
+{
+    while (*i < n) {
+        if (f[*i] == '#') { while (*i < n && f[*i] != '\n') (*i)++; }
+        else if (isspace(f[*i])) (*i)++;
+        else return 1;
+    }
+    return 0;
+}
+
+static int pnm_number(const unsigned char *f, size_t n, size_t *i, unsigned int *v)
+{
+    unsigned long long t = 0;
+    int digits = 0;
+    if (!pnm_skip_space(f, n, i)) return 0;
+    while (*i < n && isdigit(f[*i])) {
+        t = t * 10 + (unsigned)(f[*i] - '0');
+        if (t > 0xFFFFFFFFull) return 0;
+        (*i)++;
+        digits++;
+    }
+    *v = (unsigned int)t;
+    return digits > 0;
+}
+
+int ppmx_probe_pnm(const unsigned char *file, size_t filesize, unsigned int *width, unsigned int *height,
+                   unsigned int *max_color, size_t *raster_offset, int *format)
+{
+    size_t i = 2, need;
+    int p3;
+    if (filesize < 2 || file[0] != 'P' || (file[1] != '3' && file[1] != '6')) BAIL("error. invalid file format.\n"); /* ref:417 */
+    p3 = file[1] == '3';
+    if (!pnm_number(file, filesize, &i, width)) BAIL("error. invalid file format. unable to parse width from input file.\n");
+    if (!pnm_number(file, filesize, &i, height)) BAIL("error. invalid file format. unable to parse height from input file.\n");
+    if (!pnm_number(file, filesize, &i, max_color))
+        BAIL("error. invalid file format. unable to parse maximum color from input file.\n");
+    if (*max_color < 1 || *max_color > 65535) BAIL("error. invalid file format. unable to parse maximum color from input file.\n");
+    if (p3) {
+        *format = PPMX_PNM_P3;
+        *raster_offset = i;
+        return PPMX_OK;
+    }
+    if (i >= filesize || !isspace(file[i])) BAIL("file format error\n"); /* one white-space byte ends the header */
+    i++;
+    need = (size_t)(*width) * (size_t)(*height) * 3 * (*max_color > 255 ? 2 : 1);
+    if (i + need != filesize) BAIL("file format error\n"); /* ref:453 */
+    *format = *max_color > 255 ? PPMX_PNM_P6_16 : PPMX_PNM_P6_8;
+    *raster_offset = i;
+    return PPMX_OK;
+}
+
+int ppmx_decode_pnm(const unsigned char *file, size_t filesize, size_t raster_offset, int format, unsigned int width,
+                    unsigned int height, unsigned int max_color, unsigned char *dst, unsigned int *out_max_color)
+{
+    const size_t n = (size_t)width * height * 3;
+    const unsigned int scale = max_color > 255;
+    size_t i = raster_offset, k;
+    *out_max_color = scale ? 255u : max_color;
+    for (k = 0; k < n; k++) {
+        unsigned int v;
+        if (format == PPMX_PNM_P3) {
+            if (!pnm_number(file, filesize, &i, &v)) BAIL("Error: unexpected end of file.\n"); /* ref:315 */
+        } else if (format == PPMX_PNM_P6_16) {
+            if (i + 2 > filesize) BAIL("Error: unexpected end of file.\n");
+            v = ((unsigned int)file[i] << 8) | file[i + 1];
+            i += 2;
+        } else {
+            if (i + 1 > filesize) BAIL("Error: unexpected end of file.\n");
+            v = file[i++];
+        }
+        if (v > max_color) v = max_color;
+        /* round(v * 255 / maxval) with round(x) = floor(x + 0.5) (ref:27), in integers */
+        dst[k] = (unsigned char)(scale ? (2ull * v * 255u + max_color) / (2ull * max_color) : v);
+    }
+    if (format == PPMX_PNM_P3) { /* nothing but white space and comments may follow the last sample (cf. ref:453) */
+        if (pnm_skip_space(file, filesize, &i)) BAIL("file format error\n");
+    }
+    return PPMX_OK;
+}
+
 int ppmx_format_header(char *dst, size_t cap, int file_type, unsigned int width, unsigned int height,
                        unsigned int max_color)
 {
@@ -609,12 +699,22 @@ int ppmx_putImageToFile(ppmx_image_handler *h)
     return rc;
 }
 
+/* "P6", then a maxval above 255: two bytes per sample (the reference fails its size check on such a file, ref:453) */
+static int pnm_is_16bit(const unsigned char *f, size_t n)
+{
+    size_t i = 2;
+    unsigned int w, hh, mx;
+    if (n < 2 || f[0] != 'P' || f[1] != '6') return 0;
+    return pnm_number(f, n, &i, &w) && pnm_number(f, n, &i, &hh) && pnm_number(f, n, &i, &mx) && mx > 255 && mx <= 65535;
+}
+
 int ppmx_doProcessPPM(ppmx_image_handler *h)
 {
     ppmx_plan plan;
     unsigned int w = 0, hh = 0, mx = 0, ow = 0, oh = 0;
     size_t off = 0, cap, n = 0, i;
-    unsigned char *out = NULL;
+    unsigned char *out = NULL, *decoded = NULL;
+    const unsigned char *raster = NULL;
     int own_ctx = 0, ft = PPMX_FILETYPE_PPM, rc = PPMX_ERROR;
 
     memset(&plan, 0, sizeof(plan));
@@ -624,7 +724,17 @@ int ppmx_doProcessPPM(ppmx_image_handler *h)
         own_ctx = 1;
     }
     if (read_whole_file(h) != PPMX_OK) goto done;
-    if (ppmx_parse_header(h->file_buffer, h->filesize, &w, &hh, &mx, &off) != PPMX_OK) goto done;
+    raster = h->file_buffer;
+    if (h->filesize >= 2 && h->file_buffer[0] == 'P' && (h->file_buffer[1] == '3' || pnm_is_16bit(h->file_buffer, h->filesize))) {
+        /* EXTENSION: an encoding the reference rejects (ref:386, 453) is decoded on the host into the same raster */
+        int fmt = 0;
+        if (ppmx_probe_pnm(h->file_buffer, h->filesize, &w, &hh, &mx, &off, &fmt) != PPMX_OK) goto done;
+        decoded = (unsigned char *)ppmx_gpu_host_alloc(h->ctx, (size_t)w * hh * 3 + 1);
+        if (!decoded) { printf("error. can not allocate memory\n"); goto done; }
+        if (ppmx_decode_pnm(h->file_buffer, h->filesize, off, fmt, w, hh, mx, decoded, &mx) != PPMX_OK) goto done;
+        raster = decoded;
+        off = 0;
+    } else if (ppmx_parse_header(h->file_buffer, h->filesize, &w, &hh, &mx, &off) != PPMX_OK) goto done;
     h->imginfo.width = w; h->imginfo.height = hh; h->imginfo.max_color = mx; h->index_buffer = off;
 
     if (ppmx_plan_chain_ext2(&h->arg_flag, h->output_width_size, h->angle, w, hh, h->conv_preset,
@@ -642,13 +752,14 @@ int ppmx_doProcessPPM(ppmx_image_handler *h)
     out = (unsigned char *)ppmx_gpu_host_alloc(h->ctx, cap);
     if (!out) { printf("error. can not allocate memory\n"); goto done; }
 
-    if (ppmx_gpu_apply(h->ctx, plan.ops, plan.nops, h->file_buffer + off, w, hh, out, cap, &n, &ow, &oh, &ft) != PPMX_OK)
+    if (ppmx_gpu_apply(h->ctx, plan.ops, plan.nops, raster + off, w, hh, out, cap, &n, &ow, &oh, &ft) != PPMX_OK)
         goto done;
     h->imginfo.new_width = ow; h->imginfo.new_height = oh; h->imginfo.file_type = (unsigned int)ft;
     rc = write_output(h->filename, ft, ow, oh, mx, out, n);
 done:
     ppmx_plan_free(&plan);
     if (out) ppmx_gpu_host_free(h->ctx, out);
+    if (decoded) ppmx_gpu_host_free(h->ctx, decoded);
     if (h->file_buffer) { ppmx_gpu_host_free(h->ctx, h->file_buffer); h->file_buffer = NULL; }
     if (own_ctx) { ppmx_gpu_free(h->ctx); h->ctx = NULL; }
     return rc;

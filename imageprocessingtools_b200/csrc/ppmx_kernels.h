@@ -49,6 +49,20 @@ cudaError_t imresize(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, i
 cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef /*host*/,
                  int32_t div, int32_t bias, const Band &band, cudaStream_t s);
 
+// Geometry + pointwise tail in one pass (ppmx_fused.cu).  Output pixel (X, Y) = point(source pixel (x, y)):
+//   transpose 0: x = rev_x ? w-1-X : X,  y = rev_y ? h-1-Y : Y          (flips, 180 degrees)
+//   transpose 1: y = rev_x ? h-1-X : X,  x = rev_y ? w-1-Y : Y          (90 / 270 degrees, with or without a flip)
+// point: 0 RGB8 -> RGB8, 1 grey -> R8 (ref:1000), 2 .r -> R8 (ref:263-267), 3 mono -> packed bits (ref:964-969 + 268-284),
+// whose Bayer index (xm%4)*4 + (ym%4) is taken at xm = +-(mx_from_y ? y : x) + mx_add, ym = +-(mx_from_y ? x : y) + my_add.
+struct GeomOp {
+    int transpose, rev_x, rev_y, point;
+    int mx_from_y, mx_neg, mx_add, my_neg, my_add;
+};
+bool geom_point_supported(uint32_t w, uint32_t h, const GeomOp &go);
+// in_pitch: bytes between source rows (0 = 3 * w; larger for a column slab of a wider raster)
+cudaError_t geom_point(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t in_pitch, const GeomOp &go,
+                       cudaStream_t s);
+
 // every byte of the raster through a 256-entry table (host pointer)
 cudaError_t levels(const uint8_t *src, uint8_t *dst, size_t nbytes, const uint8_t *lut /*host*/, cudaStream_t s);
 

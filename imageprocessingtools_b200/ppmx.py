@@ -174,6 +174,9 @@ def host_lib() -> C.CDLL:
         H.ppmx_band_plan.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, _u32p, _u32p]
         H.ppmx_parse_header.argtypes = [C.c_char_p, C.c_size_t, _u32p, _u32p, _u32p, C.POINTER(C.c_size_t)]
         H.ppmx_format_header.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_uint]
+        H.ppmx_probe_pnm.argtypes = [C.c_char_p, C.c_size_t, _u32p, _u32p, _u32p, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+        H.ppmx_decode_pnm.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_void_p,
+                                      _u32p]
         H.ppmx_synth_lcg.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32]
         H.ppmx_synth_lcg.restype = None
         _host = H
@@ -263,6 +266,21 @@ def parse_header(data: bytes):
     if rc != 0:
         raise PpmxError("ppmx_parse_header failed")
     return w.value, h.value, m.value, off.value
+
+
+def decode_pnm(data: bytes):
+    """EXTENSION (ppmx_probe_pnm + ppmx_decode_pnm): a P3 or P6 file of any maxval -> ((h, w, 3) uint8, out maxval)."""
+    H = host_lib()
+    w, h, m, fmt = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_int()
+    off = C.c_size_t()
+    if H.ppmx_probe_pnm(data, len(data), C.byref(w), C.byref(h), C.byref(m), C.byref(off), C.byref(fmt)) != 0:
+        raise PpmxError("ppmx_probe_pnm failed")
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    om = C.c_uint32()
+    if H.ppmx_decode_pnm(data, len(data), off.value, fmt.value, w.value, h.value, m.value,
+                         C.c_void_p(out.ctypes.data), C.byref(om)) != 0:
+        raise PpmxError("ppmx_decode_pnm failed")
+    return out, om.value
 
 
 def format_header(file_type: int, w: int, h: int, maxval: int = 255) -> bytes:

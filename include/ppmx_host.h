@@ -120,6 +120,18 @@ void ppmx_plan_free(ppmx_plan *plan);
  * of the raster.  Same acceptance rules and messages (P6 only, comments, exact size). */
 int ppmx_parse_header(const unsigned char *file, size_t filesize, unsigned int *width,
                       unsigned int *height, unsigned int *max_color, size_t *raster_offset);
+/* EXTENSION (the reference rejects both, ref:386, 453): ASCII P3 and 16-bit samples.  probe reads the header of a
+ * P3 or P6 file of any maxval 1..65535; decode writes width * height * 3 bytes to dst -- samples as they are for
+ * maxval <= 255 (header maxval kept, like the reference does for P6, ref:259), scaled to 0..255 with
+ * round(v * 255 / maxval) (ref:27 rounding, in integers) for larger maxvals (*out_max_color = 255). */
+#define PPMX_PNM_P6_8 0
+#define PPMX_PNM_P6_16 1
+#define PPMX_PNM_P3 2
+int ppmx_probe_pnm(const unsigned char *file, size_t filesize, unsigned int *width, unsigned int *height,
+                   unsigned int *max_color, size_t *raster_offset, int *format);
+int ppmx_decode_pnm(const unsigned char *file, size_t filesize, size_t raster_offset, int format, unsigned int width,
+                    unsigned int height, unsigned int max_color, unsigned char *dst, unsigned int *out_max_color);
+
 /* Header text of ref:239-261 ("# generated by ppmx_edward"); returns its length. */
 int ppmx_format_header(char *dst, size_t cap, int file_type, unsigned int width,
                        unsigned int height, unsigned int max_color);

@@ -1,0 +1,82 @@
+"""GPU parity of the fused "geometry + pointwise tail" kernel (csrc/ppmx_fused.cu) and of the chain fusion pass:
+every orientation x every tail, at aligned and ragged sizes, against the oracle's stage-by-stage result; the fused
+chain must equal the unfused one byte for byte."""
+import os
+
+import numpy as np
+import pytest
+
+import patterns as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import imageprocessingtools_b200 as ip
+    g = ip.Ppmx(0)
+    yield g
+    g.close()
+
+
+SIZES = [(64, 64), (128, 64), (64, 192), (16, 16), (80, 48), (1, 1), (3, 5), (37, 23), (130, 70), (200, 56), (96, 1080 // 8),
+         (257, 129), (72, 40), (8, 8), (24, 136)]
+FUSED_CHAINS = [dict(angle=90, mono=True, fliph=True), dict(angle=90, gray=True, flipv=True), dict(angle=270, gray=True, fliph=True),
+                dict(angle=180, mono=True, flipv=True), dict(angle=90, flipv=True), dict(angle=270, fliph=True),
+                dict(angle=180, gray=True), dict(angle=90, gray=True), dict(angle=270, mono=True), dict(angle=90, mono=True),
+                dict(angle=90, mono=True, flipv=True), dict(angle=270, mono=True, fliph=True), dict(angle=180, mono=True, fliph=True),
+                dict(angle=90), dict(angle=270), dict(gray=True, fliph=True), dict(gray=True, flipv=True),
+                dict(angle=180, fliph=True), dict(angle=180, flipv=True)]
+
+
+def test_fused_chains_match_oracle(gpu, orc):
+    import imageprocessingtools_b200.ppmx as pp
+    fused_seen = 0
+    for (w, h) in SIZES:
+        for name in ("lcg", "bayer"):
+            img = P.all_patterns(w, h)[name]
+            for kw in FUSED_CHAINS:
+                exp, ew, eh, eft = orc.process(img, **kw)
+                got, gw, gh, gft = gpu.process(img, **kw)
+                assert (gw, gh, gft) == (ew, eh, eft), (w, h, name, kw)
+                assert np.array_equal(got, exp), (w, h, name, kw)
+                ph = pp._PlanHolder(w=w, h=h, **kw)
+                ops = [ph.plan.ops[i] for i in range(ph.plan.nops)]
+                fused_seen += pp.chain_info(ops, w, h)[5] == 1
+                ph.close()
+    assert fused_seen > 100  # most of these chains are ONE kernel
+
+
+def test_config5_chains_kernel_counts(gpu, orc):
+    """BASELINE config 5 chains on a 1920x1080 frame: "-r90 -mono -fh" is one kernel, "-w960 -r90 -gray -fv" three."""
+    import imageprocessingtools_b200.ppmx as pp
+    img = P.lcg(1920, 1080, 0xC0FFEE ^ 5)
+    for kw, kernels in ((dict(angle=90, mono=True, fliph=True), 1), (dict(resize_w=960, angle=90, gray=True, flipv=True), 3)):
+        ph = pp._PlanHolder(w=1920, h=1080, **kw)
+        ops = [ph.plan.ops[i] for i in range(ph.plan.nops)]
+        assert pp.chain_info(ops, 1920, 1080)[5] == kernels, kw
+        ph.close()
+        n0 = gpu.launch_count()
+        got = gpu.process(img, **kw)
+        assert gpu.launch_count() - n0 == kernels, kw
+        exp = orc.process(img, **kw)
+        assert got[1:] == exp[1:] and np.array_equal(got[0], exp[0]), kw
+
+
+def test_fused_equals_unfused(gpu, orc, monkeypatch):
+    for (w, h) in [(200, 56), (37, 23), (64, 64)]:
+        img = P.lcg(w, h, 5 + w)
+        for kw in FUSED_CHAINS:
+            a = gpu.process(img, **kw)
+            monkeypatch.setenv("PPMX_NO_FUSE", "1")
+            b = gpu.process(img, **kw)
+            monkeypatch.delenv("PPMX_NO_FUSE")
+            assert a[1:] == b[1:] and np.array_equal(a[0], b[0]), (w, h, kw)
+
+
+def test_odd_size_rotations_take_the_tile_kernel(gpu, orc):
+    """90 / 270 degrees at sizes the bulk-copy transposer can not take (ragged tiles, unaligned rows)."""
+    for (w, h) in [(1920, 1080), (1080, 1920), (4090 // 8, 4090 // 8 + 3), (1000, 37), (33, 1000)]:
+        img = P.lcg(w, h, 77)
+        for a in (90, 270):
+            assert np.array_equal(gpu.rotate(img, a), orc.rotate(img, a)), (w, h, a)

@@ -218,8 +218,19 @@ def test_chain_linearisation_and_band_rows(pp):
     def ops_of(**kw):
         ph = pp._PlanHolder(w=64, h=40, **kw)
         return ph, [ph.plan.ops[i] for i in range(ph.plan.nops)]
-    ph, ops = ops_of(gray=True, fliph=True)         # the leaked grey raster: flip + .r extraction only
-    assert pp.chain_info(ops, 64, 40) == (64, 40, pp.FT_PGM, 64 * 40, True, 2)
+    ph, ops = ops_of(gray=True, fliph=True)         # the leaked grey raster: flip + .r extraction only,
+    assert pp.chain_info(ops, 64, 40) == (64, 40, pp.FT_PGM, 64 * 40, True, 1)   # ... fused into one kernel
+    os.environ["PPMX_NO_FUSE"] = "1"
+    try:
+        assert pp.chain_info(ops, 64, 40) == (64, 40, pp.FT_PGM, 64 * 40, True, 2)
+    finally:
+        del os.environ["PPMX_NO_FUSE"]
+    ph.close()
+    ph, ops = ops_of(angle=90, mono=True, fliph=True)   # config 5: one kernel
+    assert pp.chain_info(ops, 1920, 1080)[5] == 1
+    ph.close()
+    ph, ops = ops_of(resize_w=960, angle=90, gray=True, flipv=True)
+    assert pp.chain_info(ops, 64, 40)[5] == 3           # two resize passes + one fused rotate/grey/flip
     ph.close()
     ph, ops = ops_of(mono=True)                      # mono + P4 packer in one kernel
     assert pp.chain_info(ops, 64, 40) == (64, 40, pp.FT_PBM, 8 * 40, True, 1)
@@ -266,3 +277,28 @@ def test_release_library_carries_no_tuning_variants(pp):
     assert L.ppmx_gpu_set_tuning(b"pdl", 1) == 0
     T = pp.gpu_lib(tuning=True)
     assert T.ppmx_gpu_set_tuning(b"variant", 3) == 0 and T.ppmx_gpu_set_tuning(b"variant", 0) == 0
+
+
+def test_extension_p3_and_16bit_decoding(pp):
+    """EXTENSION (the reference rejects P3, ref:386, and 16-bit samples, ref:453): both decode to the packed 8-bit
+    raster; maxval <= 255 keeps bytes and maxval, larger maxvals scale with round(v * 255 / maxval)."""
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    txt = b"P3\n# made by a test\n7 5\n255\n" + b"\n".join(b" ".join(b"%d" % v for v in row.reshape(-1)) for row in img) + b"\n"
+    got, mx = pp.decode_pnm(txt)
+    assert mx == 255 and np.array_equal(got, img)
+    low = (img // 16).astype(np.uint8)   # maxval 15: samples stay as they are, the header keeps 15
+    txt = b"P3 7 5 15 " + b" ".join(b"%d" % v for v in low.reshape(-1)) + b" # trailing comment\n"
+    got, mx = pp.decode_pnm(txt)
+    assert mx == 15 and np.array_equal(got, low)
+    wide = rng.integers(0, 65536, (5, 7, 3), dtype=np.uint32)
+    exp = ((2 * wide.astype(np.uint64) * 255 + 65535) // (2 * 65535)).astype(np.uint8)
+    got, mx = pp.decode_pnm(b"P6\n7 5\n65535\n" + wide.astype(">u2").tobytes())
+    assert mx == 255 and np.array_equal(got, exp)
+    got, mx = pp.decode_pnm(b"P3\n7 5\n1000\n" + b" ".join(b"%d" % min(v, 1000) for v in wide.reshape(-1)))
+    w1000 = np.minimum(wide, 1000).astype(np.uint64)
+    assert mx == 255 and np.array_equal(got, ((2 * w1000 * 255 + 1000) // 2000).astype(np.uint8))
+    for bad in (b"P3\n7 5\n255\n1 2 3", b"P3\n7 5\n255\n" + b"1 " * 105 + b"x", b"P6\n7 5\n65535\n" + b"\0" * 209,
+                b"P5\n7 5\n255\n" + b"\0" * 35, b"P3\n7 5\n70000\n" + b"1 " * 105):
+        with pytest.raises(pp.PpmxError):
+            pp.decode_pnm(bad)
