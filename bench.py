@@ -643,11 +643,12 @@ class OpRunner:
             k.close()
 
 
-def time_op(torch, g, name, device, min_ms=60.0, graph=True):
+def time_op(torch, g, name, device, min_ms=60.0, graph=True, lanes=1):
     """One extra workload, timed over at least min_ms of launches; returns its per_op entry."""
     peak, _ = peaks()
     r = OpRunner(torch, g, name, device, seed=0xC0FFEE ^ 7)
-    run = StepRunner(torch, g, r.calls, 1, graph)
+    # chains (resize: two passes per raster) keep their launch order on one stream; independent rasters alternate
+    run = StepRunner(torch, g, r.calls, 1, graph, lanes if len(r.ops) == 1 else 1)
     t, _, _ = time_runner(torch, run, 3, 3)
     nst = max(3, min(400, int(min_ms / max(t / 3, 1e-3))))
     t, _, _ = time_runner(torch, run, nst, 1)
@@ -1173,7 +1174,7 @@ def run_ours(args):
         per = {}
         for op_name in PER_OP:
             try:
-                per[op_name] = time_op(torch, g, op_name, device, graph=not args.no_graph)
+                per[op_name] = time_op(torch, g, op_name, device, graph=not args.no_graph, lanes=args.lanes)
             except Exception as e:  # an extra must not take the headline down
                 per[op_name] = {"error": str(e)[:120]}
         e2e_extra = {}

@@ -441,6 +441,21 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
         unsigned grid = wave_grid(ngroups ? ngroups : 1, 256, 8);
         launch(gray_vec_kernel<HIST, STORE>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const uint4 *>(src),
                                                           reinterpret_cast<uint4 *>(dst), ngroups, npix, d_hist);
+    } else if (!HIST && STORE && PPMX_VARIANT == 0 && npix >= 8192) {
+        // odd pointers (e.g. raster b of a batch whose size is no multiple of 16): a flat operator may view the pixel run as
+        // rows of any length -- 4096-pixel rows through the tile kernel of ppmx_fused.cu, the remainder one byte per thread
+        const uint32_t vw = 4096;
+        const size_t vh = npix / vw, rest = npix - vh * vw;
+        GeomOp go = {};
+        go.point = 1;
+        for (size_t y = 0; y < vh; y += 65535u * 64u) {
+            const uint32_t rows = (uint32_t)(vh - y < 65535u * 64u ? vh - y : 65535u * 64u);
+            cudaError_t e = geom_point(src + y * vw * 3, dst + y * vw, vw, rows, 0, go, s);
+            if (e != cudaSuccess) return e;
+        }
+        if (rest)
+            launch(gray_scalar_kernel<false, true>, dim3(wave_grid(rest, 256, 8)), dim3(256), 0, s, src + vh * vw * 3, dst + vh * vw, rest,
+                   (unsigned long long *)nullptr);
     } else {
         launch(gray_scalar_kernel<HIST, STORE>, dim3(wave_grid(npix, 256, 8)), dim3(256), 0, s, src, dst, npix, d_hist);
     }
@@ -549,6 +564,12 @@ cudaError_t mono_bits(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, 
         size_t ngroups = (size_t)(w / 16u) * h;
         launch(mono_bits_vec_kernel, dim3((unsigned)((ngroups + 255) / 256)), dim3(256), 0, s,
                reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint16_t *>(dst), w / 16u, ngroups, y0);
+    } else if (PPMX_VARIANT == 0 && (size_t)w * h >= 4096 && h <= 65535u * 64u) {
+        // any width / alignment: the tile kernel of ppmx_fused.cu (rows in as aligned words, bits out as shifted words)
+        GeomOp go = {};
+        go.point = 3;
+        go.my_add = (int)(y0 & 3u);
+        return geom_point(src, dst, w, h, 0, go, s);
     } else {
         uint32_t rb = (w + 7u) / 8u;
         launch(mono_bits_generic_kernel, dim3(wave_grid((size_t)rb * h, 256, 8)), dim3(256), 0, s, src, dst, w, h, rb, y0);
@@ -593,6 +614,19 @@ __global__ void __launch_bounds__(256) extract_r_kernel(const uint8_t *__restric
 cudaError_t extract_r(const uint8_t *src, uint8_t *dst, size_t npix, cudaStream_t s)
 {
     if (!npix) return cudaSuccess;
+    if (PPMX_VARIANT == 0 && npix >= 8192) {  // the writer's .r gather as rows of 4096 pixels through the tile kernel
+        const uint32_t vw = 4096;
+        const size_t vh = npix / vw, rest = npix - vh * vw;
+        GeomOp go = {};
+        go.point = 2;
+        for (size_t y = 0; y < vh; y += 65535u * 64u) {
+            const uint32_t rows = (uint32_t)(vh - y < 65535u * 64u ? vh - y : 65535u * 64u);
+            cudaError_t e = geom_point(src + y * vw * 3, dst + y * vw, vw, rows, 0, go, s);
+            if (e != cudaSuccess) return e;
+        }
+        if (rest) launch(extract_r_kernel, dim3(wave_grid(rest, 256, 8)), dim3(256), 0, s, src + vh * vw * 3, dst + vh * vw, rest);
+        return PPMX_LAUNCHED();
+    }
     launch(extract_r_kernel, dim3(wave_grid(npix, 256, 8)), dim3(256), 0, s, src, dst, npix);
     return PPMX_LAUNCHED();
 }

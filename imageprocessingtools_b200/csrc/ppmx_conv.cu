@@ -928,13 +928,13 @@ static cudaError_t conv_padded(const uint8_t *src, uint8_t *dst, uint32_t w, uin
         return e;
     }
     // (wp - w <= k/2 + 15 <= 20 pixels = 60 bytes: one 64-thread CTA per row)
-    if (e == cudaSuccess) e = cudaMemcpy2DAsync(tin, (size_t)wp * 3, src, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = geom_repitch(src, tin, w, h, w * 3u, wp * 3u, s);  // (the copy engine's 2-D path is several times slower)
     if (e == cudaSuccess) {
         launch(conv_pad_edge_kernel, dim3(h), dim3(64), 0, s, tin, w, wp);
         e = PPMX_LAUNCHED();
     }
     if (e == cudaSuccess) e = conv(tin, tout, wp, h, k, coef, div, bias, Band(), s);
-    if (e == cudaSuccess) e = cudaMemcpy2DAsync(dst, (size_t)w * 3, tout, (size_t)wp * 3, (size_t)w * 3, h, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = geom_repitch(tout, dst, w, h, wp * 3u, w * 3u, s);
     cudaFreeAsync(tin, s);
     cudaFreeAsync(tout, s);
     return e;

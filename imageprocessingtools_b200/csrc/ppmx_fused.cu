@@ -5,27 +5,27 @@
 //
 // A CTA moves one 64 x 64 pixel tile:
 //   1. the tile's source rows come into shared memory as raw interleaved bytes -- by the bulk-copy engine
-//      (cp.async.bulk + mbarrier) when rows are 16-byte aligned, else as aligned 32-bit words whose leading 0..3
+//      (cp.async.bulk + mbarrier) when rows are 16-byte aligned, else as aligned 16-byte vectors whose leading 0..15
 //      bytes of misalignment are kept in the staged row and undone when pixels are cut out;
 //   2. a thread takes 16 pixels -- down one source COLUMN for the four transposing orientations, along one source
 //      ROW for the others --, applies the pointwise tail and writes them where they belong in an output tile in
 //      shared memory (reversed when the orientation mirrors that axis);
 //   3. the output tile's rows leave by the bulk-copy engine (16-byte aligned destination rows), as 8-byte vectors
-//      (8-byte aligned, e.g. a 1080-pixel-wide result), or as aligned words assembled by a funnel shift with the
-//      row ends written byte by byte (anything else).
+//      (8-byte aligned, e.g. a 1080-pixel-wide result), or as aligned 16-byte vectors assembled by funnel shifts with
+//      the up to 15 bytes at either end of a row piece written one by one (anything else).
 // The Bayer index of mono, (x%4)*4 + (y%4) (ref:967), is taken in the coordinates of the stage where mono sits in
 // the chain; the host passes that stage's coordinates as a signed permutation of the source coordinates.
 #include "ppmx_common.cuh"
 
 namespace ppmx {
 
-constexpr int GI_PITCH = 208;  // staged source row: 192 B of pixels + up to 3 B of misalignment, 52 words (rows spread over banks)
+constexpr int GI_PITCH = 208;  // staged source row: 192 B of pixels + up to 15 B of misalignment = 13 vectors, 52 words (rows spread over banks)
 constexpr int GO_PITCH = 240;  // output tile row (RGB): 192 B + up to 45 B of front pad; 60 words: 16-byte stores of 8 rows never collide
 constexpr int GO_PITCH_R8 = 80;
 constexpr int GO_PITCH_BITS = 16;
 
 enum { GP_RGB = 0, GP_GRAY = 1, GP_RED = 2, GP_MONO = 3 };
-enum { GL_BULK = 0, GL_WORDS = 1 };
+enum { GL_BULK = 0, GL_VEC = 1 };
 enum { GS_BULK = 0, GS_VEC8 = 1, GS_SHIFT = 2 };
 
 __device__ __forceinline__ uint32_t gs_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -35,30 +35,29 @@ struct GeomOut {
     static constexpr int pitch = POINT == GP_RGB ? GO_PITCH : POINT == GP_MONO ? GO_PITCH_BITS : GO_PITCH_R8;
 };
 
-// a row piece of `nbytes` bytes from shared memory (16-byte aligned row, piece at byte `soff`) to any global address
+// A row piece of `nbytes` (<= 208) bytes from shared memory (4-byte aligned row, piece at byte `soff`) to any global
+// address, by HALF a warp (hl = 0..15): up to 15 bytes each at the piece's ends go out one by one, everything between
+// as 16-byte vectors to aligned addresses, each assembled from five shared-memory words by a funnel shift.
 template <int STORE>
-__device__ __forceinline__ void store_piece(uint8_t *g, const uint8_t *srow, uint32_t soff, uint32_t nbytes, uint32_t lane)
+__device__ __forceinline__ void store_piece(uint8_t *g, const uint8_t *srow, uint32_t soff, uint32_t nbytes, uint32_t hl)
 {
     if (STORE == GS_VEC8) {  // g, soff and nbytes are multiples of 8
         const uint2 *s = reinterpret_cast<const uint2 *>(srow + soff);
-        for (uint32_t k = lane; k < nbytes / 8u; k += 32u) reinterpret_cast<uint2 *>(g)[k] = s[k];
+        for (uint32_t k = hl; k < nbytes / 8u; k += 16u) reinterpret_cast<uint2 *>(g)[k] = s[k];
         return;
     }
-    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u), nwords = (a + nbytes + 3u) >> 2;
-    uint32_t *gw = reinterpret_cast<uint32_t *>(g - a);
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(srow);
-    for (uint32_t k = lane; k < nwords; k += 32u) {
-        const int p = (int)(4u * k) - (int)a;  // position in the piece of this destination word's first byte
-        if (p >= 0 && (uint32_t)p + 4u <= nbytes) {
-            const uint32_t q = soff + (uint32_t)p, w0 = sw[q >> 2], w1 = (q & 3u) ? sw[(q >> 2) + 1] : 0u;
-            gw[k] = __funnelshift_r(w0, w1, 8u * (q & 3u));
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int q = p + j;
-                if (q >= 0 && (uint32_t)q < nbytes) (reinterpret_cast<uint8_t *>(gw))[4u * k + j] = srow[soff + q];
-            }
-        }
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
+    const uint32_t hb = min(nbytes, (16u - a) & 15u), nv = (nbytes - hb) >> 4, tb = nbytes - hb - 16u * nv;
+    if (hl < nv) {
+        const uint32_t q = soff + hb + 16u * hl, sh = 8u * (q & 3u);
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(srow) + (q >> 2);
+        const uint32_t w0 = sw[0], w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sh ? sw[4] : 0u;
+        reinterpret_cast<uint4 *>(g + hb)[hl] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                                                          __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+    for (uint32_t b = hl; b < hb + tb; b += 16u) {
+        const uint32_t pos = b < hb ? b : nbytes - tb + (b - hb);
+        g[pos] = srow[soff + pos];
     }
 }
 
@@ -70,14 +69,15 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
 {
     pdl_trigger();
     constexpr int OP = GeomOut<POINT>::pitch;
-    __shared__ __align__(128) uint8_t tin[64 * GI_PITCH];
+    __shared__ __align__(128) uint8_t tin[64 * GI_PITCH + 16];  // (+16: the funnel shift's second word of the last pixel)
     __shared__ __align__(128) uint8_t tout[64 * OP];
     __shared__ __align__(8) uint64_t bar;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tx0 = blockIdx.x * 64u, ty0 = blockIdx.y * 64u;
     const uint32_t nc = min(64u, w - tx0), nr = min(64u, h - ty0);
     const uintptr_t g0 = reinterpret_cast<uintptr_t>(src) + (size_t)ty0 * in_pitch + (size_t)tx0 * 3;
-    const uint32_t a0 = LOAD == GL_BULK ? 0u : (uint32_t)(g0 & 3u), ap = LOAD == GL_BULK ? 0u : (in_pitch & 3u);
+    // rows staged as aligned 16-byte vectors keep their 0..15 bytes of misalignment in front of them in tin
+    const uint32_t a0 = LOAD == GL_BULK ? 0u : (uint32_t)(g0 & 15u), ap = LOAD == GL_BULK ? 0u : (in_pitch & 15u);
 
     // ---- 1. the tile's source rows -> tin ------------------------------------------------------------------
     if (LOAD == GL_BULK) {
@@ -108,24 +108,22 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
             : "memory");
     } else {
         pdl_wait();
-        // aligned words covering [g, g + 3 nc): the row's 0..3 bytes of misalignment stay in front of it in tin
-#pragma unroll 1
-        for (uint32_t r4 = 0; r4 < 16u; r4 += 4u) {
-            uint32_t v[4][2];
+        // aligned 16-byte vectors covering [g, g + 3 nc), half a warp per row (at most 13 vectors), four row pairs in flight
+        const uint32_t hl = lane & 15u, hr = lane >> 4;
+#pragma unroll
+        for (uint32_t i4 = 0; i4 < 8u; i4 += 4u) {
+            uint4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const uint32_t r = warp * 16u + r4 + u;
+                const uint32_t r = warp * 16u + 2u * (i4 + u) + hr;
                 const uintptr_t g = g0 + (size_t)r * in_pitch;
-                const uint32_t a = (uint32_t)(g & 3u), nwords = r < nr ? (a + nc * 3u + 3u) >> 2 : 0u;
-                const uint32_t *gw = reinterpret_cast<const uint32_t *>(g - a);
-                v[u][0] = lane < nwords ? __ldg(gw + lane) : 0u;
-                v[u][1] = lane + 32u < nwords ? __ldg(gw + lane + 32u) : 0u;
+                const uint32_t a = (uint32_t)(g & 15u), nvec = r < nr ? (a + nc * 3u + 15u) >> 4 : 0u;
+                v[u] = hl < nvec ? __ldg(reinterpret_cast<const uint4 *>(g - a) + hl) : make_uint4(0u, 0u, 0u, 0u);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                uint32_t *trow = reinterpret_cast<uint32_t *>(tin + (warp * 16u + r4 + u) * GI_PITCH);
-                trow[lane] = v[u][0];
-                if (lane < 20u) trow[lane + 32u] = v[u][1];
+                const uint32_t r = warp * 16u + 2u * (i4 + u) + hr;
+                if (hl < 13u) reinterpret_cast<uint4 *>(tin + r * GI_PITCH)[hl] = v[u];
             }
         }
         __syncthreads();
@@ -148,15 +146,15 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
         if (TRANSPOSE) {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const uint32_t r = 16u * j + k, off = ((a0 + r * ap) & 3u) + 3u * fix;
+                const uint32_t r = 16u * j + k, off = ((a0 + r * ap) & 15u) + 3u * fix;
                 const uint32_t *p = tin32 + r * (GI_PITCH / 4) + (off >> 2);
                 px[k] = __funnelshift_r(p[0], p[1], (off & 3u) * 8u);
             }
         } else {
-            const uint32_t off = (a0 + fix * ap) & 3u;
-            const uint32_t *p = tin32 + fix * (GI_PITCH / 4) + 12u * j;
+            const uint32_t off = (a0 + fix * ap) & 15u;
+            const uint32_t *p = tin32 + fix * (GI_PITCH / 4) + 12u * j + (off >> 2);
 #pragma unroll
-            for (int i = 0; i < 12; i++) rw12[i] = __funnelshift_r(p[i], p[i + 1], off * 8u);
+            for (int i = 0; i < 12; i++) rw12[i] = __funnelshift_r(p[i], p[i + 1], (off & 3u) * 8u);
         }
         // where the 16 pixels go: tout row `orow`, pixel block `oblk` of that row's piece (+ pad)
         const uint32_t orow = fix;
@@ -313,12 +311,13 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may go once it has been read
         }
     } else {
-#pragma unroll 1
-        for (uint32_t rr = 0; rr < 16u; rr++) {
-            const uint32_t crow = warp * 16u + rr;
-            if (crow >= nrows_out) break;
+        const uint32_t hl = lane & 15u, hr = lane >> 4;  // half a warp per output row
+#pragma unroll 2
+        for (uint32_t i = 0; i < 8u; i++) {
+            const uint32_t crow = warp * 16u + 2u * i + hr;
+            if (crow >= nrows_out) continue;
             const uint32_t y = go.rev_y ? out_h - 1u - (row0 + crow) : row0 + crow;
-            store_piece<STORE>(dst + (size_t)y * out_pitch + goff, tout + crow * OP, soff, pbytes, lane);
+            store_piece<STORE>(dst + (size_t)y * out_pitch + goff, tout + crow * OP, soff, pbytes, hl);
         }
     }
 }
@@ -344,9 +343,9 @@ static cudaError_t geom_launch(const uint8_t *src, uint8_t *dst, uint32_t w, uin
         else if (store == GS_VEC8) PPMX_GEOM(GL_BULK, GS_VEC8);
         else PPMX_GEOM(GL_BULK, GS_SHIFT);
     } else {
-        if (store == GS_BULK) PPMX_GEOM(GL_WORDS, GS_BULK);
-        else if (store == GS_VEC8) PPMX_GEOM(GL_WORDS, GS_VEC8);
-        else PPMX_GEOM(GL_WORDS, GS_SHIFT);
+        if (store == GS_BULK) PPMX_GEOM(GL_VEC, GS_BULK);
+        else if (store == GS_VEC8) PPMX_GEOM(GL_VEC, GS_VEC8);
+        else PPMX_GEOM(GL_VEC, GS_SHIFT);
     }
 #undef PPMX_GEOM
     return PPMX_LAUNCHED();
@@ -383,6 +382,20 @@ cudaError_t geom_point(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h,
         if (go.rev_x) { PPMX_GEOM_P(0, true) } else { PPMX_GEOM_P(0, false) }
     }
 #undef PPMX_GEOM_P
+}
+
+// rows of 3 * w bytes from one pitch to another (any alignment either side): the tile kernel as a plain copy
+cudaError_t geom_repitch(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t in_pitch, uint32_t out_pitch, cudaStream_t s)
+{
+    if (!w || !h) return cudaSuccess;
+    GeomOp go = {};
+    for (uint32_t y = 0; y < h; y += 65535u * 64u) {
+        const uint32_t rows = h - y < 65535u * 64u ? h - y : 65535u * 64u;
+        cudaError_t e = geom_launch<0, false, GP_RGB>(src + (size_t)y * in_pitch, dst + (size_t)y * out_pitch, w, rows, in_pitch,
+                                                      out_pitch, go, s);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace ppmx

@@ -142,6 +142,11 @@ cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int b
             size_t n = row / 4 * h;
             launch(flipv_kernel<uint32_t>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
                    reinterpret_cast<const uint32_t *>(src), reinterpret_cast<uint32_t *>(dst), (uint32_t)(row / 4), h, n);
+        } else if (bpp == 3 && PPMX_VARIANT == 0 && (size_t)w * h >= 4096 && h <= 65535u * 64u) {
+            // rows at any alignment (width no multiple of 16): the tile kernel of ppmx_fused.cu
+            GeomOp go = {};
+            go.rev_y = 1;
+            return geom_point(src, dst, w, h, 0, go, s);
         } else if (h <= 65535u && PPMX_VARIANT != 1) {
             const unsigned gx = (unsigned)((row / 4 + 1 + 255) / 256);
             if (bpp == 3) launch(flip_rows_kernel<false, 3>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
@@ -155,6 +160,10 @@ cudaError_t flip(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int b
             size_t n = (size_t)(w / 16u) * h;
             launch(fliph_rgb16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
                    reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), w / 16u, n);
+        } else if (bpp == 3 && PPMX_VARIANT == 0 && (size_t)w * h >= 4096 && h <= 65535u * 64u) {
+            GeomOp go = {};
+            go.rev_x = 1;
+            return geom_point(src, dst, w, h, 0, go, s);
         } else if (h <= 65535u && (bpp == 3 || bpp == 1) && PPMX_VARIANT != 1) {
             const unsigned gx = (unsigned)((row / 4 + 1 + 255) / 256);
             if (bpp == 3) launch(flip_rows_kernel<true, 3>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);
@@ -461,6 +470,10 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
             if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
             launch(fliph_rgb16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s,
                    reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), (uint32_t)n, n);
+        } else if (PPMX_VARIANT == 0 && npix >= 4096 && h <= 65535u * 64u) {  // any alignment: the tile kernel (ppmx_fused.cu)
+            GeomOp go = {};
+            go.rev_x = go.rev_y = 1;
+            return geom_point(src, dst, w, h, 0, go, s);
         } else if (h <= 65535u && PPMX_VARIANT != 1) {  // any layout: mirrored rows taken from the mirrored row
             const unsigned gx = (unsigned)(((size_t)w * 3 / 4 + 1 + 255) / 256);
             launch(flip_rows_kernel<true, 3, true>, dim3(gx < 64u ? gx : 64u, h), dim3(256), 0, s, src, dst, w, h);

@@ -63,6 +63,9 @@ bool geom_point_supported(uint32_t w, uint32_t h, const GeomOp &go);
 cudaError_t geom_point(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t in_pitch, const GeomOp &go,
                        cudaStream_t s);
 
+cudaError_t geom_repitch(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t in_pitch, uint32_t out_pitch,
+                         cudaStream_t s);
+
 // every byte of the raster through a 256-entry table (host pointer)
 cudaError_t levels(const uint8_t *src, uint8_t *dst, size_t nbytes, const uint8_t *lut /*host*/, cudaStream_t s);
 
