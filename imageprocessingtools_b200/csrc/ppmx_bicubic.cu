@@ -195,6 +195,7 @@ cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_
     if ((w % 4u) == 0 && aligned4(src) && PPMX_VARIANT != 1) {
         // with the index conversions off the XU pipe (floor_int/floor_both) all 48 byte conversions fit there:
         // measured 56.5 Gpix/s (CONV 0) vs 53.5 (3 of 4 on XU) vs 51.0 (half) vs 47.8 (all on the FP64 pipe)
+#ifdef PPMX_TUNING  // other splits of the byte conversions between the XU and FP64 pipes (profiles/r1_sweep_fp64.txt)
         if (PPMX_VARIANT == 2)
             launch(rotate_bicubic_kernel<true, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
         else if (PPMX_VARIANT == 3)
@@ -202,6 +203,7 @@ cudaError_t rotate_bicubic(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_
         else if (PPMX_VARIANT == 4)
             launch(rotate_bicubic_kernel<true, 3>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
         else
+#endif
             launch(rotate_bicubic_kernel<true, 0>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
     } else {
         launch(rotate_bicubic_kernel<false, 1>, grid, block, 0, s, src, dst, w, h, nw, nh, cos_t, sin_t, xc, yc, xo, yo, (double)xc, (double)yc);
@@ -413,6 +415,7 @@ static void launch_colsK(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t 
     for (uint32_t y0 = 0; y0 < h; y0 += 65535u * rows_per_cta) {
         uint32_t rows = min(65535u * rows_per_cta, h - y0);
         dim3 grid((out_w + 127) / 128, (rows + rows_per_cta - 1) / rows_per_cta);
+#ifdef PPMX_TUNING
         if (PPMX_VARIANT == 2)
             launch(imresize_colsK_kernel<K, 1>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
                    dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
@@ -423,6 +426,7 @@ static void launch_colsK(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t 
             launch(imresize_colsK_kernel<K, 2>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
                    dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
         else  // three of four byte conversions on the XU pipe: 1-3 % faster than half/half once the first-tap adds are gone
+#endif
             launch(imresize_colsK_kernel<K, 3>, grid, dim3(128), 0, s, src + (size_t)y0 * w * 3,
                    dst + (size_t)y0 * out_w * 3, w, rows, out_w, rows_per_cta, wts, idx);
     }
@@ -516,11 +520,14 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
                 uint8_t *d0 = dst + (size_t)y0 * row_bytes;
                 const double *w0 = d_weights + (size_t)y0 * taps;
                 const int *i0 = d_indices + (size_t)y0 * taps;
+#ifdef PPMX_TUNING
                 if (narrow) launch(imresize_rows16_kernel<2, 2>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (PPMX_VARIANT == 2) launch(imresize_rows16_kernel<1, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (PPMX_VARIANT == 3) launch(imresize_rows16_kernel<0, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (PPMX_VARIANT == 4) launch(imresize_rows16_kernel<2, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else if (taps == 4 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else
+#endif
+                if (taps == 4 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 5 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 5>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 6 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 6>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 7 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 7>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);

@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(BLOCK) gray_flat_kernel(const uint4 *__restric
     }
 }
 
+#ifdef PPMX_TUNING
 // ---- TMA bulk-copy pipeline (cp.async.bulk + mbarrier): one elected thread streams 12 KB tiles
 // of the raster into a ring of shared-memory stages; the CTA reads each tile conflict-free
 // (48 B per thread), computes, and stores 16 B per thread straight to global memory.
@@ -383,6 +384,8 @@ __global__ void __launch_bounds__(256) gray_tma_kernel(const uint8_t *__restrict
     }
 }
 
+#endif  // PPMX_TUNING
+
 template <bool HIST, bool STORE>
 static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, unsigned long long *d_hist,
                                  cudaStream_t s)
@@ -390,16 +393,7 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
     if (npix == 0) return cudaSuccess;
     if (aligned16(src) && (!STORE || aligned16(dst))) {
         size_t ngroups = npix / 16;
-        if (HIST && PPMX_VARIANT != 2 && PPMX_VARIANT != 5) {
-            // lane-private columns, RED.shared; one 1024-thread CTA per SM
-            static SmemOptIn ok;
-            allow_smem(gray_hist_lanes_kernel<STORE>, HL_SMEM, ok);
-            size_t want = (ngroups + HL_THREADS - 1) / HL_THREADS, wave = (size_t)sm_count();
-            unsigned grid = (unsigned)(want < 1 ? 1 : want < wave ? want : wave);
-            launch(gray_hist_lanes_kernel<STORE>, dim3(grid), dim3(HL_THREADS), HL_SMEM, s, reinterpret_cast<const uint4 *>(src),
-                   reinterpret_cast<uint4 *>(dst), ngroups, npix, d_hist);
-            return PPMX_LAUNCHED();
-        }
+#ifdef PPMX_TUNING  // alternative implementations, measured and not chosen (profiles/r1_sweep_variants.txt): tuning build only
         if (HIST && PPMX_VARIANT == 5) {
             // thread-private byte counters: <= 15 groups per thread between folds, 3 CTAs per SM
             static SmemOptIn ok;
@@ -415,22 +409,16 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
                    reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), ngroups, npix, (uint32_t)per, d_hist);
             return PPMX_LAUNCHED();
         }
-        if (!HIST && PPMX_VARIANT != 1 && PPMX_VARIANT != 4) {  // default: one group per thread, no loop
-            if (PPMX_VARIANT == 6 || PPMX_VARIANT == 7) {  // smaller CTAs: shorter tail, more CTA launches
-                const unsigned blk = PPMX_VARIANT == 6 ? 128u : 64u;
-                unsigned grid = (unsigned)((ngroups + blk - 1) / blk);
-                if (blk == 128) launch(gray_flat_kernel<128>, dim3(grid ? grid : 1), dim3(128), 0, s,
-                                       reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), ngroups, npix);
-                else launch(gray_flat_kernel<64>, dim3(grid ? grid : 1), dim3(64), 0, s,
-                            reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), ngroups, npix);
-                return PPMX_LAUNCHED();
-            }
-            unsigned grid = (unsigned)((ngroups + 255) / 256);
-            launch(gray_flat_kernel<256>, dim3(grid ? grid : 1), dim3(256), 0, s, reinterpret_cast<const uint4 *>(src),
-                   reinterpret_cast<uint4 *>(dst), ngroups, npix);
+        if (!HIST && (PPMX_VARIANT == 6 || PPMX_VARIANT == 7)) {  // smaller CTAs: shorter tail, more CTA launches
+            const unsigned blk = PPMX_VARIANT == 6 ? 128u : 64u;
+            unsigned grid = (unsigned)((ngroups + blk - 1) / blk);
+            if (blk == 128) launch(gray_flat_kernel<128>, dim3(grid ? grid : 1), dim3(128), 0, s,
+                                   reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), ngroups, npix);
+            else launch(gray_flat_kernel<64>, dim3(grid ? grid : 1), dim3(64), 0, s,
+                        reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), ngroups, npix);
             return PPMX_LAUNCHED();
         }
-        if (!HIST && PPMX_VARIANT == 4) {
+        if (!HIST && PPMX_VARIANT == 4) {  // cp.async.bulk + mbarrier ring
             static SmemOptIn ok;
             allow_smem(gray_tma_kernel, GT_SMEM, ok);
             size_t ntiles = (ngroups + GT_TILE_GROUPS - 1) / GT_TILE_GROUPS;
@@ -438,9 +426,27 @@ static cudaError_t gray_dispatch(const uint8_t *src, uint8_t *dst, size_t npix, 
             launch(gray_tma_kernel, dim3(grid), dim3(256), GT_SMEM, s, src, reinterpret_cast<uint4 *>(dst), ngroups, npix);
             return PPMX_LAUNCHED();
         }
-        unsigned grid = wave_grid(ngroups ? ngroups : 1, 256, 8);
-        launch(gray_vec_kernel<HIST, STORE>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const uint4 *>(src),
-                                                          reinterpret_cast<uint4 *>(dst), ngroups, npix, d_hist);
+        if ((HIST && PPMX_VARIANT == 2) || (!HIST && PPMX_VARIANT == 1)) {  // persistent grid-stride grid, per-warp bins
+            unsigned grid = wave_grid(ngroups ? ngroups : 1, 256, 8);
+            launch(gray_vec_kernel<HIST, STORE>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const uint4 *>(src),
+                   reinterpret_cast<uint4 *>(dst), ngroups, npix, d_hist);
+            return PPMX_LAUNCHED();
+        }
+#endif
+        if (HIST) {
+            // lane-private columns, RED.shared; one 1024-thread CTA per SM
+            static SmemOptIn ok;
+            allow_smem(gray_hist_lanes_kernel<STORE>, HL_SMEM, ok);
+            size_t want = (ngroups + HL_THREADS - 1) / HL_THREADS, wave = (size_t)sm_count();
+            unsigned grid = (unsigned)(want < 1 ? 1 : want < wave ? want : wave);
+            launch(gray_hist_lanes_kernel<STORE>, dim3(grid), dim3(HL_THREADS), HL_SMEM, s, reinterpret_cast<const uint4 *>(src),
+                   reinterpret_cast<uint4 *>(dst), ngroups, npix, d_hist);
+            return PPMX_LAUNCHED();
+        }
+        // one 16-pixel group per thread, one CTA per 256 groups, no loop
+        unsigned grid = (unsigned)((ngroups + 255) / 256);
+        launch(gray_flat_kernel<256>, dim3(grid ? grid : 1), dim3(256), 0, s, reinterpret_cast<const uint4 *>(src),
+               reinterpret_cast<uint4 *>(dst), ngroups, npix);
     } else if (!HIST && STORE && PPMX_VARIANT == 0 && npix >= 8192) {
         // odd pointers (e.g. raster b of a batch whose size is no multiple of 16): a flat operator may view the pixel run as
         // rows of any length -- 4096-pixel rows through the tile kernel of ppmx_fused.cu, the remainder one byte per thread
@@ -733,7 +739,7 @@ cudaError_t levels(const uint8_t *src, uint8_t *dst, size_t nbytes, const uint8_
     LevelsLut l;
     for (int i = 0; i < 64; i++)
         l.w[i] = (uint32_t)lut[4 * i] | (uint32_t)lut[4 * i + 1] << 8 | (uint32_t)lut[4 * i + 2] << 16 | (uint32_t)lut[4 * i + 3] << 24;
-    if (aligned16(src) && aligned16(dst) && nbytes >= (size_t)1 << 20 && PPMX_VARIANT != 1) {
+    if (aligned16(src) && aligned16(dst) && nbytes >= (size_t)1 << 20 && PPMX_VARIANT != 1) {  // (variant: tuning build only)
         static SmemOptIn ok;
         allow_smem(levels_lanes_kernel, LV_SMEM, ok);
         const size_t nvec = nbytes / 16, want = (nvec + LV_THREADS - 1) / LV_THREADS, wave = (size_t)sm_count();

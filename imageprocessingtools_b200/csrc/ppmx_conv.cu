@@ -442,12 +442,15 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
         else launch(conv3_strip_kernel<2, 4, 2, 128, true>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd);
         return PPMX_LAUNCHED();
     }
+#ifdef PPMX_TUNING
     if (PPMX_VARIANT == 9) PPMX_CONV3_MODES(2, 1, 128);
     else if (PPMX_VARIANT == 10) PPMX_CONV3_MODES(4, 2, 256);
     else if (PPMX_VARIANT == 11) PPMX_CONV3_MODES(8, 2, 128);
     else if (PPMX_VARIANT == 12) PPMX_CONV3_MODES(16, 1, 128);
     else if (PPMX_VARIANT == 13) PPMX_CONV3_MODES(4, 2, 64);
-    else PPMX_CONV3_MODES(4, 2, 128);
+    else
+#endif
+    PPMX_CONV3_MODES(4, 2, 128);
 #undef PPMX_CONV3_MODES
 #undef PPMX_CONV3_LAUNCH
     return PPMX_LAUNCHED();
@@ -643,9 +646,12 @@ static cudaError_t conv_box(const RowSource &rs, uint8_t *dst, uint32_t w, uint3
         if (grid.y > 65535u) return cudaErrorInvalidValue;                                    \
         launch(conv_box_kernel<K, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, M, C);        \
     } while (0)
+#ifdef PPMX_TUNING
     if (PPMX_VARIANT == 10) PPMX_BOX_LAUNCH(32);
     else if (PPMX_VARIANT == 11) PPMX_BOX_LAUNCH(64);
-    else PPMX_BOX_LAUNCH(16);
+    else
+#endif
+    PPMX_BOX_LAUNCH(16);
 #undef PPMX_BOX_LAUNCH
     return PPMX_LAUNCHED();
 }
@@ -849,8 +855,10 @@ static bool conv_sep(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, 
                      cudaStream_t s, cudaError_t *err)
 {
     // rows per strip, 7x7 / 5x5 binomial at 8192^2: 16 -> 0.46 / 0.53 of the HBM roofline, 32 -> 0.45 / 0.52, 64 -> 0.42 / 0.48
+#ifdef PPMX_TUNING
     if (PPMX_VARIANT == 9) return conv_sep_rh<K, 8>(rs, dst, w, h, coef, rnd, s, err);
     if (PPMX_VARIANT == 10) return conv_sep_rh<K, 32>(rs, dst, w, h, coef, rnd, s, err);
+#endif
     return conv_sep_rh<K, 16>(rs, dst, w, h, coef, rnd, s, err);
 }
 

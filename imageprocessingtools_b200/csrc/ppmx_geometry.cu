@@ -490,6 +490,7 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
         else launch(rotate_bulk64_kernel<false>, grid, dim3(128), 0, s, src, dst, w, h);
         return PPMX_LAUNCHED();
     }
+#ifdef PPMX_TUNING  // the register-path transposer the bulk-copy kernel replaced (variants 6, 7, 8 and its 2-tile default)
     if ((w % 16u) == 0 && (h % 16u) == 0 && aligned16(src) && aligned16(dst) && PPMX_VARIANT != 1) {
         // (numbering the CTAs down bands of 2..16 tile rows, for DRAM page locality on the write side,
         // measured 1-5 % SLOWER than this plain 2-D grid: the index arithmetic costs more than it gains)
@@ -517,6 +518,7 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
         }
         return PPMX_LAUNCHED();
     }
+#endif
     if (PPMX_VARIANT == 0) {
         // any size, any alignment (1920 x 1080 frames: height no multiple of 16): the tile kernel of ppmx_fused.cu, rows in
         // by bulk copy or aligned words, out as 8-byte vectors or shifted words
@@ -526,6 +528,7 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
         go.rev_y = angle == 270;  // out[w-1-x][y] = in[y][x], ref:725
         return geom_point(src, dst, w, h, 0, go, s);
     }
+#ifdef PPMX_TUNING  // the byte-wise transposers the tile kernel replaced
     if (PPMX_VARIANT != 1) {
         dim3 ga((w + RA - 1) / RA, (h + RA - 1) / RA);
         if (ga.y > 65535u) return cudaErrorInvalidValue;
@@ -541,5 +544,9 @@ cudaError_t rotate_orth(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h
     return PPMX_LAUNCHED();
 }
 
+#else
+    return cudaErrorInvalidValue;  // (not reached: the tile kernel above takes every raster)
+}
+#endif
 
 }  // namespace ppmx
