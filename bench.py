@@ -871,6 +871,24 @@ def cli_rows(g):
                 ent[label] = round(best, 3) if best is not None else None
             ent.pop("sha_out", None)
             rows.append(ent)
+        # a batch of files: one run of ppmx-b200 -batch (one device context, file I/O overlapped with the device work)
+        # beside one run of the reference per file
+        n = 8
+        paths = []
+        for i in range(n):
+            p = os.path.join(td, "b%d.ppm" % i)
+            oracle.write_p6(p, pp.synth_lcg(4096, 4096, 0xC0FFEE ^ 2 ^ (i + 1)))
+            paths.append(p)
+        ent = {"args": "-gray", "files": "%d x 4096x4096 P6 (50 MB each)" % n}
+        if os.path.exists(pp.CLI):
+            t0 = time.perf_counter()
+            pr = subprocess.run([pp.CLI, "-batch", "-gray"] + paths, capture_output=True)
+            ent["ppmx_b200_batch_s"] = round(time.perf_counter() - t0, 3) if pr.returncode == 0 else None
+        if os.path.exists(oracle.REF_CLI):
+            t0 = time.perf_counter()
+            ok = all(subprocess.run([oracle.REF_CLI, "-gray", p], capture_output=True).returncode == 0 for p in paths)
+            ent["reference_cli_one_run_per_file_s"] = round(time.perf_counter() - t0, 3) if ok else None
+        rows.append(ent)
     return rows
 
 

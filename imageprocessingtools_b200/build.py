@@ -89,11 +89,11 @@ def build_all(force: bool = False, verbose: bool = False) -> None:
                  verbose)
     host_c = os.path.join(CSRC, "ppmx_host.c")
     if force or _newer(HOST_SO, [host_c, GPU_SO] + hdrs):
-        _run(["gcc"] + GCC_FLAGS + ["-shared", "-o", HOST_SO, host_c, "-L" + PKG, "-lppmx_gpu", "-lm",
+        _run(["gcc"] + GCC_FLAGS + ["-shared", "-o", HOST_SO, host_c, "-L" + PKG, "-lppmx_gpu", "-lm", "-lpthread",
                                     "-Wl,-rpath,$ORIGIN"], verbose)
     cli_c = os.path.join(CSRC, "ppmx_cli.c")
     if force or _newer(CLI, [cli_c, HOST_SO]):
-        _run(["gcc"] + GCC_FLAGS + ["-o", CLI, cli_c, "-L" + PKG, "-lppmx_host", "-lppmx_gpu", "-lm",
+        _run(["gcc"] + GCC_FLAGS + ["-o", CLI, cli_c, "-L" + PKG, "-lppmx_host", "-lppmx_gpu", "-lm", "-lpthread",
                                     "-Wl,-rpath,$ORIGIN"], verbose)
 
 

@@ -11,8 +11,10 @@
 
 #include <ctype.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define PPMX_PI 3.14159265358979323846 /* the reference's own literal, ref:12 */
 
@@ -618,26 +620,6 @@ int ppmx_format_header(char *dst, size_t cap, int file_type, unsigned int width,
     return snprintf(dst, cap, "%s\n# generated by ppmx_edward\n%u %u\n%u\n", magic, width, height, max_color);
 }
 
-static int read_whole_file(ppmx_image_handler *h)
-{
-    FILE *fp = fopen(h->filename, "rb");
-    long sz;
-    if (!fp) BAIL("error. can not open file\n"); /* ref:1059 */
-    if (fseek(fp, 0, SEEK_END) < 0) { fclose(fp); BAIL("error. can not set file position in fseek.\n"); }
-    sz = ftell(fp);
-    rewind(fp);
-    h->filesize = (size_t)(sz < 0 ? 0 : sz);
-    /* straight into pinned memory: after the header this IS the packed raster (ref:316-318) */
-    h->file_buffer = (unsigned char *)ppmx_gpu_host_alloc(h->ctx, h->filesize + 1);
-    if (!h->file_buffer) { fclose(fp); BAIL("error. can not allocate memory\n"); }
-    if (fread(h->file_buffer, 1, h->filesize, fp) != h->filesize) {
-        fclose(fp);
-        BAIL("error in reading input file.\n"); /* ref:1069 */
-    }
-    fclose(fp);
-    return PPMX_OK;
-}
-
 int ppmx_getImageInfo(ppmx_image_handler *h)
 {
     unsigned int w = 0, hh = 0, mx = 0;
@@ -708,61 +690,311 @@ static int pnm_is_16bit(const unsigned char *f, size_t n)
     return pnm_number(f, n, &i, &w) && pnm_number(f, n, &i, &hh) && pnm_number(f, n, &i, &mx) && mx > 255 && mx <= 65535;
 }
 
-int ppmx_doProcessPPM(ppmx_image_handler *h)
-{
-    ppmx_plan plan;
-    unsigned int w = 0, hh = 0, mx = 0, ow = 0, oh = 0;
-    size_t off = 0, cap, n = 0, i;
-    unsigned char *out = NULL, *decoded = NULL;
-    const unsigned char *raster = NULL;
-    int own_ctx = 0, ft = PPMX_FILETYPE_PPM, rc = PPMX_ERROR;
+/* ---- one file = one job: read -> plan + device chain -> write ---------------------------------------- */
 
-    memset(&plan, 0, sizeof(plan));
-    if (!h->ctx) {
-        const char *dev = getenv("PPMX_DEVICE");
-        if (ppmx_gpu_init(&h->ctx, dev ? atoi(dev) : 0) != PPMX_OK) return PPMX_ERROR;
-        own_ctx = 1;
+typedef struct ppmx_job {
+    const char *filename;
+    unsigned char *file_buffer; /* the whole input file, pinned */
+    size_t filesize, file_cap;
+    unsigned char *decoded;     /* pinned 8-bit raster of a P3 / 16-bit input (extension), else NULL */
+    size_t decoded_cap;
+    const unsigned char *raster;
+    unsigned int w, h, maxval;
+    unsigned char *out;         /* what follows the output header, pinned */
+    size_t out_cap, out_bytes;
+    unsigned int ow, oh;
+    int ft, rc;
+} ppmx_job;
+
+/* pinned buffers are expensive to make (the pages are locked one by one): a batch keeps a few and reuses them */
+typedef struct ppmx_pin_cache {
+    void *p[8];
+    size_t cap[8];
+    pthread_mutex_t mu;
+    ppmx_gpu_ctx *ctx;
+} ppmx_pin_cache;
+
+static void *pin_get(ppmx_pin_cache *pc, size_t need, size_t *cap)
+{
+    int i, best = -1;
+    void *p;
+    pthread_mutex_lock(&pc->mu);
+    for (i = 0; i < 8; i++)
+        if (pc->p[i] && pc->cap[i] >= need && (best < 0 || pc->cap[i] < pc->cap[best])) best = i;
+    if (best >= 0) {
+        p = pc->p[best];
+        *cap = pc->cap[best];
+        pc->p[best] = NULL;
+        pthread_mutex_unlock(&pc->mu);
+        return p;
     }
-    if (read_whole_file(h) != PPMX_OK) goto done;
-    raster = h->file_buffer;
-    if (h->filesize >= 2 && h->file_buffer[0] == 'P' && (h->file_buffer[1] == '3' || pnm_is_16bit(h->file_buffer, h->filesize))) {
+    pthread_mutex_unlock(&pc->mu);
+    *cap = need;
+    return ppmx_gpu_host_alloc(pc->ctx, need);
+}
+
+static void pin_put(ppmx_pin_cache *pc, void *p, size_t cap)
+{
+    int i, slot = -1;
+    void *drop = p;
+    if (!p) return;
+    pthread_mutex_lock(&pc->mu);
+    for (i = 0; i < 8 && slot < 0; i++)
+        if (!pc->p[i]) slot = i;
+    if (slot < 0) /* full: keep the larger buffers */
+        for (i = 0; i < 8; i++)
+            if (pc->cap[i] < cap && (slot < 0 || pc->cap[i] < pc->cap[slot])) slot = i;
+    if (slot >= 0) {
+        drop = pc->p[slot];
+        pc->p[slot] = p;
+        pc->cap[slot] = cap;
+    }
+    pthread_mutex_unlock(&pc->mu);
+    if (drop) ppmx_gpu_host_free(pc->ctx, drop);
+}
+
+static void pin_cache_free(ppmx_pin_cache *pc)
+{
+    int i;
+    for (i = 0; i < 8; i++)
+        if (pc->p[i]) { ppmx_gpu_host_free(pc->ctx, pc->p[i]); pc->p[i] = NULL; }
+}
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* ref:1058-1069 + 409-456: the whole file into pinned memory; after the header it IS the packed raster (ref:316-318) */
+static int job_read(ppmx_pin_cache *pc, ppmx_job *j)
+{
+    FILE *fp = fopen(j->filename, "rb");
+    long sz;
+    size_t off = 0;
+    if (!fp) BAIL("error. can not open file\n"); /* ref:1059 */
+    if (fseek(fp, 0, SEEK_END) < 0) { fclose(fp); BAIL("error. can not set file position in fseek.\n"); }
+    sz = ftell(fp);
+    rewind(fp);
+    j->filesize = (size_t)(sz < 0 ? 0 : sz);
+    j->file_buffer = (unsigned char *)pin_get(pc, j->filesize + 1, &j->file_cap);
+    if (!j->file_buffer) { fclose(fp); BAIL("error. can not allocate memory\n"); }
+    if (fread(j->file_buffer, 1, j->filesize, fp) != j->filesize) {
+        fclose(fp);
+        BAIL("error in reading input file.\n"); /* ref:1069 */
+    }
+    fclose(fp);
+    if (j->filesize >= 2 && j->file_buffer[0] == 'P' && (j->file_buffer[1] == '3' || pnm_is_16bit(j->file_buffer, j->filesize))) {
         /* EXTENSION: an encoding the reference rejects (ref:386, 453) is decoded on the host into the same raster */
         int fmt = 0;
-        if (ppmx_probe_pnm(h->file_buffer, h->filesize, &w, &hh, &mx, &off, &fmt) != PPMX_OK) goto done;
-        decoded = (unsigned char *)ppmx_gpu_host_alloc(h->ctx, (size_t)w * hh * 3 + 1);
-        if (!decoded) { printf("error. can not allocate memory\n"); goto done; }
-        if (ppmx_decode_pnm(h->file_buffer, h->filesize, off, fmt, w, hh, mx, decoded, &mx) != PPMX_OK) goto done;
-        raster = decoded;
-        off = 0;
-    } else if (ppmx_parse_header(h->file_buffer, h->filesize, &w, &hh, &mx, &off) != PPMX_OK) goto done;
-    h->imginfo.width = w; h->imginfo.height = hh; h->imginfo.max_color = mx; h->index_buffer = off;
+        if (ppmx_probe_pnm(j->file_buffer, j->filesize, &j->w, &j->h, &j->maxval, &off, &fmt) != PPMX_OK) return PPMX_ERROR;
+        j->decoded = (unsigned char *)pin_get(pc, (size_t)j->w * j->h * 3 + 1, &j->decoded_cap);
+        if (!j->decoded) BAIL("error. can not allocate memory\n");
+        if (ppmx_decode_pnm(j->file_buffer, j->filesize, off, fmt, j->w, j->h, j->maxval, j->decoded, &j->maxval) != PPMX_OK)
+            return PPMX_ERROR;
+        j->raster = j->decoded;
+        return PPMX_OK;
+    }
+    if (ppmx_parse_header(j->file_buffer, j->filesize, &j->w, &j->h, &j->maxval, &off) != PPMX_OK) return PPMX_ERROR;
+    j->raster = j->file_buffer + off;
+    return PPMX_OK;
+}
 
-    if (ppmx_plan_chain_ext2(&h->arg_flag, h->output_width_size, h->angle, w, hh, h->conv_preset,
-                             h->levels_enable ? h->levels_lo : -1, h->levels_hi, &plan) != PPMX_OK) goto done;
-    if (plan.nops == 0) { printf("Error: no data to write\n"); goto done; } /* ref:235 */
-
+/* ref:1084-1155: the op chain, as one ppmx_gpu_apply call */
+static int job_run(const ppmx_image_handler *h, ppmx_gpu_ctx *ctx, ppmx_pin_cache *pc, ppmx_job *j)
+{
+    ppmx_plan plan;
+    unsigned int ow = j->w, oh = j->h;
+    int i, rc;
+    memset(&plan, 0, sizeof(plan));
+    if (ppmx_plan_chain_ext2(&h->arg_flag, h->output_width_size, h->angle, j->w, j->h, h->conv_preset,
+                             h->levels_enable ? h->levels_lo : -1, h->levels_hi, &plan) != PPMX_OK) return PPMX_ERROR;
+    if (plan.nops == 0) { ppmx_plan_free(&plan); BAIL("Error: no data to write\n"); } /* ref:235 */
     /* the largest raster any stage can hand to the writer is RGB at the final size */
-    ow = w; oh = hh;
-    for (i = 0; i < (size_t)plan.nops; i++) {
+    for (i = 0; i < plan.nops; i++) {
         int lay = PPMX_LAYOUT_RGB8;
         if (plan.ops[i].kind == PPMX_OP_IMRESIZE || plan.ops[i].kind == PPMX_OP_ROTATE)
             ppmx_gpu_op_output(&plan.ops[i], ow, oh, PPMX_LAYOUT_RGB8, &ow, &oh, &lay);
     }
-    cap = (size_t)ow * oh * 3 + 16;
-    out = (unsigned char *)ppmx_gpu_host_alloc(h->ctx, cap);
-    if (!out) { printf("error. can not allocate memory\n"); goto done; }
-
-    if (ppmx_gpu_apply(h->ctx, plan.ops, plan.nops, raster + off, w, hh, out, cap, &n, &ow, &oh, &ft) != PPMX_OK)
-        goto done;
-    h->imginfo.new_width = ow; h->imginfo.new_height = oh; h->imginfo.file_type = (unsigned int)ft;
-    rc = write_output(h->filename, ft, ow, oh, mx, out, n);
-done:
+    j->out = (unsigned char *)pin_get(pc, (size_t)ow * oh * 3 + 16, &j->out_cap);
+    if (!j->out) { ppmx_plan_free(&plan); BAIL("error. can not allocate memory\n"); }
+    rc = ppmx_gpu_apply(ctx, plan.ops, plan.nops, j->raster, j->w, j->h, j->out, j->out_cap, &j->out_bytes, &j->ow, &j->oh, &j->ft);
     ppmx_plan_free(&plan);
-    if (out) ppmx_gpu_host_free(h->ctx, out);
-    if (decoded) ppmx_gpu_host_free(h->ctx, decoded);
-    if (h->file_buffer) { ppmx_gpu_host_free(h->ctx, h->file_buffer); h->file_buffer = NULL; }
+    return rc;
+}
+
+static int job_write(ppmx_job *j) /* ref:221-301: header + ONE fwrite of the raster */
+{
+    return write_output(j->filename, j->ft, j->ow, j->oh, j->maxval, j->out, j->out_bytes);
+}
+
+static void job_release(ppmx_pin_cache *pc, ppmx_job *j)
+{
+    pin_put(pc, j->out, j->out_cap);
+    pin_put(pc, j->decoded, j->decoded_cap);
+    pin_put(pc, j->file_buffer, j->file_cap);
+    j->out = j->decoded = j->file_buffer = NULL;
+}
+
+static int open_ctx(ppmx_image_handler *h, int *own)
+{
+    *own = 0;
+    if (!h->ctx) {
+        /* PPMX_DEVICE = n: that GPU; PPMX_DEVICE = all: every visible GPU (one large raster is cut into row bands,
+         * a batch of files is dealt round-robin) */
+        const char *dev = getenv("PPMX_DEVICE");
+        int rc = (dev && strcmp(dev, "all") == 0) ? ppmx_gpu_init_multi(&h->ctx, NULL, 0) : ppmx_gpu_init(&h->ctx, dev ? atoi(dev) : 0);
+        if (rc != PPMX_OK) return PPMX_ERROR;
+        *own = 1;
+    }
+    return PPMX_OK;
+}
+
+int ppmx_doProcessPPM(ppmx_image_handler *h)
+{
+    ppmx_job j;
+    ppmx_pin_cache pc;
+    int own_ctx = 0, rc = PPMX_ERROR;
+    const int trace = getenv("PPMX_TRACE") != NULL;
+    double t0 = now_s(), t1, t2, t3, t4;
+
+    memset(&j, 0, sizeof(j));
+    memset(&pc, 0, sizeof(pc));
+    pthread_mutex_init(&pc.mu, NULL);
+    if (open_ctx(h, &own_ctx) != PPMX_OK) return PPMX_ERROR;
+    pc.ctx = h->ctx;
+    t1 = now_s();
+    j.filename = h->filename;
+    t2 = t3 = t1;
+    if (job_read(&pc, &j) == PPMX_OK) {
+        h->imginfo.width = j.w; h->imginfo.height = j.h; h->imginfo.max_color = j.maxval;
+        t2 = now_s();
+        if (job_run(h, h->ctx, &pc, &j) == PPMX_OK) {
+            h->imginfo.new_width = j.ow; h->imginfo.new_height = j.oh; h->imginfo.file_type = (unsigned int)j.ft;
+            t3 = now_s();
+            rc = job_write(&j);
+        }
+    }
+    t4 = now_s();
+    if (trace)
+        fprintf(stderr, "ppmx trace: device context %.1f ms, read+parse %.1f ms, chain (upload, kernels, download) %.1f ms, write %.1f ms\n",
+                1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3));
+    job_release(&pc, &j);
+    pin_cache_free(&pc);
+    pthread_mutex_destroy(&pc.mu);
     if (own_ctx) { ppmx_gpu_free(h->ctx); h->ctx = NULL; }
     return rc;
+}
+
+/* ---- EXTENSION: several files in one run (the reference takes exactly one, ref:180) -----------------------
+ * One device context for all of them, and a three-stage pipeline: a reader thread brings file n+1 into pinned memory
+ * and a writer thread puts result n-1 on disk while the calling thread runs the device chain of file n. */
+
+typedef struct ppmx_queue {
+    ppmx_job *slot[4];
+    int head, count, closed;
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+} ppmx_queue;
+
+static void q_init(ppmx_queue *q) { memset(q, 0, sizeof(*q)); pthread_mutex_init(&q->mu, NULL); pthread_cond_init(&q->cv, NULL); }
+static void q_push(ppmx_queue *q, ppmx_job *j)
+{
+    pthread_mutex_lock(&q->mu);
+    while (q->count == 2) pthread_cond_wait(&q->cv, &q->mu); /* at most two jobs wait between stages */
+    q->slot[(q->head + q->count) % 4] = j;
+    q->count++;
+    pthread_cond_broadcast(&q->cv);
+    pthread_mutex_unlock(&q->mu);
+}
+static ppmx_job *q_pop(ppmx_queue *q)
+{
+    ppmx_job *j = NULL;
+    pthread_mutex_lock(&q->mu);
+    while (q->count == 0 && !q->closed) pthread_cond_wait(&q->cv, &q->mu);
+    if (q->count) {
+        j = q->slot[q->head];
+        q->head = (q->head + 1) % 4;
+        q->count--;
+        pthread_cond_broadcast(&q->cv);
+    }
+    pthread_mutex_unlock(&q->mu);
+    return j;
+}
+static void q_close(ppmx_queue *q)
+{
+    pthread_mutex_lock(&q->mu);
+    q->closed = 1;
+    pthread_cond_broadcast(&q->cv);
+    pthread_mutex_unlock(&q->mu);
+}
+
+typedef struct ppmx_batch {
+    ppmx_job *jobs;
+    int njobs;
+    ppmx_pin_cache pc;
+    ppmx_queue read_q, write_q;
+} ppmx_batch;
+
+static void *reader_main(void *arg)
+{
+    ppmx_batch *b = (ppmx_batch *)arg;
+    int i;
+    for (i = 0; i < b->njobs; i++) {
+        b->jobs[i].rc = job_read(&b->pc, &b->jobs[i]);
+        q_push(&b->read_q, &b->jobs[i]);
+    }
+    q_close(&b->read_q);
+    return NULL;
+}
+
+static void *writer_main(void *arg)
+{
+    ppmx_batch *b = (ppmx_batch *)arg;
+    ppmx_job *j;
+    while ((j = q_pop(&b->write_q)) != NULL) {
+        if (j->rc == PPMX_OK) j->rc = job_write(j);
+        job_release(&b->pc, j);
+    }
+    return NULL;
+}
+
+int ppmx_doProcessBatch(ppmx_image_handler *h, const char *const *filenames, int nfiles)
+{
+    ppmx_batch b;
+    pthread_t rd, wr;
+    ppmx_job *j;
+    int own_ctx = 0, i, failed = 0;
+    const int trace = getenv("PPMX_TRACE") != NULL;
+    double t0 = now_s();
+    if (nfiles < 1 || !filenames) BAIL("Error: invalid options\n");
+    if (open_ctx(h, &own_ctx) != PPMX_OK) return PPMX_ERROR;
+    memset(&b, 0, sizeof(b));
+    b.jobs = (ppmx_job *)calloc((size_t)nfiles, sizeof(ppmx_job));
+    if (!b.jobs) { if (own_ctx) { ppmx_gpu_free(h->ctx); h->ctx = NULL; } BAIL("error. can not allocate memory\n"); }
+    b.njobs = nfiles;
+    for (i = 0; i < nfiles; i++) b.jobs[i].filename = filenames[i];
+    pthread_mutex_init(&b.pc.mu, NULL);
+    b.pc.ctx = h->ctx;
+    q_init(&b.read_q);
+    q_init(&b.write_q);
+    pthread_create(&rd, NULL, reader_main, &b);
+    pthread_create(&wr, NULL, writer_main, &b);
+    while ((j = q_pop(&b.read_q)) != NULL) {
+        if (j->rc == PPMX_OK) j->rc = job_run(h, h->ctx, &b.pc, j);
+        q_push(&b.write_q, j);
+    }
+    q_close(&b.write_q);
+    pthread_join(rd, NULL);
+    pthread_join(wr, NULL);
+    for (i = 0; i < nfiles; i++) failed += b.jobs[i].rc != PPMX_OK;
+    if (trace) fprintf(stderr, "ppmx trace: %d file(s), %d failed, %.1f ms in all\n", nfiles, failed, 1e3 * (now_s() - t0));
+    pin_cache_free(&b.pc);
+    pthread_mutex_destroy(&b.pc.mu);
+    free(b.jobs);
+    if (own_ctx) { ppmx_gpu_free(h->ctx); h->ctx = NULL; }
+    return failed ? PPMX_ERROR : PPMX_OK;
 }
 
 /* ------------------------------------------------------------------ command line */
@@ -790,15 +1022,22 @@ static int all_digits(const char *s)
 int ppmx_main(int argc, char *argv[])
 {
     ppmx_image_handler hd;
-    int i, have_file = 0;
+    int i, have_file = 0, batch = 0, nfiles = 0, rc;
+    const char **files = (const char **)calloc((size_t)(argc > 0 ? argc : 1), sizeof(char *));
+    if (!files) BAIL("error. can not allocate memory\n");
     memset(&hd, 0, sizeof(hd));
+    for (i = 1; i < argc; i++) /* EXTENSION flag -batch: any number of input files in one run (the reference takes one, ref:180) */
+        if (strcmp(argv[i], "-batch") == 0) batch = 1;
 
     for (i = 1; i < argc; i++) { /* same options, checks and messages as ref:125-183 */
         const char *a = argv[i];
         if (a[0] != '-') {
-            if (have_file) BAIL("Error: invalid options\n");
+            if (have_file && !batch) { free(files); BAIL("Error: invalid options\n"); } /* ref:180 */
             hd.filename = a;
+            files[nfiles++] = a;
             have_file = 1;
+        } else if (strcmp(a, "-batch") == 0) {
+            continue;
         } else if (a[1] == 'f') {
             if (a[2] == 'h') {
                 if (hd.arg_flag.fliph_enable) BAIL("Error: Duplicate options not allowed\n");
@@ -851,8 +1090,11 @@ int ppmx_main(int argc, char *argv[])
         }
     }
     if (!have_file) {
+        free(files);
         ppmx_usage();
         return PPMX_ERROR;
     }
-    return ppmx_doProcessPPM(&hd) != 0 ? PPMX_ERROR : 0;
+    rc = batch ? ppmx_doProcessBatch(&hd, files, nfiles) : ppmx_doProcessPPM(&hd);
+    free(files);
+    return rc != 0 ? PPMX_ERROR : 0;
 }

@@ -151,6 +151,10 @@ void ppmx_synth_lcg(unsigned char *rgb, size_t first, size_t npix, uint32_t seed
 int ppmx_getImageInfo(ppmx_image_handler *handler);   /* ref:409-456: parse + upload        */
 int ppmx_putImageToFile(ppmx_image_handler *handler); /* ref:221-301: download + one fwrite */
 int ppmx_doProcessPPM(ppmx_image_handler *handler);   /* ref:1053-1172                      */
+/* EXTENSION (the reference takes exactly one file, ref:180; the command line offers this as -batch): the handler's
+ * flags applied to every file, `<name>.out` beside each, on ONE device context, with file n+1 being read into pinned
+ * memory and result n-1 being written while the device works on file n.  Returns -1 if any file failed. */
+int ppmx_doProcessBatch(ppmx_image_handler *handler, const char *const *filenames, int nfiles);
 void ppmx_usage(void);                                /* ref:194-205 */
 int ppmx_main(int argc, char *argv[]);                /* ref:117-191 */
 

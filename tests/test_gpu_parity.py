@@ -808,3 +808,52 @@ def test_cuda_graph_replays_launches(gpu, orc):
     assert gpu.launch_count() - n0 == 2 + 4
     gpu.graph_free(graph)
     assert np.array_equal(out.cpu().numpy(), orc.gray(orc.conv(img, coef, div, bias)))
+
+
+def test_cli_batch_p3_and_multi_device(gpu, orc, tmp_path):
+    """EXTENSION flags of the command line: -batch (several files, one device context, file I/O overlapped with the device
+    work) gives the same files as one run per file; a P3 / 16-bit input gives the P6 result; PPMX_DEVICE=all spreads one
+    raster over every visible GPU as row bands."""
+    import imageprocessingtools_b200.ppmx as pp
+    imgs = [P.lcg(96 + 16 * i, 40 + 3 * i, 700 + i) for i in range(5)]
+    paths = []
+    for i, im in enumerate(imgs):
+        p = str(tmp_path / ("b%d.ppm" % i))
+        oracle.write_p6(p, im)
+        paths.append(p)
+    r = subprocess.run([pp.CLI, "-batch", "-r90", "-gray", "-fv"] + paths, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    for p, im in zip(paths, imgs):
+        exp, ew, eh, eft = orc.process(im, angle=90, gray=True, flipv=True)
+        assert open(p + ".out", "rb").read() == orc.header(eft, ew, eh, 255) + exp.tobytes(), p
+    # without -batch a second file name is refused like the reference does (ref:180)
+    r = subprocess.run([pp.CLI, "-gray", paths[0], paths[1]], capture_output=True, text=True)
+    assert r.returncode != 0 and "Error: invalid options" in r.stdout
+    # one bad file in a batch fails the run but the others are still written
+    bad = str(tmp_path / "bad.ppm")
+    open(bad, "wb").write(b"P6\n4 4\n255\nxx")
+    for p in paths:
+        os.remove(p + ".out")
+    r = subprocess.run([pp.CLI, "-batch", "-mono", paths[0], bad, paths[1]], capture_output=True, text=True)
+    assert r.returncode != 0 and os.path.exists(paths[0] + ".out") and os.path.exists(paths[1] + ".out")
+    # P3 and 16-bit P6 of the same picture
+    im = imgs[0]
+    h, w, _ = im.shape
+    p3 = str(tmp_path / "t.p3.ppm")
+    open(p3, "wb").write(b"P3\n%d %d\n255\n" % (w, h) + b" ".join(b"%d" % v for v in im.reshape(-1)) + b"\n")
+    p16 = str(tmp_path / "t.p16.ppm")
+    open(p16, "wb").write(b"P6\n%d %d\n65535\n" % (w, h) + (im.astype(np.uint16) * 257).astype(">u2").tobytes())
+    exp, ew, eh, eft = orc.process(im, gray=True)
+    for p in (p3, p16):
+        r = subprocess.run([pp.CLI, "-gray", p], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout
+        assert open(p + ".out", "rb").read() == orc.header(eft, ew, eh, 255) + exp.tobytes(), p
+    # every visible GPU on one raster
+    big = str(tmp_path / "big.ppm")
+    bimg = P.lcg(512, 700, 99)
+    oracle.write_p6(big, bimg)
+    env = dict(os.environ, PPMX_DEVICE="all", PPMX_PART_BYTES="100000")
+    r = subprocess.run([pp.CLI, "-blur", "-mono", "-fv", big], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout
+    exp, ew, eh, eft = _orc_chain(orc, bimg, conv_preset=1, mono=True, flipv=True)
+    assert open(big + ".out", "rb").read() == orc.header(eft, ew, eh, 255) + exp.tobytes()
