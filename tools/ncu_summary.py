@@ -25,6 +25,11 @@ WANT = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "st_wait"),
         ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64pipe%"),
         ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64cyc%"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
+        ("sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "fmaheavy%"),
+        ("sm__inst_executed.avg.per_cycle_elapsed", "ipc"),
+        ("smsp__inst_executed.sum", "warp_inst"),
         ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
         ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"),
         ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "ld_sectors"),
