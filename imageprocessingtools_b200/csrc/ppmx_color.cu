@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(256) gray_scalar_kernel(const uint8_t *__restr
 // of 16 pixels per thread the CTA folds the counters into 256 per-CTA totals (dp4a column sums)
 // and clears them; the totals go to global memory in one atomic pass at the end.
 constexpr int HP_THREADS = 256;
-constexpr int HP_MAX_GROUPS = 15;
-constexpr size_t HP_SMEM = (64 * HP_THREADS + 256) * sizeof(uint32_t);
+[[maybe_unused]] constexpr int HP_MAX_GROUPS = 15;
+[[maybe_unused]] constexpr size_t HP_SMEM = (64 * HP_THREADS + 256) * sizeof(uint32_t);
 
 __device__ __forceinline__ void hp_bump(uint8_t *mine, uint32_t g)
 {

@@ -322,6 +322,230 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
     }
 }
 
+// ---- the four orientations that keep rows rows (identity, horizontal / vertical flip, 180 degrees) -----------------
+// No tile is needed: a warp takes 32 consecutive 16-pixel groups of ONE source row (1536 bytes at any alignment).
+//   load   a thread reads the four aligned 16-byte vectors that cover its 48 bytes; the row's misalignment m (0..15) is
+//          the same for every thread of the row, so undoing it is a warp-uniform choice of a word offset (m / 4) and one
+//          funnel-shift amount (m % 4);
+//   tail   the same pointwise tails as the tile kernel (nothing, grey, .r, Bayer bits), pixel order reversed in
+//          registers when the row is mirrored;
+//   store  the warp's 32 results are one contiguous run of the destination row: they are laid down in a warp-private
+//          piece of shared memory in destination order and leave as aligned 16-byte vectors assembled by funnel shifts
+//          (up to 15 bytes at either end of the run byte by byte) -- rows of any pitch and alignment on both sides.
+constexpr int RS_STAGE = 48 + 32 * 48 + 16;  // 16 pixels of front pad (a ragged mirrored group starts inside it) + the run + slack
+
+// `nbytes` bytes from shared memory (4-byte aligned `srow`, run at byte `soff`) to any global address, by one warp
+__device__ __forceinline__ void store_run(uint8_t *g, const uint8_t *srow, uint32_t soff, uint32_t nbytes, uint32_t lane)
+{
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
+    const uint32_t hb = min(nbytes, (16u - a) & 15u), nv = (nbytes - hb) >> 4, tb = nbytes - hb - 16u * nv;
+    for (uint32_t k = lane; k < nv; k += 32u) {
+        const uint32_t q = soff + hb + 16u * k, sh = 8u * (q & 3u);
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(srow) + (q >> 2);
+        const uint32_t w0 = sw[0], w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sh ? sw[4] : 0u;
+        reinterpret_cast<uint4 *>(g + hb)[k] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                                                         __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+    if (lane < hb + tb) {
+        const uint32_t pos = lane < hb ? lane : nbytes - tb + (lane - hb);
+        g[pos] = srow[soff + pos];
+    }
+}
+
+template <int POINT, bool REV_X>
+__global__ void __launch_bounds__(128) rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t w, uint32_t h,
+                                                   uint32_t in_pitch, uint32_t out_pitch, const uint8_t *src_end, const GeomOp go)
+{
+    pdl_trigger();
+    __shared__ __align__(16) uint8_t stage_all[4][RS_STAGE];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t y = blockIdx.y, ngroups = (w + 15u) >> 4;
+    const uint32_t g0 = (blockIdx.x * 4u + warp) * 32u;  // the warp's first group
+    if (g0 >= ngroups) return;
+    const uint32_t grp = g0 + lane;
+    uint8_t *stage = stage_all[warp];
+    const uintptr_t A = reinterpret_cast<uintptr_t>(src) + (size_t)y * in_pitch + (size_t)grp * 48u;
+    const uint32_t m = (uint32_t)((reinterpret_cast<uintptr_t>(src) + (size_t)y * in_pitch) & 15u);  // 48 * grp is a multiple of 16
+    pdl_wait();
+
+    // ---- load: four aligned vectors cover [A, A + 48) whatever m is; none starts at or beyond the raster's end ------
+    uint32_t W[17];
+    {
+        const uint4 *vp = reinterpret_cast<const uint4 *>(A - m);
+        const bool live = grp < ngroups;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (live && reinterpret_cast<const uint8_t *>(vp + k) < src_end && (k < 3 || m)) v = __ldg(vp + k);
+            W[4 * k] = v.x, W[4 * k + 1] = v.y, W[4 * k + 2] = v.z, W[4 * k + 3] = v.w;
+        }
+        W[16] = 0u;
+    }
+    uint32_t in[12];  // 16 pixels, packed
+    {
+        const uint32_t sh = (m & 3u) * 8u;
+        switch (m >> 2) {  // warp-uniform: every group of a row is misaligned alike
+        case 0:
+#pragma unroll
+            for (int i = 0; i < 12; i++) in[i] = __funnelshift_r(W[i], W[i + 1], sh);
+            break;
+        case 1:
+#pragma unroll
+            for (int i = 0; i < 12; i++) in[i] = __funnelshift_r(W[i + 1], W[i + 2], sh);
+            break;
+        case 2:
+#pragma unroll
+            for (int i = 0; i < 12; i++) in[i] = __funnelshift_r(W[i + 2], W[i + 3], sh);
+            break;
+        default:
+#pragma unroll
+            for (int i = 0; i < 12; i++) in[i] = __funnelshift_r(W[i + 3], W[i + 4], sh);
+            break;
+        }
+    }
+
+    // ---- where this warp's run lies in the destination row -----------------------------------------------------------
+    // pixels [16 g0, min(w, 16 g0 + 512)) of the source row; mirrored, the run starts at pixel max(0, w - 16 g0 - 512)
+    // The staging area counts pixels from 16 before the run's first one (a front pad): the run starts at staging pixel 16.
+    // Source pixel px0 + 16 lane + k goes to run pixel 16 lane + k, or mirrored to npx - 1 - 16 lane - k: the reversed block
+    // of a group then starts at run pixel npx - 16 - 16 lane, which for the row's ragged last group lies inside the pad.
+    const uint32_t px0 = 16u * g0, npx = min(512u, w - px0);
+    const bool inrun = 16u * lane < npx;
+    const uint32_t P = REV_X ? npx - 16u * lane : 16u + 16u * lane;  // this group's block, in staging pixels (inrun lanes only)
+    const bool vec_ok = !REV_X || (npx & 15u) == 0u;                 // blocks sit on 16-byte boundaries of the staging area
+
+    // ---- pointwise tail, in destination order ----------------------------------------------------------------------
+    if (POINT == GP_RGB) {
+        uint32_t o[12];
+        if (REV_X) {
+#pragma unroll
+            for (int kk = 0; kk < 12; kk++) {  // reverse the order of 16 packed pixels: byte selections only (PRMT)
+                const int ob0 = 4 * kk;
+                uint32_t v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int ob = ob0 + b, ib = 3 * (15 - ob / 3) + (ob % 3);
+                    v |= ((in[ib >> 2] >> (8 * (ib & 3))) & 0xFFu) << (8 * b);
+                }
+                o[kk] = v;
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < 12; kk++) o[kk] = in[kk];
+        }
+        if (inrun) {
+            uint8_t *q = stage + 3u * P;
+            if (vec_ok) {
+                uint4 *q4 = reinterpret_cast<uint4 *>(q);
+                q4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                q4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                q4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 12; kk++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) q[4 * kk + b] = (uint8_t)(o[kk] >> (8 * b));
+            }
+        }
+    } else {
+        uint32_t val[16];
+        int thr3[4] = {0, 0, 0, 0};
+        if (POINT == GP_MONO) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {  // x = 16 grp + 4 k + i: x % 4 == i
+                const uint32_t sx = (uint32_t)i, sy = y;
+                const uint32_t cx = go.mx_from_y ? sy : sx, cy = go.mx_from_y ? sx : sy;
+                const uint32_t xm = ((go.mx_neg ? 0u - cx : cx) + (uint32_t)go.mx_add) & 3u;
+                const uint32_t ym = ((go.my_neg ? 0u - cy : cy) + (uint32_t)go.my_add) & 3u;
+                thr3[i] = -3 * (int)c_bayer[xm * 4u + ym];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {  // 4 pixels in 3 words
+            const uint32_t a = in[3 * i], b = in[3 * i + 1], c = in[3 * i + 2];
+            if (POINT == GP_RED) {
+                val[4 * i] = a & 0xFFu;
+                val[4 * i + 1] = a >> 24;
+                val[4 * i + 2] = (b >> 16) & 0xFFu;
+                val[4 * i + 3] = (c >> 8) & 0xFFu;
+            } else {
+                const uint32_t t0 = POINT == GP_MONO ? (uint32_t)thr3[0] : 0u, t1 = POINT == GP_MONO ? (uint32_t)thr3[1] : 0u;
+                const uint32_t t2 = POINT == GP_MONO ? (uint32_t)thr3[2] : 0u, t3 = POINT == GP_MONO ? (uint32_t)thr3[3] : 0u;
+                const uint32_t s0 = __dp4a(a, 0x00010101u, t0), s1 = __dp4a(a, 0x01000000u, __dp4a(b, 0x00000101u, t1));
+                const uint32_t s2 = __dp4a(b, 0x01010000u, __dp4a(c, 0x00000001u, t2)), s3 = __dp4a(c, 0x01010100u, t3);
+                if (POINT == GP_GRAY) {
+                    val[4 * i] = div3(s0), val[4 * i + 1] = div3(s1), val[4 * i + 2] = div3(s2), val[4 * i + 3] = div3(s3);
+                } else {
+                    val[4 * i] = s0 >> 31, val[4 * i + 1] = s1 >> 31, val[4 * i + 2] = s2 >> 31, val[4 * i + 3] = s3 >> 31;
+                }
+            }
+        }
+        if (POINT == GP_MONO) {
+            uint32_t bits = 0;  // first DESTINATION pixel in the most significant bit (ref:273)
+#pragma unroll
+            for (int k = 0; k < 16; k++) bits |= val[REV_X ? 15 - k : k] << (15 - k);
+            const uint32_t valid = 16u * lane < npx ? min(16u, npx - 16u * lane) : 0u;  // pixels beyond the row are pad bits: zero
+            if (valid < 16u) bits &= REV_X ? (0xFFFFu >> (16u - valid)) : (0xFFFFu << (16u - valid));
+            if (inrun) {
+                uint8_t *q = stage + (P >> 3);  // (a mirrored row of bits has w % 8 == 0, so P is a multiple of 8)
+                q[0] = (uint8_t)(bits >> 8);
+                q[1] = (uint8_t)bits;
+            }
+        } else {
+            uint32_t o[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const int i0 = REV_X ? 15 - 4 * kk : 4 * kk, st = REV_X ? -1 : 1;
+                o[kk] = val[i0] | (val[i0 + st] << 8) | (val[i0 + 2 * st] << 16) | (val[i0 + 3 * st] << 24);
+            }
+            if (inrun) {
+                uint8_t *q = stage + P;
+                if (vec_ok) *reinterpret_cast<uint4 *>(q) = make_uint4(o[0], o[1], o[2], o[3]);
+                else {
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) q[4 * kk + b] = (uint8_t)(o[kk] >> (8 * b));
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- store: the run, to wherever the destination row puts it ----------------------------------------------------------
+    const uint32_t oy = go.rev_y ? h - 1u - y : y;
+    const uint32_t xs = REV_X ? w - px0 - npx : px0;  // first destination pixel of the run
+    uint32_t nbytes, soff;
+    size_t goff;
+    if (POINT == GP_RGB) nbytes = npx * 3u, soff = 48u, goff = (size_t)xs * 3;
+    else if (POINT == GP_MONO) nbytes = (npx + 7u) >> 3, soff = 2u, goff = xs >> 3;
+    else nbytes = npx, soff = 16u, goff = xs;
+    store_run(dst + (size_t)oy * out_pitch + goff, stage, soff, nbytes, lane);
+}
+
+template <int POINT, bool REV_X>
+static cudaError_t rows_launch(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t in_pitch, uint32_t out_pitch,
+                               const GeomOp &go, cudaStream_t s)
+{
+    const uint32_t ngroups = (w + 15u) / 16u;
+    const uint8_t *src_end = src + (size_t)(h - 1) * in_pitch + (size_t)w * 3;
+    for (uint32_t y0 = 0; y0 < h; y0 += 65535u) {  // rows ride on grid.y
+        const uint32_t rows = h - y0 < 65535u ? h - y0 : 65535u;
+        GeomOp g2 = go;
+        // mono's Bayer phase counts whole-raster rows: shift it by the slab's first source row
+        const int shift = (int)(y0 & 3u);
+        if (g2.mx_from_y) g2.mx_add = (g2.mx_add + (g2.mx_neg ? 4 - shift : shift)) & 3;
+        else g2.my_add = (g2.my_add + (g2.my_neg ? 4 - shift : shift)) & 3;
+        // a vertically mirrored slab lands at the mirrored place
+        uint8_t *d0 = dst + (size_t)(go.rev_y ? h - y0 - rows : y0) * out_pitch;
+        dim3 grid((ngroups + 127u) / 128u, rows);
+        launch(rows_kernel<POINT, REV_X>, grid, dim3(128), 0, s, src + (size_t)y0 * in_pitch, d0, w, rows, in_pitch, out_pitch, src_end, g2);
+        cudaError_t e = PPMX_LAUNCHED();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 template <int TRANSPOSE, bool REV_X, int POINT>
 static cudaError_t geom_launch(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t in_pitch, uint32_t out_pitch,
                                const GeomOp &go, cudaStream_t s)
@@ -376,26 +600,29 @@ cudaError_t geom_point(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h,
     case GP_MONO: return geom_launch<T, R, GP_MONO>(src, dst, w, h, in_pitch, out_pitch, go, s);   \
     default: return cudaErrorInvalidValue;                                                         \
     }
+#define PPMX_ROWS_P(R)                                                                             \
+    switch (go.point) {                                                                            \
+    case GP_RGB: return rows_launch<GP_RGB, R>(src, dst, w, h, in_pitch, out_pitch, go, s);        \
+    case GP_GRAY: return rows_launch<GP_GRAY, R>(src, dst, w, h, in_pitch, out_pitch, go, s);      \
+    case GP_RED: return rows_launch<GP_RED, R>(src, dst, w, h, in_pitch, out_pitch, go, s);        \
+    case GP_MONO: return rows_launch<GP_MONO, R>(src, dst, w, h, in_pitch, out_pitch, go, s);      \
+    default: return cudaErrorInvalidValue;                                                         \
+    }
     if (go.transpose) {
         if (go.rev_x) { PPMX_GEOM_P(1, true) } else { PPMX_GEOM_P(1, false) }
     } else {
-        if (go.rev_x) { PPMX_GEOM_P(0, true) } else { PPMX_GEOM_P(0, false) }
+        if (go.rev_x) { PPMX_ROWS_P(true) } else { PPMX_ROWS_P(false) }
     }
 #undef PPMX_GEOM_P
+#undef PPMX_ROWS_P
 }
 
-// rows of 3 * w bytes from one pitch to another (any alignment either side): the tile kernel as a plain copy
+// rows of 3 * w bytes from one pitch to another (any alignment either side): the row kernel as a plain copy
 cudaError_t geom_repitch(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, uint32_t in_pitch, uint32_t out_pitch, cudaStream_t s)
 {
     if (!w || !h) return cudaSuccess;
     GeomOp go = {};
-    for (uint32_t y = 0; y < h; y += 65535u * 64u) {
-        const uint32_t rows = h - y < 65535u * 64u ? h - y : 65535u * 64u;
-        cudaError_t e = geom_launch<0, false, GP_RGB>(src + (size_t)y * in_pitch, dst + (size_t)y * out_pitch, w, rows, in_pitch,
-                                                      out_pitch, go, s);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    return rows_launch<GP_RGB, false>(src, dst, w, h, in_pitch, out_pitch, go, s);
 }
 
 }  // namespace ppmx

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) reverse_pixels_kernel(const uint8_t *__re
 //   90:  out[x][h-1-y] = in[y][x]   (ref:717)      out is h wide, w tall
 //   270: out[w-1-x][y] = in[y][x]   (ref:725)
 constexpr int RT = 32;            // tile edge in pixels
-constexpr int RT_PITCH = RT * 3 + 4;  // bytes; +4 keeps column reads off a single bank
+[[maybe_unused]] constexpr int RT_PITCH = RT * 3 + 4;  // bytes; +4 keeps column reads off a single bank
 
 template <bool CW>
 __global__ void __launch_bounds__(256) rotate_transpose_kernel(const uint8_t *__restrict__ src,
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256) rotate_transpose_kernel(const uint8_t *__
 // bytes at a time and writes destination rows the same way (every global access is one 32-byte sector per
 // instruction); no division by a run-time value.  4090 x 4090: 0.125 (32 x 32 byte-indexed tile, variant 1) -> 0.26 of the roofline.
 constexpr int RA = 64;
-constexpr int RA_PITCH = RA * 3 + 4;  // 196 B = 49 words: consecutive tile rows start 17 banks apart
+[[maybe_unused]] constexpr int RA_PITCH = RA * 3 + 4;  // 196 B = 49 words: consecutive tile rows start 17 banks apart
 
 template <bool CW>
 __global__ void __launch_bounds__(256) rotate_transpose_any_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(256) rotate_transpose_any_kernel(const uint8_t
 //   phase 2: a lane reads one source column over 16 source rows, one word per row (conflict
 //            free), repacks the 16 pixels to 48 B and writes them as three 16-byte stores into
 //            the destination row that column became; 4 lanes complete 192 contiguous bytes.
-constexpr int XT = 64;
+[[maybe_unused]] constexpr int XT = 64;
 
 __device__ __forceinline__ uint32_t xt_slot(uint32_t row, uint32_t chunk)
 {
