@@ -197,17 +197,18 @@ class StepRunner:
     recording go round-robin over that many streams forked from / joined into the timing stream (independent
     rasters: their ramps and tails overlap)."""
 
-    def __init__(self, torch, g, calls, replays=1, graph=True, lanes=1):
+    def __init__(self, torch, g, calls, replays=1, graph=True, lanes=1, fn=None, kernels_per_call=1):
         import ctypes as C
         self.torch, self.g, self.calls, self.replays, self.lanes = torch, g, calls, replays, max(1, lanes)
         self.C = C
+        self.fn = fn if fn is not None else g.L.ppmx_gpu_launch  # any ABI call whose LAST argument is the stream
         self.main = torch.cuda.current_stream()
         self.side = [torch.cuda.Stream() for _ in range(self.lanes - 1)]
         self.fork = torch.cuda.Event()
         self.join = [torch.cuda.Event() for _ in self.side]
         self.graph = None
         self.mode = "direct launches (prebuilt argument lists)"
-        self.launches_per_step = len(calls) * replays
+        self.launches_per_step = len(calls) * replays * kernels_per_call
         if graph:
             try:
                 g.graph_begin(self.main.cuda_stream)
@@ -215,8 +216,8 @@ class StepRunner:
                     self._issue()
                 finally:
                     self.graph, n = g.graph_end(self.main.cuda_stream)
-                if n != len(calls):
-                    raise RuntimeError("graph holds %d kernel nodes, expected %d" % (n, len(calls)))
+                if n != len(calls) * kernels_per_call:
+                    raise RuntimeError("graph holds %d kernel nodes, expected %d" % (n, len(calls) * kernels_per_call))
                 self.mode = "CUDA graph of %d kernel nodes (ppmx_gpu_graph_*), %d replay(s) per step" % (n, replays)
             except Exception as e:  # stay measurable without graphs; say so in the line
                 self.graph = None
@@ -225,7 +226,7 @@ class StepRunner:
             self.mode += ", %d streams" % self.lanes
 
     def _issue(self):
-        C, fn = self.C, self.g.L.ppmx_gpu_launch
+        C, fn = self.C, self.fn
         streams = [self.main] + self.side
         ptrs = [C.c_void_p(s.cuda_stream) for s in streams]
         if self.side:
@@ -235,7 +236,7 @@ class StepRunner:
         n = len(streams)
         for i, a in enumerate(self.calls):
             if fn(*a, ptrs[i % n]) != 0:
-                raise RuntimeError("ppmx_gpu_launch failed")
+                raise RuntimeError("launch failed")
         for s, e in zip(self.side, self.join):
             e.record(s)
             self.main.wait_event(e)
@@ -829,13 +830,40 @@ def batch_chain_run(torch, g, dist, world, images=128):
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        out.append({"chain": label, "images": images * world, "frame": "%dx%d" % (w, h),
-                    "out": "%dx%d type %d" % (ow.value, oh.value, ft.value),
-                    "kernels_per_frame": round(kernels, 2), "stages": info[5],
-                    "e2e_mpix_s": round(world * images * w * h / dt / 1e6, 1),
-                    "images_per_s": round(world * images / dt, 1)})
-        ph.close()
+        ent = {"chain": label, "images": images * world, "frame": "%dx%d" % (w, h),
+               "out": "%dx%d type %d" % (ow.value, oh.value, ft.value),
+               "kernels_per_frame": round(kernels, 2), "stages": info[5],
+               "e2e_mpix_s": round(world * images * w * h / dt / 1e6, 1),
+               "images_per_s": round(world * images / dt, 1)}
         del dst
+        # the same chain on frames that are already in HBM (ppmx_gpu_chain_prepare / _run): kernels only
+        try:
+            lanes = 3
+            dsrc = src.cuda()
+            prepared = [g.chain_prepare(ops, w, h) for _ in range(lanes)]
+            meta = prepared[0][1]
+            ddst = [torch.empty(meta["out_bytes"] + 16, dtype=torch.uint8, device="cuda") for _ in range(lanes)]
+            calls = [(prepared[i % lanes][0], C.c_void_p(dsrc[i].data_ptr()), C.c_void_p(ddst[i % lanes].data_ptr()))
+                     for i in range(images)]
+            run = StepRunner(torch, g, calls, 1, True, lanes, fn=g.L.ppmx_gpu_chain_run, kernels_per_call=meta["kernels"])
+            t, _, _ = time_runner(torch, run, 3, 2, dist)
+            nst = max(3, min(200, int(60.0 / max(t / 3, 1e-3))))
+            t, _, _ = time_runner(torch, run, nst, 1, dist)
+            fps = world * nst * images / (t / 1e3)
+            ent.update({"device_resident_images_per_s": round(fps, 1),
+                        "device_resident_mpix_s": round(fps * w * h / 1e6, 1),
+                        "bytes_moved_per_frame": meta["bytes_moved"],
+                        "device_resident_gbs": round(fps * meta["bytes_moved"] / 1e9 / world, 1),
+                        "device_resident_launch": run.mode})
+            run.close()
+            for ch, _ in prepared:
+                g.chain_free(ch)
+            del dsrc, ddst
+            torch.cuda.empty_cache()
+        except Exception as e:
+            ent["device_resident_error"] = str(e)[:160]
+        out.append(ent)
+        ph.close()
     return out
 
 

@@ -770,3 +770,102 @@ extern "C" int ppmx_gpu_band_rows(const ppmx_op *ops, int nops, uint32_t w, uint
     if (src_rows) *src_rows = a < b ? need.hi - need.lo : 0;
     return PPMX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// a chain prepared once and run on rasters that are ALREADY in HBM (device-resident batches, benchmarks): the
+// intermediate rasters and resize tables are allocated at prepare time, so a run is kernel launches only and can be
+// recorded into a CUDA graph (ppmx_gpu_graph_*)
+// ---------------------------------------------------------------------------------------------
+
+struct ppmx_gpu_chain {
+    ppmx_gpu_ctx *c = nullptr;
+    Pipeline P;
+    std::vector<DeviceTables> tables;
+    std::vector<uint8_t *> mid;  // output raster of every stage but the last
+};
+
+extern "C" void ppmx_gpu_chain_free(ppmx_gpu_chain *ch)
+{
+    if (!ch) return;
+    if (ch->c) {
+        cudaSetDevice(ch->c->device);
+        cudaStreamSynchronize(ch->c->lane[0]);
+        for (uint8_t *p : ch->mid)
+            if (p) cudaFreeAsync(p, ch->c->lane[0]);
+        for (auto &t : ch->tables)
+            if (t.base) cudaFreeAsync(t.base, ch->c->lane[0]);
+    }
+    delete ch;
+}
+
+extern "C" int ppmx_gpu_chain_prepare(ppmx_gpu_ctx *c, const ppmx_op *ops, int nops, uint32_t w, uint32_t h, ppmx_gpu_chain **out)
+{
+    if (!c || !ops || nops < 1 || !out) return fail("ppmx_gpu_chain_prepare: bad argument");
+    *out = nullptr;
+    c = primary(c);
+    PPMX_CK(cudaSetDevice(c->device), "cudaSetDevice");
+    ppmx_gpu_chain *ch = new (std::nothrow) ppmx_gpu_chain();
+    if (!ch) return fail("out of host memory");
+    ch->c = c;
+    int rc = build_pipeline(ops, nops, w, h, &ch->P);
+    if (rc == PPMX_OK && ch->P.hist_stage >= 0) rc = fail("a prepared chain can not hold a histogram stage");
+    ch->tables.assign(nops, DeviceTables());
+    ch->mid.assign(ch->P.st.size(), nullptr);
+    size_t last = 0;
+    for (size_t i = 0; i < ch->P.st.size(); i++)
+        if (!ch->P.st[i].passthrough) last = i;
+    for (size_t i = 0; i < ch->P.st.size() && rc == PPMX_OK; i++) {
+        const Stage &st = ch->P.st[i];
+        if (st.op.kind == PPMX_OP_IMRESIZE && st.op_index >= 0 && !ch->tables[st.op_index].base)
+            rc = upload_tables(c, &st.op, &ch->tables[st.op_index], c->lane[0]);
+        if (rc == PPMX_OK && i != last && !st.passthrough &&
+            pool_alloc(c, (void **)&ch->mid[i], row_bytes(st.out_w, st.out_layout) * st.out_h + 16, c->lane[0]) != cudaSuccess)
+            rc = fail("can not allocate image buff in HBM");
+    }
+    if (rc == PPMX_OK && cudaStreamSynchronize(c->lane[0]) != cudaSuccess) rc = fail("sync");
+    if (rc != PPMX_OK) {
+        ppmx_gpu_chain_free(ch);
+        return rc;
+    }
+    *out = ch;
+    return PPMX_OK;
+}
+
+extern "C" int ppmx_gpu_chain_info2(const ppmx_gpu_chain *ch, uint32_t *out_w, uint32_t *out_h, int *out_file_type, size_t *out_bytes,
+                                    int *kernels, size_t *bytes_moved)
+{
+    if (!ch) return fail("ppmx_gpu_chain_info2: null chain");
+    const Pipeline &P = ch->P;
+    if (out_w) *out_w = P.out_w;
+    if (out_h) *out_h = P.out_h;
+    if (out_file_type) *out_file_type = P.file_type;
+    if (out_bytes) *out_bytes = P.out_bytes();
+    if (kernels) *kernels = (int)P.st.size();
+    if (bytes_moved) {  // what the stages read and write, by their algorithmic raster sizes
+        size_t t = 0;
+        for (const Stage &st : P.st)
+            t += row_bytes(st.in_w, st.in_layout) * st.in_h + (st.passthrough ? 0 : row_bytes(st.out_w, st.out_layout) * st.out_h);
+        *bytes_moved = t;
+    }
+    return PPMX_OK;
+}
+
+extern "C" int ppmx_gpu_chain_run(ppmx_gpu_chain *ch, const void *d_src, void *d_dst, void *stream)
+{
+    if (!ch || !d_src || !d_dst) return fail("ppmx_gpu_chain_run: null argument");
+    const Pipeline &P = ch->P;
+    const uint8_t *S = (const uint8_t *)d_src;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P.st.empty()) {  // (a chain of "-r0" alone: the raster as it is)
+        PPMX_CK(cudaMemcpyAsync(d_dst, d_src, P.out_bytes(), cudaMemcpyDeviceToDevice, s), "copy");
+        return PPMX_OK;
+    }
+    for (size_t i = 0; i < P.st.size(); i++) {
+        const Stage &st = P.st[i];
+        const DeviceTables *t = (st.op.kind == PPMX_OP_IMRESIZE && st.op_index >= 0) ? &ch->tables[st.op_index] : nullptr;
+        uint8_t *D = ch->mid[i] ? ch->mid[i] : (uint8_t *)d_dst;
+        if (launch_stage(st, S, Rows{0, st.in_h}, D, 0, st.out_h, nullptr, t, s) != PPMX_OK) return PPMX_ERROR;
+        S = D;
+    }
+    return PPMX_OK;
+}

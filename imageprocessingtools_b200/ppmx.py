@@ -101,6 +101,12 @@ def _declare(L: C.CDLL) -> C.CDLL:
                                           C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ppmx_gpu_band_rows.argtypes = [C.POINTER(PpmxOp), C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u32p, _u32p,
                                          _u32p, _u32p]
+        L.ppmx_gpu_chain_prepare.argtypes = [vp, C.POINTER(PpmxOp), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+        L.ppmx_gpu_chain_run.argtypes = [vp, vp, vp, vp]
+        L.ppmx_gpu_chain_info2.argtypes = [vp, _u32p, _u32p, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int),
+                                           C.POINTER(C.c_size_t)]
+        L.ppmx_gpu_chain_free.argtypes = [vp]
+        L.ppmx_gpu_chain_free.restype = None
         L.ppmx_gpu_graph_begin.argtypes = [vp]
         L.ppmx_gpu_graph_end.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
         L.ppmx_gpu_graph_launch.argtypes = [vp, vp]
@@ -514,6 +520,24 @@ class Ppmx:
     @staticmethod
     def chain_info(ops, w: int, h: int):
         return chain_info(ops, w, h)
+
+    # -- a chain prepared for device-resident rasters ----------------------------------------------
+    def chain_prepare(self, ops, w: int, h: int):
+        arr = (PpmxOp * len(ops))(*ops)
+        ch = C.c_void_p()
+        if self.L.ppmx_gpu_chain_prepare(self.ctx, arr, len(ops), w, h, C.byref(ch)) != 0:
+            raise PpmxError("ppmx_gpu_chain_prepare failed")
+        ow, oh, ft, nb, k, moved = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_size_t(), C.c_int(), C.c_size_t()
+        self.L.ppmx_gpu_chain_info2(ch, C.byref(ow), C.byref(oh), C.byref(ft), C.byref(nb), C.byref(k), C.byref(moved))
+        return ch, dict(out_w=ow.value, out_h=oh.value, file_type=ft.value, out_bytes=nb.value, kernels=k.value,
+                        bytes_moved=moved.value)
+
+    def chain_run(self, chain, d_src: int, d_dst: int, stream: int = 0) -> None:
+        if self.L.ppmx_gpu_chain_run(chain, C.c_void_p(d_src), C.c_void_p(d_dst), C.c_void_p(stream)) != 0:
+            raise PpmxError("ppmx_gpu_chain_run failed")
+
+    def chain_free(self, chain) -> None:
+        self.L.ppmx_gpu_chain_free(chain)
 
     # -- CUDA graphs over raw launches ---------------------------------------------------------
     def graph_begin(self, stream: int) -> None:

@@ -87,6 +87,7 @@ typedef struct ppmx_op {
 typedef struct ppmx_gpu_ctx ppmx_gpu_ctx;     /* one CUDA device (or several), streams, a private buffer pool */
 typedef struct ppmx_gpu_image ppmx_gpu_image; /* a raster resident in HBM                   */
 typedef struct ppmx_gpu_graph ppmx_gpu_graph; /* a recorded sequence of raw launches        */
+typedef struct ppmx_gpu_chain ppmx_gpu_chain; /* an op chain prepared for device-resident rasters */
 
 /* ---- lifetime ------------------------------------------------------------------------ */
 
@@ -159,6 +160,18 @@ int ppmx_gpu_band_rows(const ppmx_op *ops, int nops, uint32_t w, uint32_t h, int
 int ppmx_gpu_chain_info(const ppmx_op *ops, int nops, uint32_t w, uint32_t h, uint32_t *out_w,
                         uint32_t *out_h, int *out_file_type, size_t *out_bytes, int *splittable,
                         int *kernels);
+
+/* The same chain for rasters that are ALREADY in HBM (a device-resident batch): prepare linearises and fuses the
+ * chain for w x h rasters, uploads the resize tables and allocates the intermediate rasters once; run then only
+ * launches kernels (d_src -> d_dst, caller-owned device memory, any stream; recordable with ppmx_gpu_graph_*).
+ * One prepared chain serves one stream at a time (the intermediates are its own).  Histogram stages are not taken. */
+int ppmx_gpu_chain_prepare(ppmx_gpu_ctx *ctx, const ppmx_op *ops, int nops, uint32_t w, uint32_t h,
+                           ppmx_gpu_chain **chain);
+int ppmx_gpu_chain_run(ppmx_gpu_chain *chain, const void *d_src, void *d_dst, void *stream);
+/* geometry, writer's file type and bytes of the result; kernels per run; bytes the stages read + write per run */
+int ppmx_gpu_chain_info2(const ppmx_gpu_chain *chain, uint32_t *out_w, uint32_t *out_h, int *out_file_type,
+                         size_t *out_bytes, int *kernels, size_t *bytes_moved);
+void ppmx_gpu_chain_free(ppmx_gpu_chain *chain);
 
 /* ---- device-resident rasters: one operator per call ---------------------------------- */
 

@@ -80,3 +80,35 @@ def test_odd_size_rotations_take_the_tile_kernel(gpu, orc):
         img = P.lcg(w, h, 77)
         for a in (90, 270):
             assert np.array_equal(gpu.rotate(img, a), orc.rotate(img, a)), (w, h, a)
+
+
+def test_prepared_chain_on_device_rasters(gpu, orc):
+    """ppmx_gpu_chain_prepare / _run: the chain on a raster already in HBM, recorded into a CUDA graph and replayed."""
+    import torch
+    import imageprocessingtools_b200.ppmx as pp
+    dev = torch.device("cuda", 0)
+    for (w, h, kw) in [(1920, 1080, dict(angle=90, mono=True, fliph=True)), (200, 56, dict(resize_w=100, angle=90, gray=True, flipv=True)),
+                       (130, 70, dict(conv_preset=1, mono=True, flipv=True)), (64, 64, dict(angle=0))]:
+        img = P.lcg(w, h, 31 + w)
+        ph = pp._PlanHolder(w=w, h=h, **kw)
+        ops = [ph.plan.ops[i] for i in range(ph.plan.nops)]
+        ch, meta = gpu.chain_prepare(ops, w, h)
+        src = torch.from_numpy(img).to(dev)
+        dst = torch.zeros(meta["out_bytes"] + 16, dtype=torch.uint8, device=dev)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            gpu.graph_begin(s.cuda_stream)
+            gpu.chain_run(ch, src.data_ptr(), dst.data_ptr(), s.cuda_stream)
+            graph, nodes = gpu.graph_end(s.cuda_stream)
+            assert nodes == meta["kernels"] or kw == dict(angle=0)
+            gpu.graph_launch(graph, s.cuda_stream)
+            s.synchronize()
+        gpu.graph_free(graph)
+        if "conv_preset" in kw:
+            exp = orc.process(orc.conv(img, np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]]), 16, 0), angle=0, mono=True, flipv=True)
+        else:
+            exp = orc.process(img, **kw)
+        got = dst.cpu().numpy()[:meta["out_bytes"]]
+        assert (meta["out_w"], meta["out_h"], meta["file_type"]) == exp[1:] and np.array_equal(got, exp[0]), kw
+        gpu.chain_free(ch)
+        ph.close()
