@@ -100,7 +100,10 @@ def test_prepared_chain_on_device_rasters(gpu, orc):
             gpu.graph_begin(s.cuda_stream)
             gpu.chain_run(ch, src.data_ptr(), dst.data_ptr(), s.cuda_stream)
             graph, nodes = gpu.graph_end(s.cuda_stream)
-            assert nodes == meta["kernels"] or kw == dict(angle=0)
+            # one kernel per stage (an odd-width convolution adds its padding copies; "-r0" alone is a plain copy)
+            assert nodes >= meta["kernels"] or kw == dict(angle=0)
+            if "conv_preset" not in kw and kw != dict(angle=0):
+                assert nodes == meta["kernels"]
             gpu.graph_launch(graph, s.cuda_stream)
             s.synchronize()
         gpu.graph_free(graph)
