@@ -322,6 +322,126 @@ __global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource sr
     reinterpret_cast<vec_t *>(dst + (size_t)y * row_bytes)[xv] = ov;
 }
 
+// Height pass, TWO output rows per CTA (a thread: 8 bytes of each).  Away from the raster's top and bottom the K taps of an
+// output row are K consecutive source rows, and the next output row's taps start `delta` rows further (0 or 1 when
+// upscaling, about 1/scale when downscaling): the pair reads K + delta distinct source rows instead of 2 K, and every source
+// byte is converted to double ONCE for both rows -- the conversions (XU pipe, 16 lanes/clk/SM) are what kept the FP64 pipe at
+// 55 % in the one-row kernel.  Each row's sum still runs over its own taps in tap order with separately rounded products
+// and sums (ref:826-830), so the bytes are the same.  Pairs whose taps are not consecutive rows (mirrored taps at the
+// raster's ends) and a last odd row take the one-row arithmetic inside the same kernel.
+template <int CONV, int KT>
+__global__ void __launch_bounds__(256) imresize_rows8x2_kernel(const RowSource src, uint8_t *__restrict__ dst, uint32_t row_vecs,
+                                                               int out_rows, const double *__restrict__ wts,
+                                                               const int *__restrict__ idx)
+{
+    PDL_PROLOGUE();
+    __shared__ double s_w[2][KT];
+    __shared__ int s_i[2][KT];
+    const int y0 = 2 * blockIdx.y;
+    const bool two = y0 + 1 < out_rows;
+    if ((int)threadIdx.x < 2 * KT) {
+        const int r = threadIdx.x / KT, z = threadIdx.x % KT;
+        if (r == 0 || two) {
+            s_w[r][z] = __ldg(wts + (size_t)(y0 + r) * KT + z);
+            s_i[r][z] = __ldg(idx + (size_t)(y0 + r) * KT + z);
+        }
+    }
+    __syncthreads();
+    const uint32_t xv = blockIdx.x * 256 + threadIdx.x;
+    if (xv >= row_vecs) return;
+    const size_t row_bytes = (size_t)row_vecs * 8;
+    // shared path: both rows' taps are consecutive source rows and the second row's start `delta` rows after the first's
+    const int base = s_i[0][0];
+    int delta = two ? s_i[1][0] - base : -1;
+    bool shared = two && delta >= 0 && delta <= KT;
+#pragma unroll
+    for (int z = 1; z < KT; z++) shared = shared && s_i[0][z] == base + z && (!two || s_i[1][z] == s_i[1][0] + z);
+
+    double accA[8], accB[8];
+    if (shared) {
+        const int U = KT + delta;  // distinct source rows of the pair
+#pragma unroll
+        for (int u0 = 0; u0 < 2 * KT; u0 += 4) {
+            if (u0 >= U) break;
+            uint2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (u0 + q < U) v[q] = __ldg(reinterpret_cast<const uint2 *>(src.row_plain(base + u0 + q, row_bytes)) + xv);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int u = u0 + q;
+                if (u >= U) break;
+                double d[8];
+                {
+                    double t[4];
+                    word_to_double4<CONV>(v[q].x, t);
+                    d[0] = t[0], d[1] = t[1], d[2] = t[2], d[3] = t[3];
+                    word_to_double4<CONV>(v[q].y, t);
+                    d[4] = t[0], d[5] = t[1], d[6] = t[2], d[7] = t[3];
+                }
+                if (u < KT) {  // tap u of the first row (tap order = source-row order, ref:826-830)
+                    const double wa = s_w[0][u];
+#pragma unroll
+                    for (int b = 0; b < 8; b++) accA[b] = u ? dadd(accA[b], dmul(d[b], wa)) : dmul(d[b], wa);
+                }
+                if (u >= delta) {  // tap u - delta of the second row
+                    const double wb = s_w[1][u - delta];
+#pragma unroll
+                    for (int b = 0; b < 8; b++) accB[b] = (u > delta) ? dadd(accB[b], dmul(d[b], wb)) : dmul(d[b], wb);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (r == 1 && !two) break;
+            double(&acc)[8] = r ? accB : accA;
+#pragma unroll
+            for (int z0 = 0; z0 < KT; z0 += 4) {
+                uint2 v[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (z0 + q < KT) v[q] = __ldg(reinterpret_cast<const uint2 *>(src.row_plain(s_i[r][z0 + q], row_bytes)) + xv);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int z = z0 + q;
+                    if (z >= KT) break;
+                    const double wz = s_w[r][z];
+                    double t[4];
+                    word_to_double4<CONV>(v[q].x, t);
+#pragma unroll
+                    for (int b = 0; b < 4; b++) acc[b] = z ? dadd(acc[b], dmul(t[b], wz)) : dmul(t[b], wz);
+                    word_to_double4<CONV>(v[q].y, t);
+#pragma unroll
+                    for (int b = 0; b < 4; b++) acc[4 + b] = z ? dadd(acc[4 + b], dmul(t[b], wz)) : dmul(t[b], wz);
+                }
+            }
+        }
+    }
+    uint2 o;
+    o.x = quantise_pack4(accA[0], accA[1], accA[2], accA[3]);
+    o.y = quantise_pack4(accA[4], accA[5], accA[6], accA[7]);
+    reinterpret_cast<uint2 *>(dst + (size_t)y0 * row_bytes)[xv] = o;
+    if (two) {
+        o.x = quantise_pack4(accB[0], accB[1], accB[2], accB[3]);
+        o.y = quantise_pack4(accB[4], accB[5], accB[6], accB[7]);
+        reinterpret_cast<uint2 *>(dst + (size_t)(y0 + 1) * row_bytes)[xv] = o;
+    }
+}
+
+template <int KT>
+static void launch_rows8x2(const RowSource &src, uint8_t *dst, uint32_t row_bytes, int rows, const double *w0, const int *i0,
+                           cudaStream_t s)
+{
+    const uint32_t vecs = row_bytes / 8;
+    for (int y0 = 0; y0 < rows; y0 += 2 * 65535) {
+        const int n = min(2 * 65535, rows - y0);
+        dim3 grid((vecs + 255) / 256, (n + 1) / 2);
+        launch(imresize_rows8x2_kernel<3, KT>, grid, dim3(256), 0, s, src, dst + (size_t)y0 * row_bytes, vecs, n, w0 + (size_t)y0 * KT,
+               i0 + (size_t)y0 * KT);
+    }
+}
+
 // (A pipelined variant -- a CTA owning 8 consecutive output rows, tables staged once, the next group of four source
 // vectors in flight in a second register buffer while the current one is multiplied -- measured SLOWER than the
 // one-row-per-CTA kernel above: 67.6 vs 73.1 Gpix/s at x1.5 and 135 vs 178 at x0.5, profiles/r1_sweep_fp64.txt.
@@ -379,14 +499,20 @@ __global__ void __launch_bounds__(128) imresize_colsK_kernel(const uint8_t *__re
             o[1] = (uint8_t)quantise_fast(s1);
             o[2] = (uint8_t)quantise_fast(s2);
         };
-        uint32_t qa[NS + 1], qb[NS + 1];
+        // three register sets rotate: the words of rows y + 1 and y + 2 are in flight while row y is evaluated (with two
+        // sets the kernel waited on memory: long-scoreboard stalls 5.1 per issue, profiles/r2_ncu_*.txt)
+        uint32_t qa[NS + 1], qb[NS + 1], qc[NS + 1];
         fetch(y0, qa);
-        for (uint32_t y = y0; y < y1; y += 2) {
-            fetch(y + 1, qb);
+        fetch(y0 + 1, qb);
+        for (uint32_t y = y0; y < y1; y += 3) {
+            fetch(y + 2, qc);
             eval(y, qa);
             if (y + 1 >= y1) break;
-            fetch(y + 2, qa);
+            fetch(y + 3, qa);
             eval(y + 1, qb);
+            if (y + 2 >= y1) break;
+            fetch(y + 4, qb);
+            eval(y + 2, qc);
         }
     } else {
         for (uint32_t y = y0; y < y1; y++) {
@@ -511,7 +637,17 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
         const bool halo_ok = (!band.top || aligned16(band.top)) && (!band.bottom || aligned16(band.bottom));
         uint32_t row_bytes = w * 3u;
         if (row_bytes % 16 == 0 && aligned16(src_ptr) && aligned16(dst) && halo_ok && taps <= ROWS16_MAXK && PPMX_VARIANT != 1) {
-            const bool narrow = (PPMX_VARIANT == 6);  // 8 bytes per thread
+            if (taps >= 4 && taps <= 8 && PPMX_VARIANT == 0) {  // two output rows per CTA share their source rows' conversions
+                switch (taps) {
+                case 4: launch_rows8x2<4>(src, dst, row_bytes, out_size, d_weights, d_indices, s); break;
+                case 5: launch_rows8x2<5>(src, dst, row_bytes, out_size, d_weights, d_indices, s); break;
+                case 6: launch_rows8x2<6>(src, dst, row_bytes, out_size, d_weights, d_indices, s); break;
+                case 7: launch_rows8x2<7>(src, dst, row_bytes, out_size, d_weights, d_indices, s); break;
+                default: launch_rows8x2<8>(src, dst, row_bytes, out_size, d_weights, d_indices, s); break;
+                }
+                return cudaGetLastError();
+            }
+            [[maybe_unused]] const bool narrow = (PPMX_VARIANT == 6);  // 8 bytes per thread
             const uint32_t vecs = narrow ? row_bytes / 8 : row_bytes / 16;
             dim3 grid((vecs + 255) / 256, 1);
             for (int y0 = 0; y0 < out_size; y0 += 65535) {
@@ -525,14 +661,14 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
                 else if (PPMX_VARIANT == 2) launch(imresize_rows16_kernel<1, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (PPMX_VARIANT == 3) launch(imresize_rows16_kernel<0, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (PPMX_VARIANT == 4) launch(imresize_rows16_kernel<2, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else
-#endif
-                if (taps == 4 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else if (taps == 4 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 5 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 5>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 6 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 6>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 7 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 7>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 8 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 8>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else launch(imresize_rows16_kernel<3, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else
+#endif
+                launch(imresize_rows16_kernel<3, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
             }
             return cudaGetLastError();
         }

@@ -290,16 +290,70 @@ __device__ __forceinline__ uint32_t strip_pack4(const ConvRound &rnd, int32_t a0
     return rnd.template pack4<MODE>(a0, a1, a2, a3);
 }
 
-template <int MODE, int RH, int PF, bool INNER, bool WIDE>
+// UA ("unaligned"): rows of any length at any alignment (a width that is no multiple of 16, odd pointers).  A row's
+// misalignment is the same for every thread of it, so a thread loads the aligned 16-byte vectors that cover its 24-byte
+// window and undoes the shift with a warp-uniform word offset and one funnel-shift amount; the one or two chunks whose
+// window crosses the row's end (and the first one) are read byte by byte with the mirror rule; the 16 result bytes of
+// the warp's 32 threads are one run of the destination row, laid down in warp-private shared memory and written as
+// aligned vectors (store_run) -- the padded copy the kernel used to need (two more passes over the raster) is gone.
+constexpr int C3_STAGE = 32 * 16 + 16;
+
+template <int MODE, int RH, int PF, bool INNER, bool WIDE, bool UA = false>
 __device__ __forceinline__ void conv3_strip_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, uint32_t cx,
-                                                 int ys, const Conv3Coef &cf, const ConvRound &rnd)
+                                                 int ys, const Conv3Coef &cf, const ConvRound &rnd, uint32_t row_bytes = 0,
+                                                 uint8_t *stage = nullptr, uint32_t cx0 = 0)
 {
-    const size_t pitch = (size_t)nchunks * 16;
+    const size_t pitch = UA ? (size_t)row_bytes : (size_t)nchunks * 16;
     const bool left = cx == 0, right = cx == nchunks - 1;
     const int gy0 = rs.y0 + ys;
     const uint8_t *src = rs.own + (size_t)cx * 16 + (size_t)(INNER ? ys - 1 : 0) * pitch;
+    // UA: the window [16 cx - 4, 16 cx + 20) of the first chunk starts before the row, that of the last ones ends beyond it
+    const bool slow = UA && (cx == 0 || 16u * cx + 20u > row_bytes);
     auto load_row = [&](int i, uint32_t(&r)[6]) {  // row i counted from the strip's first source row (gy0 - 1)
         const uint8_t *p = INNER ? src + (size_t)i * pitch : rs.row(gy0 - 1 + i, pitch) + (size_t)cx * 16;
+        if (UA) {
+            if (slow) {
+                const uint8_t *rowp = p - (size_t)cx * 16;
+#pragma unroll
+                for (int k = 0; k < 6; k++) r[k] = 0;
+#pragma unroll
+                for (int j = 0; j < 24; j++) {
+                    int col = (int)(16u * cx) - 4 + j;
+                    if (col < 0) col += 3;                         // pixel -1 mirrors to pixel 0
+                    else if (col >= (int)row_bytes) col -= 3;      // pixel W to pixel W - 1
+                    if (col < 0) col = 0;                          // (column -4: not used by any tap)
+                    if (col >= (int)row_bytes) col = (int)row_bytes - 1;  // (bytes of this chunk beyond the row: never stored)
+                    r[j >> 2] |= (uint32_t)rowp[col] << (8 * (j & 3));
+                }
+                return;
+            }
+            const uintptr_t a = reinterpret_cast<uintptr_t>(p) - 4u;
+            const uint32_t o = (uint32_t)(a & 15u), sh = (o & 3u) * 8u;
+            const uint4 *vp = reinterpret_cast<const uint4 *>(a - o);
+            const uint4 v0 = __ldg(vp), v1 = __ldg(vp + 1);
+            uint4 v2 = make_uint4(0u, 0u, 0u, 0u);
+            if (o > 8u) v2 = __ldg(vp + 2);  // 24 bytes from offset o end in the third vector
+            const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+            switch (o >> 2) {  // warp-uniform
+            case 0:
+#pragma unroll
+                for (int k = 0; k < 6; k++) r[k] = __funnelshift_r(W[k], W[k + 1], sh);
+                break;
+            case 1:
+#pragma unroll
+                for (int k = 0; k < 6; k++) r[k] = __funnelshift_r(W[k + 1], W[k + 2], sh);
+                break;
+            case 2:
+#pragma unroll
+                for (int k = 0; k < 6; k++) r[k] = __funnelshift_r(W[k + 2], W[k + 3], sh);
+                break;
+            default:
+#pragma unroll
+                for (int k = 0; k < 6; k++) r[k] = __funnelshift_r(W[k + 3], W[k + 4], sh);
+                break;
+            }
+            return;
+        }
         const uint4 m = __ldg(reinterpret_cast<const uint4 *>(p));
         r[1] = m.x, r[2] = m.y, r[3] = m.z, r[4] = m.w;
         // columns -3..-1 / 16..18; at the raster's edge pixel -1 mirrors to pixel 0 and pixel W to W-1
@@ -369,9 +423,22 @@ __device__ __forceinline__ void conv3_strip_body(const RowSource &rs, uint8_t *_
                 oa[b] = strip_pack4<MODE>(rnd, accA[0], accA[1], accA[2], accA[3]);
                 ob[b] = strip_pack4<MODE>(rnd, accB[0], accB[1], accB[2], accB[3]);
             }
-            *reinterpret_cast<uint4 *>(out) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
-            if (INNER || ys + 2 * g + 1 < rs.h) *reinterpret_cast<uint4 *>(out + pitch) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
-            out += 2 * pitch;
+            if (UA) {
+                // the warp's 32 x 16 result bytes = one run of the destination row, for each of the two rows
+                const uint32_t lane = threadIdx.x & 31u, run = min(512u, row_bytes - 16u * cx0);
+                const bool second = INNER || ys + 2 * g + 1 < rs.h;
+                reinterpret_cast<uint4 *>(stage)[lane] = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+                reinterpret_cast<uint4 *>(stage + C3_STAGE)[lane] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+                __syncwarp();
+                uint8_t *o0 = dst + (size_t)(ys + 2 * g) * pitch + (size_t)cx0 * 16;
+                store_run(o0, stage, 0, run, lane);
+                if (second) store_run(o0 + pitch, stage + C3_STAGE, 0, run, lane);
+                __syncwarp();
+            } else {
+                *reinterpret_cast<uint4 *>(out) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+                if (INNER || ys + 2 * g + 1 < rs.h) *reinterpret_cast<uint4 *>(out + pitch) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+                out += 2 * pitch;
+            }
         }
     }
 }
@@ -390,8 +457,23 @@ __global__ void __launch_bounds__(BLOCK) conv3_strip_kernel(RowSource rs, uint8_
     else conv3_strip_body<MODE, RH, PF, false, WIDE>(rs, dst, nchunks, cx, ys, cf, rnd);
 }
 
+// any width, any alignment: 4 rows per strip, one warp = 32 chunks of a row (lanes beyond the row's last chunk idle along)
+template <int MODE, bool WIDE>
+__global__ void __launch_bounds__(128) conv3_strip_ua_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks,
+                                                             uint32_t row_bytes, const Conv3Coef cf, const ConvRound rnd)
+{
+    pdl_trigger();
+    __shared__ __align__(16) uint8_t stage_all[4][2 * C3_STAGE];
+    const uint32_t warp = threadIdx.x >> 5, cx0 = blockIdx.x * 128u + warp * 32u;
+    if (cx0 >= nchunks) return;  // (a whole warp)
+    const uint32_t cx = min(blockIdx.x * 128u + threadIdx.x, nchunks - 1u);
+    const int ys = blockIdx.y * 4;
+    if (ys >= 1 && ys + 4 + 1 <= rs.h) conv3_strip_body<MODE, 4, 2, true, WIDE, true>(rs, dst, nchunks, cx, ys, cf, rnd, row_bytes, stage_all[warp], cx0);
+    else conv3_strip_body<MODE, 4, 2, false, WIDE, true>(rs, dst, nchunks, cx, ys, cf, rnd, row_bytes, stage_all[warp], cx0);
+}
+
 static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef,
-                               ConvRound rnd, int32_t div, int32_t bias, cudaStream_t s)
+                               ConvRound rnd, int32_t div, int32_t bias, cudaStream_t s, bool unaligned = false)
 {
     const int32_t *c = coef;
     // (pre-scaling the coefficients of a normalised non-negative filter so that the quotient is byte 1 of the sum
@@ -416,6 +498,21 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
         cf.b[dx] = lo[0] << 8 | lo[1] << 16 | lo[2] << 24;
         cf.ah[dx] = hi[0] | hi[1] << 8 | hi[2] << 16;
         cf.bh[dx] = hi[0] << 8 | hi[1] << 16 | hi[2] << 24;
+    }
+    if (unaligned) {
+        const uint32_t row_bytes = w * 3u, nch = (row_bytes + 15u) / 16u;
+        dim3 grid((nch + 127) / 128, (h + 3) / 4);
+        if (grid.y > 65535u) return cudaErrorInvalidValue;
+#define PPMX_CONV3_UA(MODE)                                                                                             \
+    do {                                                                                                                \
+        if (wide) launch(conv3_strip_ua_kernel<MODE, true>, grid, dim3(128), 0, s, rs, dst, nch, row_bytes, cf, rnd);   \
+        else launch(conv3_strip_ua_kernel<MODE, false>, grid, dim3(128), 0, s, rs, dst, nch, row_bytes, cf, rnd);       \
+    } while (0)
+        if (mode == 0) PPMX_CONV3_UA(0);
+        else if (mode == 1) PPMX_CONV3_UA(1);
+        else PPMX_CONV3_UA(2);
+#undef PPMX_CONV3_UA
+        return PPMX_LAUNCHED();
     }
     const uint32_t nchunks = w * 3 / 16;
 #define PPMX_CONV3_LAUNCH(MODE, RH, PF, BLOCK)                                                                   \
@@ -996,6 +1093,12 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         if (k == 3) return conv_fast<3>(rs, dst, w, h, coef, rnd, s);
         if (k == 5) return conv_fast<5>(rs, dst, w, h, coef, rnd, s);
         return conv_fast<7>(rs, dst, w, h, coef, rnd, s);
+    }
+    if (k == 3 && rnd_ok && !fast_layout && w >= 16 && (size_t)w * h >= 4096 && PPMX_VARIANT == 0) {
+        // 3x3 at any width / alignment (whole rasters and row bands alike): the strip kernel's unaligned form
+        bool ok16 = true;
+        for (int i = 0; i < 9; i++) ok16 = ok16 && coef[i] >= -16320 && coef[i] <= 16320;
+        if (ok16) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s, true);
     }
     // a whole raster that only lacks the layout for the vector kernels goes through a padded copy (variant 1 = never)
     const bool layout_only = ((w % 16u) != 0 || !aligned16(src) || !aligned16(dst)) && !band.full_h && PPMX_VARIANT != 1 &&

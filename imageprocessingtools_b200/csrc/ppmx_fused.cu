@@ -334,24 +334,6 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
 //          (up to 15 bytes at either end of the run byte by byte) -- rows of any pitch and alignment on both sides.
 constexpr int RS_STAGE = 48 + 32 * 48 + 16;  // 16 pixels of front pad (a ragged mirrored group starts inside it) + the run + slack
 
-// `nbytes` bytes from shared memory (4-byte aligned `srow`, run at byte `soff`) to any global address, by one warp
-__device__ __forceinline__ void store_run(uint8_t *g, const uint8_t *srow, uint32_t soff, uint32_t nbytes, uint32_t lane)
-{
-    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
-    const uint32_t hb = min(nbytes, (16u - a) & 15u), nv = (nbytes - hb) >> 4, tb = nbytes - hb - 16u * nv;
-    for (uint32_t k = lane; k < nv; k += 32u) {
-        const uint32_t q = soff + hb + 16u * k, sh = 8u * (q & 3u);
-        const uint32_t *sw = reinterpret_cast<const uint32_t *>(srow) + (q >> 2);
-        const uint32_t w0 = sw[0], w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sh ? sw[4] : 0u;
-        reinterpret_cast<uint4 *>(g + hb)[k] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
-                                                         __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-    }
-    if (lane < hb + tb) {
-        const uint32_t pos = lane < hb ? lane : nbytes - tb + (lane - hb);
-        g[pos] = srow[soff + pos];
-    }
-}
-
 template <int POINT, bool REV_X>
 __global__ void __launch_bounds__(128) rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t w, uint32_t h,
                                                    uint32_t in_pitch, uint32_t out_pitch, const uint8_t *src_end, const GeomOp go)
