@@ -358,6 +358,8 @@ __global__ void __launch_bounds__(256) imresize_rows8x2_kernel(const RowSource s
     for (int z = 1; z < KT; z++) shared = shared && s_i[0][z] == base + z && (!two || s_i[1][z] == s_i[1][0] + z);
 
     double accA[8], accB[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) accB[b] = 0.0;  // (x + 0.0 == x up to the sign of a zero, which the rounding never sees)
     if (shared) {
         const int U = KT + delta;  // distinct source rows of the pair
 #pragma unroll
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(256) imresize_rows8x2_kernel(const RowSource s
                 if (u >= delta) {  // tap u - delta of the second row
                     const double wb = s_w[1][u - delta];
 #pragma unroll
-                    for (int b = 0; b < 8; b++) accB[b] = (u > delta) ? dadd(accB[b], dmul(d[b], wb)) : dmul(d[b], wb);
+                    for (int b = 0; b < 8; b++) accB[b] = dadd(accB[b], dmul(d[b], wb));
                 }
             }
         }

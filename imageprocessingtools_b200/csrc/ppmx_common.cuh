@@ -183,18 +183,30 @@ struct RowSource {
     }
 };
 
-// `nbytes` bytes from shared memory (4-byte aligned `srow`, run at byte `soff`) to any global address, by one warp
+// 16 bytes from shared memory at any byte offset `q` of a 16-byte aligned row: two aligned 16-byte reads (consecutive lanes
+// read consecutive vectors: no bank conflicts) and a funnel shift; q % 16 is the same for every lane of a run, so the
+// word offset is a warp-uniform choice
+__device__ __forceinline__ uint4 smem_vec_at(const uint8_t *srow, uint32_t q)
+{
+    const uint4 *v = reinterpret_cast<const uint4 *>(srow + (q & ~15u));
+    const uint4 a = v[0], b = (q & 15u) ? v[1] : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t W[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}, sh = 8u * (q & 3u);
+    switch ((q >> 2) & 3u) {
+    case 0: return make_uint4(__funnelshift_r(W[0], W[1], sh), __funnelshift_r(W[1], W[2], sh), __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh));
+    case 1: return make_uint4(__funnelshift_r(W[1], W[2], sh), __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh));
+    case 2: return make_uint4(__funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh), __funnelshift_r(W[5], W[6], sh));
+    default: return make_uint4(__funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh), __funnelshift_r(W[5], W[6], sh), __funnelshift_r(W[6], W[7], sh));
+    }
+}
+
+// `nbytes` bytes from shared memory (16-byte aligned `srow` with 16 bytes of slack behind the run, run at byte `soff`) to
+// any global address, by one warp: everything between the first and last 16-byte boundary of the destination as aligned
+// vectors, the up to 15 bytes at either end one by one
 __device__ __forceinline__ void store_run(uint8_t *g, const uint8_t *srow, uint32_t soff, uint32_t nbytes, uint32_t lane)
 {
     const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
     const uint32_t hb = min(nbytes, (16u - a) & 15u), nv = (nbytes - hb) >> 4, tb = nbytes - hb - 16u * nv;
-    for (uint32_t k = lane; k < nv; k += 32u) {
-        const uint32_t q = soff + hb + 16u * k, sh = 8u * (q & 3u);
-        const uint32_t *sw = reinterpret_cast<const uint32_t *>(srow) + (q >> 2);
-        const uint32_t w0 = sw[0], w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sh ? sw[4] : 0u;
-        reinterpret_cast<uint4 *>(g + hb)[k] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
-                                                         __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-    }
+    for (uint32_t k = lane; k < nv; k += 32u) reinterpret_cast<uint4 *>(g + hb)[k] = smem_vec_at(srow, soff + hb + 16u * k);
     if (lane < hb + tb) {
         const uint32_t pos = lane < hb ? lane : nbytes - tb + (lane - hb);
         g[pos] = srow[soff + pos];

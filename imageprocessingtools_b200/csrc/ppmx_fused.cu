@@ -48,13 +48,7 @@ __device__ __forceinline__ void store_piece(uint8_t *g, const uint8_t *srow, uin
     }
     const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
     const uint32_t hb = min(nbytes, (16u - a) & 15u), nv = (nbytes - hb) >> 4, tb = nbytes - hb - 16u * nv;
-    if (hl < nv) {
-        const uint32_t q = soff + hb + 16u * hl, sh = 8u * (q & 3u);
-        const uint32_t *sw = reinterpret_cast<const uint32_t *>(srow) + (q >> 2);
-        const uint32_t w0 = sw[0], w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sh ? sw[4] : 0u;
-        reinterpret_cast<uint4 *>(g + hb)[hl] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
-                                                          __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-    }
+    if (hl < nv) reinterpret_cast<uint4 *>(g + hb)[hl] = smem_vec_at(srow, soff + hb + 16u * hl);
     for (uint32_t b = hl; b < hb + tb; b += 16u) {
         const uint32_t pos = b < hb ? b : nbytes - tb + (b - hb);
         g[pos] = srow[soff + pos];
@@ -70,7 +64,7 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
     pdl_trigger();
     constexpr int OP = GeomOut<POINT>::pitch;
     __shared__ __align__(128) uint8_t tin[64 * GI_PITCH + 16];  // (+16: the funnel shift's second word of the last pixel)
-    __shared__ __align__(128) uint8_t tout[64 * OP];
+    __shared__ __align__(128) uint8_t tout[64 * OP + 16];  // (+16: store_piece reads whole vectors)
     __shared__ __align__(8) uint64_t bar;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tx0 = blockIdx.x * 64u, ty0 = blockIdx.y * 64u;
