@@ -639,7 +639,10 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
         const bool halo_ok = (!band.top || aligned16(band.top)) && (!band.bottom || aligned16(band.bottom));
         uint32_t row_bytes = w * 3u;
         if (row_bytes % 16 == 0 && aligned16(src_ptr) && aligned16(dst) && halo_ok && taps <= ROWS16_MAXK && PPMX_VARIANT != 1) {
-            if (taps >= 4 && taps <= 8 && PPMX_VARIANT == 0) {  // two output rows per CTA share their source rows' conversions
+#ifdef PPMX_TUNING
+            // two output rows per CTA sharing their source rows' conversions: measured 15 % SLOWER than one row per CTA
+            // (x1.5: 67.3 vs 79.0 Gpix/s over both passes, profiles/r2_sweep_fp64.txt) -- kept for the record only
+            if (taps >= 4 && taps <= 8 && PPMX_VARIANT == 9) {
                 switch (taps) {
                 case 4: launch_rows8x2<4>(src, dst, row_bytes, out_size, d_weights, d_indices, s); break;
                 case 5: launch_rows8x2<5>(src, dst, row_bytes, out_size, d_weights, d_indices, s); break;
@@ -649,6 +652,7 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
                 }
                 return cudaGetLastError();
             }
+#endif
             [[maybe_unused]] const bool narrow = (PPMX_VARIANT == 6);  // 8 bytes per thread
             const uint32_t vecs = narrow ? row_bytes / 8 : row_bytes / 16;
             dim3 grid((vecs + 255) / 256, 1);
@@ -663,14 +667,14 @@ cudaError_t imresize(const uint8_t *src_ptr, uint8_t *dst, uint32_t w, uint32_t 
                 else if (PPMX_VARIANT == 2) launch(imresize_rows16_kernel<1, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (PPMX_VARIANT == 3) launch(imresize_rows16_kernel<0, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (PPMX_VARIANT == 4) launch(imresize_rows16_kernel<2, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else if (taps == 4 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else
+#endif
+                if (taps == 4 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 5 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 5>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 6 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 6>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 7 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 7>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
                 else if (taps == 8 && PPMX_VARIANT != 5) launch(imresize_rows16_kernel<3, 4, 8>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
-                else
-#endif
-                launch(imresize_rows16_kernel<3, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
+                else launch(imresize_rows16_kernel<3, 4>, grid, dim3(256), 0, s, src, d0, vecs, taps, w0, i0);
             }
             return cudaGetLastError();
         }
