@@ -183,6 +183,24 @@ struct RowSource {
     }
 };
 
+// NOUT words starting `byte_off` (0..15) bytes into the words W[0 .. NOUT + 4]: the word part of the offset is applied as
+// two conditional moves per word (by 2 words, then by 1 -- the predicate is the same for the whole warp), the byte part
+// as one funnel shift.  (A switch over the four word offsets is compiled to all four cases plus selects: twice the work.)
+template <int NIN, int NOUT>
+__device__ __forceinline__ void shift_words(const uint32_t (&W)[NIN], uint32_t byte_off, uint32_t (&out)[NOUT])
+{
+    static_assert(NIN >= NOUT + 4, "shift_words needs four spare words");
+    const bool by2 = (byte_off & 8u) != 0, by1 = (byte_off & 4u) != 0;
+    const uint32_t sh = 8u * (byte_off & 3u);
+    uint32_t X[NOUT + 2], Y[NOUT + 1];
+#pragma unroll
+    for (int j = 0; j < NOUT + 2; j++) X[j] = by2 ? W[j + 2] : W[j];
+#pragma unroll
+    for (int j = 0; j < NOUT + 1; j++) Y[j] = by1 ? X[j + 1] : X[j];
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) out[k] = __funnelshift_r(Y[k], Y[k + 1], sh);
+}
+
 // 16 bytes from shared memory at any byte offset `q` of a 16-byte aligned row: two aligned 16-byte reads (consecutive lanes
 // read consecutive vectors: no bank conflicts) and a funnel shift; q % 16 is the same for every lane of a run, so the
 // word offset is a warp-uniform choice
@@ -190,13 +208,10 @@ __device__ __forceinline__ uint4 smem_vec_at(const uint8_t *srow, uint32_t q)
 {
     const uint4 *v = reinterpret_cast<const uint4 *>(srow + (q & ~15u));
     const uint4 a = v[0], b = (q & 15u) ? v[1] : make_uint4(0u, 0u, 0u, 0u);
-    const uint32_t W[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}, sh = 8u * (q & 3u);
-    switch ((q >> 2) & 3u) {
-    case 0: return make_uint4(__funnelshift_r(W[0], W[1], sh), __funnelshift_r(W[1], W[2], sh), __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh));
-    case 1: return make_uint4(__funnelshift_r(W[1], W[2], sh), __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh));
-    case 2: return make_uint4(__funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh), __funnelshift_r(W[5], W[6], sh));
-    default: return make_uint4(__funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh), __funnelshift_r(W[5], W[6], sh), __funnelshift_r(W[6], W[7], sh));
-    }
+    const uint32_t W[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+    shift_words<8, 4>(W, q & 15u, o);
+    return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // `nbytes` bytes from shared memory (16-byte aligned `srow` with 16 bytes of slack behind the run, run at byte `soff`) to

@@ -328,30 +328,13 @@ __device__ __forceinline__ void conv3_strip_body(const RowSource &rs, uint8_t *_
                 return;
             }
             const uintptr_t a = reinterpret_cast<uintptr_t>(p) - 4u;
-            const uint32_t o = (uint32_t)(a & 15u), sh = (o & 3u) * 8u;
+            const uint32_t o = (uint32_t)(a & 15u);
             const uint4 *vp = reinterpret_cast<const uint4 *>(a - o);
             const uint4 v0 = __ldg(vp), v1 = __ldg(vp + 1);
             uint4 v2 = make_uint4(0u, 0u, 0u, 0u);
             if (o > 8u) v2 = __ldg(vp + 2);  // 24 bytes from offset o end in the third vector
             const uint32_t W[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-            switch (o >> 2) {  // warp-uniform
-            case 0:
-#pragma unroll
-                for (int k = 0; k < 6; k++) r[k] = __funnelshift_r(W[k], W[k + 1], sh);
-                break;
-            case 1:
-#pragma unroll
-                for (int k = 0; k < 6; k++) r[k] = __funnelshift_r(W[k + 1], W[k + 2], sh);
-                break;
-            case 2:
-#pragma unroll
-                for (int k = 0; k < 6; k++) r[k] = __funnelshift_r(W[k + 2], W[k + 3], sh);
-                break;
-            default:
-#pragma unroll
-                for (int k = 0; k < 6; k++) r[k] = __funnelshift_r(W[k + 3], W[k + 4], sh);
-                break;
-            }
+            shift_words<12, 6>(W, o, r);  // (o is the same for every thread of the row)
             return;
         }
         const uint4 m = __ldg(reinterpret_cast<const uint4 *>(p));

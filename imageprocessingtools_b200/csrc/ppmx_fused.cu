@@ -306,12 +306,16 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
         }
     } else {
         const uint32_t hl = lane & 15u, hr = lane >> 4;  // half a warp per output row
+        // the rows of one half warp are two apart: one 64-bit address, stepped by a constant
+        const uint32_t crow0 = warp * 16u + hr;
+        const uint32_t yfirst = go.rev_y ? out_h - 1u - (row0 + crow0) : row0 + crow0;
+        uint8_t *g = dst + (size_t)yfirst * out_pitch + goff;
+        const ptrdiff_t gstep = go.rev_y ? -2 * (ptrdiff_t)out_pitch : 2 * (ptrdiff_t)out_pitch;
+        const uint8_t *srow = tout + crow0 * OP;
 #pragma unroll 2
-        for (uint32_t i = 0; i < 8u; i++) {
-            const uint32_t crow = warp * 16u + 2u * i + hr;
-            if (crow >= nrows_out) continue;
-            const uint32_t y = go.rev_y ? out_h - 1u - (row0 + crow) : row0 + crow;
-            store_piece<STORE>(dst + (size_t)y * out_pitch + goff, tout + crow * OP, soff, pbytes, hl);
+        for (uint32_t i = 0; i < 8u; i++, g += gstep, srow += 2 * OP) {
+            if (crow0 + 2u * i >= nrows_out) break;
+            store_piece<STORE>(g, srow, soff, pbytes, hl);
         }
     }
 }
@@ -355,30 +359,10 @@ __global__ void __launch_bounds__(128) rows_kernel(const uint8_t *__restrict__ s
             if (live && reinterpret_cast<const uint8_t *>(vp + k) < src_end && (k < 3 || m)) v = __ldg(vp + k);
             W[4 * k] = v.x, W[4 * k + 1] = v.y, W[4 * k + 2] = v.z, W[4 * k + 3] = v.w;
         }
-        W[16] = 0u;
+        W[16] = 0u;  // (shift_words wants four spare words behind the twelve it returns: 12 + 3 + 1 <= 17)
     }
     uint32_t in[12];  // 16 pixels, packed
-    {
-        const uint32_t sh = (m & 3u) * 8u;
-        switch (m >> 2) {  // warp-uniform: every group of a row is misaligned alike
-        case 0:
-#pragma unroll
-            for (int i = 0; i < 12; i++) in[i] = __funnelshift_r(W[i], W[i + 1], sh);
-            break;
-        case 1:
-#pragma unroll
-            for (int i = 0; i < 12; i++) in[i] = __funnelshift_r(W[i + 1], W[i + 2], sh);
-            break;
-        case 2:
-#pragma unroll
-            for (int i = 0; i < 12; i++) in[i] = __funnelshift_r(W[i + 2], W[i + 3], sh);
-            break;
-        default:
-#pragma unroll
-            for (int i = 0; i < 12; i++) in[i] = __funnelshift_r(W[i + 3], W[i + 4], sh);
-            break;
-        }
-    }
+    shift_words<17, 12>(W, m, in);  // (m is the same for every group of the row)
 
     // ---- where this warp's run lies in the destination row -----------------------------------------------------------
     // pixels [16 g0, min(w, 16 g0 + 512)) of the source row; mirrored, the run starts at pixel max(0, w - 16 g0 - 512)
