@@ -204,7 +204,12 @@ int ppmx_gpu_sync(ppmx_gpu_ctx *ctx);
  * cudaStream_t passed as void* (NULL = default stream); d_hist is 256 x u64 on the device,
  * accumulated into (HIST ops only).  d_top / d_bottom: optional device pointers (possibly
  * PEER memory of a neighbouring GPU) to the halo rows above / below a row band; see
- * ppmx_band below.  Nothing is allocated, copied or synchronised. */
+ * ppmx_band below.  Nothing is allocated, copied or synchronised.
+ * Memory contract: rasters whose rows are not 16-byte aligned are read as whole aligned 16-byte vectors (and flips of
+ * such rasters as aligned 4-byte words), so up to 15 bytes before the first and after the last byte of a raster -- never
+ * beyond the 16-byte granule that holds them -- may be READ (nothing outside a raster is ever written).  Memory from
+ * cudaMalloc / a torch allocator (256-/512-byte granules) always satisfies this; a raster carved out of a larger buffer
+ * must not start or end inside the last 16 bytes of a mapping.  Halo rows are never read beyond `halo` rows. */
 typedef struct ppmx_band {
     uint32_t full_h;   /* height of the whole raster this band belongs to (0 = not a band)  */
     uint32_t y0;       /* first row of the band in the whole raster                          */

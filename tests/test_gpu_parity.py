@@ -758,6 +758,39 @@ def test_multi_device_context_row_bands(orc):
         g.close()
 
 
+def test_full_size_16384_square(gpu, orc):
+    """BASELINE config 4 at its full size, one GPU: 16384 x 16384 (805 MB) gray against the oracle, mono / flips
+    through size-independent properties, and the 3x3 convolution as "8 bands == whole raster" plus oracle slices at
+    the raster's top, middle and bottom."""
+    import imageprocessingtools_b200.ppmx as pp
+    w = h = 16384
+    img = pp.synth_lcg(w, h, 0xC0FFEE ^ 4)
+    g = gpu.gray(img)
+    assert np.array_equal(g, orc.gray(img))
+    bits = gpu.mono_bits(img).reshape(h, w // 8)
+    assert np.array_equal(bits[4096:4100], orc.pack_pbm(orc.mono(img[4096:4100])).reshape(4, w // 8))   # row phase 4096 % 4 == 0
+    assert np.array_equal(bits[-4:], orc.pack_pbm(orc.mono(img[-4:])).reshape(4, w // 8))
+    fv = gpu.flip(img, 1)
+    assert np.array_equal(fv, img[::-1])
+    del fv
+    r180 = gpu.rotate(img, 180)
+    assert np.array_equal(r180[:64], img[::-1, ::-1][:64]) and np.array_equal(r180[-64:], img[::-1, ::-1][-64:])
+    assert int(r180.astype(np.uint8).sum(dtype=np.uint64)) == int(img.sum(dtype=np.uint64))
+    del r180, g, bits
+    coef, div, bias = KERNELS["blur3"]
+    op = gpu.conv_op(coef, div, bias)
+    whole = gpu.conv(img, coef, div, bias)
+    out = np.zeros(w * h * 3, np.uint8)
+    for b in range(8):
+        gpu.apply_band(img, [op], b, 8, out)
+    assert np.array_equal(out.reshape(h, w, 3), whole)
+    del out
+    assert np.array_equal(whole[:40], orc.conv(img[:41], coef, div, bias)[:40])                   # mirror border at the top
+    assert np.array_equal(whole[8000:8040], orc.conv(img[7999:8041], coef, div, bias)[1:-1])      # across a band cut (8192 is one)
+    assert np.array_equal(whole[8180:8200], orc.conv(img[8179:8201], coef, div, bias)[1:-1])
+    assert np.array_equal(whole[-40:], orc.conv(img[-41:], coef, div, bias)[1:])                  # mirror border at the bottom
+
+
 def test_full_size_bands_16384(gpu, orc):
     """BASELINE config 4 size: a 16384-wide raster; N bands == whole raster for the convolutions (property), gray /
     mono / flips of a 16384 x 2048 slice against the oracle directly."""
