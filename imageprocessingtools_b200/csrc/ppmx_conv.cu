@@ -37,6 +37,8 @@ struct ConvRound {
     template <int MODE>
     __device__ __forceinline__ uint32_t pack4(int32_t a0, int32_t a1, int32_t a2, int32_t a3) const
     {
+        if (MODE == 3)  // coefficients pre-scaled by 256 / div, start 128: the quotient IS byte 1 of the sum (it can not leave 0..255)
+            return __byte_perm(__byte_perm((uint32_t)a0, (uint32_t)a1, 0x0051), __byte_perm((uint32_t)a2, (uint32_t)a3, 0x0051), 0x5410);
         uint32_t hi, out;
         asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(quotient<MODE>(a3)), "r"(quotient<MODE>(a2)), "r"(0));
         asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(quotient<MODE>(a1)), "r"(quotient<MODE>(a0)), "r"(hi));
@@ -458,10 +460,29 @@ __global__ void __launch_bounds__(128) conv3_strip_ua_kernel(RowSource rs, uint8
 static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef,
                                ConvRound rnd, int32_t div, int32_t bias, cudaStream_t s, bool unaligned = false)
 {
+    // A normalised non-negative filter with a power-of-two divisor (the blur presets) can not leave 0..255, so its
+    // coefficients are pre-scaled by 256 / div and the quotient is byte 1 of the sum: three PRMT per four bytes instead
+    // of a shift each plus two saturating packs.  Over a short run at full clocks the kernel is HBM-bound either way
+    // (round 1 measured this form 2 % slower there); in a SUSTAINED run the 1 kW power cap holds the SMs at ~1.45-1.55
+    // GHz, the alu pipe (60 % busy at full clock) becomes co-critical and every instruction saved shows.
+    int32_t scaled_coef[9];
+    int mode = rnd.mode;
+    if (mode == 1 && bias == 0 && div >= 2 && div <= 256 && (256 % div) == 0 && PPMX_VARIANT != 8) {
+        const int32_t k256 = 256 / div;
+        int64_t sum = 0;
+        bool ok = true;
+        for (int i = 0; i < 9; i++) {
+            ok = ok && coef[i] >= 0 && (int64_t)coef[i] * k256 <= 127;
+            sum += coef[i];
+        }
+        if (ok && sum == div) {
+            for (int i = 0; i < 9; i++) scaled_coef[i] = coef[i] * k256;
+            coef = scaled_coef;
+            rnd.start = 128;  // one half, in units of 1/256
+            mode = 3;
+        }
+    }
     const int32_t *c = coef;
-    // (pre-scaling the coefficients of a normalised non-negative filter so that the quotient is byte 1 of the sum
-    // -- three PRMT per four bytes instead of shift + saturating pack -- measured 2 % SLOWER: 0.934 vs 0.953)
-    const int mode = rnd.mode;
     Conv3Coef cf;
     bool wide = false;
     for (int dx = 0; dx < 3; dx++) {
@@ -493,6 +514,7 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
     } while (0)
         if (mode == 0) PPMX_CONV3_UA(0);
         else if (mode == 1) PPMX_CONV3_UA(1);
+        else if (mode == 3) PPMX_CONV3_UA(3);
         else PPMX_CONV3_UA(2);
 #undef PPMX_CONV3_UA
         return PPMX_LAUNCHED();
@@ -508,6 +530,7 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
     do {                                                         \
         if (mode == 0) PPMX_CONV3_LAUNCH(0, RH, PF, BLOCK);      \
         else if (mode == 1) PPMX_CONV3_LAUNCH(1, RH, PF, BLOCK); \
+        else if (mode == 3) PPMX_CONV3_LAUNCH(3, RH, PF, BLOCK); \
         else PPMX_CONV3_LAUNCH(2, RH, PF, BLOCK);                \
     } while (0)
     // rows per strip / row pairs in flight / threads per CTA.  Measured on 8192x8192 (profiles/r1_sweep_conv3_strip.txt):

@@ -267,6 +267,9 @@ KERNELS["box11"] = (np.ones((11, 11), np.int64), 121, 0)
 KERNELS["box11_bias"] = (np.ones((11, 11), np.int64), 121, 3)                                          # constants overflow 32 bits: generic kernel
 KERNELS["box7_twos_bias"] = (2 * np.ones((7, 7), np.int64), 196, 64)                                  # box with a factor and a bias
 KERNELS["box7_sat"] = (np.ones((7, 7), np.int64), 40, 0)                                              # would pass 255: not the box kernel
+KERNELS["blur3_div256"] = (np.array([[16, 32, 16], [32, 64, 32], [16, 32, 16]]), 256, 0)   # normalised, power-of-two divisor:
+KERNELS["cross3_div4"] = (np.array([[0, 1, 0], [1, 0, 1], [0, 1, 0]]), 4, 0)                  #   the quotient is byte 1 of the scaled sum
+KERNELS["pair3_div2"] = (np.array([[0, 0, 0], [0, 1, 1], [0, 0, 0]]), 2, 0)                   # scaled coefficient 128 > 127: shift form
 KERNELS["big5"] = (np.array([[300, -200, 0, 5, 1]] * 5), 7, -3)  # coefficients beyond int8: generic kernel
 
 
