@@ -329,6 +329,48 @@ __global__ void __launch_bounds__(256) imresize_rows16_kernel(const RowSource sr
 // 55 % in the one-row kernel.  Each row's sum still runs over its own taps in tap order with separately rounded products
 // and sums (ref:826-830), so the bytes are the same.  Pairs whose taps are not consecutive rows (mirrored taps at the
 // raster's ends) and a last odd row take the one-row arithmetic inside the same kernel.
+// OWN: all K + DELTA rows lie in the band's own raster (always, unless a neighbour's halo rows are involved): plain
+// pointer steps instead of the band resolver
+template <int CONV, int KT, int DELTA, bool OWN>
+__device__ __forceinline__ void rows_pair(const RowSource &src, int base, size_t row_bytes, uint32_t xv, const double *wa,
+                                          const double *wb, double (&accA)[8], double (&accB)[8])
+{
+    constexpr int U = KT + DELTA;  // distinct source rows of the pair
+    const uint8_t *p0 = OWN ? src.own + (size_t)(base - src.y0) * row_bytes + (size_t)xv * 8 : nullptr;
+#pragma unroll
+    for (int u0 = 0; u0 < U; u0 += 4) {
+        uint2 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (u0 + q < U)
+                v[q] = OWN ? __ldg(reinterpret_cast<const uint2 *>(p0 + (size_t)(u0 + q) * row_bytes))
+                           : __ldg(reinterpret_cast<const uint2 *>(src.row_plain(base + u0 + q, row_bytes)) + xv);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int u = u0 + q;
+            if (u >= U) break;
+            double d[8];
+            {
+                double t[4];
+                word_to_double4<CONV>(v[q].x, t);
+                d[0] = t[0], d[1] = t[1], d[2] = t[2], d[3] = t[3];
+                word_to_double4<CONV>(v[q].y, t);
+                d[4] = t[0], d[5] = t[1], d[6] = t[2], d[7] = t[3];
+            }
+            if (u < KT) {  // tap u of the first row (tap order = source-row order, ref:826-830)
+                const double w = wa[u];
+#pragma unroll
+                for (int b = 0; b < 8; b++) accA[b] = u ? dadd(accA[b], dmul(d[b], w)) : dmul(d[b], w);
+            }
+            if (u >= DELTA) {  // tap u - DELTA of the second row
+                const double w = wb[u - DELTA];
+#pragma unroll
+                for (int b = 0; b < 8; b++) accB[b] = (u > DELTA) ? dadd(accB[b], dmul(d[b], w)) : dmul(d[b], w);
+            }
+        }
+    }
+}
+
 template <int CONV, int KT>
 __global__ void __launch_bounds__(256) imresize_rows8x2_kernel(const RowSource src, uint8_t *__restrict__ dst, uint32_t row_vecs,
                                                                int out_rows, const double *__restrict__ wts,
@@ -360,39 +402,20 @@ __global__ void __launch_bounds__(256) imresize_rows8x2_kernel(const RowSource s
     double accA[8], accB[8];
 #pragma unroll
     for (int b = 0; b < 8; b++) accB[b] = 0.0;  // (x + 0.0 == x up to the sign of a zero, which the rounding never sees)
-    if (shared) {
-        const int U = KT + delta;  // distinct source rows of the pair
-#pragma unroll
-        for (int u0 = 0; u0 < 2 * KT; u0 += 4) {
-            if (u0 >= U) break;
-            uint2 v[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (u0 + q < U) v[q] = __ldg(reinterpret_cast<const uint2 *>(src.row_plain(base + u0 + q, row_bytes)) + xv);
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int u = u0 + q;
-                if (u >= U) break;
-                double d[8];
-                {
-                    double t[4];
-                    word_to_double4<CONV>(v[q].x, t);
-                    d[0] = t[0], d[1] = t[1], d[2] = t[2], d[3] = t[3];
-                    word_to_double4<CONV>(v[q].y, t);
-                    d[4] = t[0], d[5] = t[1], d[6] = t[2], d[7] = t[3];
-                }
-                if (u < KT) {  // tap u of the first row (tap order = source-row order, ref:826-830)
-                    const double wa = s_w[0][u];
-#pragma unroll
-                    for (int b = 0; b < 8; b++) accA[b] = u ? dadd(accA[b], dmul(d[b], wa)) : dmul(d[b], wa);
-                }
-                if (u >= delta) {  // tap u - delta of the second row
-                    const double wb = s_w[1][u - delta];
-#pragma unroll
-                    for (int b = 0; b < 8; b++) accB[b] = dadd(accB[b], dmul(d[b], wb));
-                }
-            }
+    if (shared && delta <= 3) {
+        // the pair's K + delta source rows with delta a COMPILE-TIME constant per case: no branch inside, every load and
+        // conversion of the pair can be in flight together
+        const bool own = base >= src.y0 && base + KT + delta <= src.y0 + src.h;
+#define PPMX_PAIR(D)                                                                                   \
+    if (own) rows_pair<CONV, KT, D, true>(src, base, row_bytes, xv, s_w[0], s_w[1], accA, accB);        \
+    else rows_pair<CONV, KT, D, false>(src, base, row_bytes, xv, s_w[0], s_w[1], accA, accB)
+        switch (delta) {
+        case 0: PPMX_PAIR(0); break;
+        case 1: PPMX_PAIR(1); break;
+        case 2: PPMX_PAIR(2); break;
+        default: PPMX_PAIR(3); break;
         }
+#undef PPMX_PAIR
     } else {
 #pragma unroll
         for (int r = 0; r < 2; r++) {
