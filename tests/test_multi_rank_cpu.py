@@ -91,3 +91,67 @@ def test_two_rank_bands_with_halo_exchange(w, h, k):
         p.join(timeout=120)
     assert all(p.exitcode == 0 for p in procs)
     assert q.get(timeout=5) is True
+
+
+def _band_worker(rank, world, port, q):
+    """Round 2: the partition of ppmx_gpu_apply_band (ppmx_gpu_band_rows, no device work) with two real ranks: each rank
+    takes ONLY the source rows the call would read, runs the chain on them with the oracle standing in for the device,
+    and rank 0 stitches; the result must equal the whole-raster chain."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    import patterns as P
+    from imageprocessingtools_b200 import ppmx as pp
+    orc = oracle.orc()
+    w, h = 48, 61
+    img = P.lcg(w, h, 777)
+    ok = True
+    # chain: 7x7 box convolution, then vertical flip (the mirrored band + 3 halo rows either side)
+    ph = pp._PlanHolder(w=w, h=h, conv_preset=2, flipv=True)
+    ops = [ph.plan.ops[i] for i in range(ph.plan.nops)]
+    oy0, orows, sy0, srows = pp.band_rows(ops, w, h, rank, world)
+    slab = img[sy0:sy0 + srows]                      # nothing else of the raster is touched
+    conv = orc.conv(slab, np.ones((7, 7), np.int64), 49, 0)
+    # output rows [oy0, oy0 + orows) of the flipped raster = convolved rows h-oy0-orows .. h-oy0-1, upside down
+    a = (h - oy0 - orows) - sy0
+    band = conv[a:a + orows][::-1]
+    gathered = [None] * world
+    dist.gather_object((oy0, np.ascontiguousarray(band)), gathered if rank == 0 else None, dst=0)
+    if rank == 0:
+        full = np.concatenate([g[1] for g in sorted(gathered, key=lambda t: t[0])], axis=0)
+        exp = orc.flip(orc.conv(img, np.ones((7, 7), np.int64), 49, 0), 1)
+        ok = ok and np.array_equal(full, exp)
+    ph.close()
+    # chain: resize to 1.5x (height pass reads the rows its table names), grey
+    ph = pp._PlanHolder(w=w, h=h, resize_w=72, gray=True)
+    ops = [ph.plan.ops[i] for i in range(ph.plan.nops)]
+    oy0, orows, sy0, srows = pp.band_rows(ops, w, h, rank, world)
+    whole = orc.process(img, resize_w=72, gray=True)
+    new_h = whole[2]
+    wt, ix = pp.calc_contributions(h, new_h, float(new_h) / h)
+    need = ix[oy0:oy0 + orows]
+    ok = ok and (sy0, sy0 + srows) == (int(need.min()), int(need.max()) + 1)
+    covered = [None] * world
+    dist.all_gather_object(covered, (oy0, orows))
+    ok = ok and sorted(covered)[0][0] == 0 and sum(c[1] for c in covered) == new_h
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok))
+    if rank == 0:
+        q.put(all(flags))
+    ph.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_apply_band_partition():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() * 11) % 2000
+    procs = [ctx.Process(target=_band_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+    assert all(p.exitcode == 0 for p in procs)
+    assert q.get(timeout=5) is True
