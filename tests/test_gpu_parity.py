@@ -423,15 +423,36 @@ def test_no_out_of_bounds_writes(gpu, orc):
     dev = torch.device("cuda", 0)
     PAD = 4096
 
-    def run(op, img, out_bytes, layout=pp.LAYOUT_RGB8, tables=0):
+    def run(op, img, out_bytes, layout=pp.LAYOUT_RGB8, tables=0, src_off=0, dst_off=0):
         h, w = img.shape[0], img.shape[1]
-        src = torch.from_numpy(np.ascontiguousarray(img)).to(dev)
+        flat = np.ascontiguousarray(img).reshape(-1)
+        srcbuf = torch.zeros((flat.size + 64,), dtype=torch.uint8, device=dev)
+        srcbuf[src_off:src_off + flat.size] = torch.from_numpy(flat).to(dev)
         buf = torch.full((PAD + out_bytes + PAD,), 0xA5, dtype=torch.uint8, device=dev)
-        gpu.launch(op, src.data_ptr(), w, h, layout, buf.data_ptr() + PAD, None, 0, tables)
+        gpu.launch(op, srcbuf.data_ptr() + src_off, w, h, layout, buf.data_ptr() + PAD + dst_off, None, 0, tables)
         torch.cuda.synchronize()
         host = buf.cpu().numpy()
-        assert (host[:PAD] == 0xA5).all() and (host[PAD + out_bytes:] == 0xA5).all(), "canary overwritten"
-        return host[PAD:PAD + out_bytes]
+        assert (host[:PAD + dst_off] == 0xA5).all() and (host[PAD + dst_off + out_bytes:] == 0xA5).all(), "canary overwritten"
+        return host[PAD + dst_off:PAD + dst_off + out_bytes]
+
+    # rasters large enough for the tile / row / unaligned-strip kernels, at odd sizes AND odd pointers on both sides
+    for (w, h) in [(130, 70), (257, 33), (1000, 9), (67, 130), (128, 80), (640, 24)]:
+        img = P.lcg(w, h, 19)
+        for (so, do) in [(0, 0), (5, 3), (1, 15), (16, 8)]:
+            kw = dict(src_off=so, dst_off=do)
+            assert np.array_equal(run(pp.PpmxOp(kind=pp.OP_GRAY), img, w * h, **kw), orc.gray(img).reshape(-1)), (w, h, so, do)
+            assert np.array_equal(run(pp.PpmxOp(kind=pp.OP_MONO_BITS), img, ((w + 7) // 8) * h, **kw), orc.pack_pbm(orc.mono(img)))
+            assert np.array_equal(run(pp.PpmxOp(kind=pp.OP_EXTRACT_R), img, w * h, **kw), img[:, :, 0].reshape(-1))
+            for d in (0, 1):
+                assert np.array_equal(run(pp.PpmxOp(kind=pp.OP_FLIP, flip_direction=d), img, w * h * 3, **kw),
+                                      orc.flip(img, d).reshape(-1)), (w, h, so, do, d)
+            for a in (90, 180, 270):
+                exp = orc.rotate(img, a)
+                assert np.array_equal(run(gpu.rotate_op(a, w, h), img, exp.size, **kw), exp.reshape(-1)), (w, h, so, do, a)
+            for kname in ("blur3", "edge3", "wide3", "box7"):
+                coef, div, bias = KERNELS[kname]
+                assert np.array_equal(run(gpu.conv_op(coef, div, bias), img, w * h * 3, **kw),
+                                      orc.conv(img, coef, div, bias).reshape(-1)), (w, h, so, do, kname)
 
     for (w, h) in [(1, 1), (5, 3), (17, 9), (33, 7), (48, 16), (64, 64), (100, 37), (128, 80), (256, 16)]:
         img = P.lcg(w, h, 9)
