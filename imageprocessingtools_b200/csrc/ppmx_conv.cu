@@ -1,6 +1,6 @@
 // ppmx_conv.cu -- EXTENSION (no reference counterpart, parity unpinned): k x k integer convolution with mirror border and row-band halos.
 // Part of libppmx_gpu.so; see ppmx_common.cuh for conventions ("ref:N" = /root/reference/ppmx-edward.c line N).
-#include "ppmx_common.cuh"
+#include "ppmx_conv.cuh"
 
 namespace ppmx {
 
@@ -11,70 +11,6 @@ namespace ppmx {
 // exact in any order, so the fast kernel may regroup taps freely and still match the self-oracle.
 // ------------------------------------------------------------------------------------------
 
-constexpr int CONV_MAXK = 15;
-
-// exact floor((2*acc + div) / (2*div)) + bias with one multiply-high: the numerator is shifted to
-// be non-negative by a multiple K of the divisor d = 2*div, then n/d = (n * M) >> (31 + l) for all
-// n < 2^31 with l = ceil(log2 d), M = ceil(2^(31+l) / d)  (Granlund & Montgomery, N = 31).
-//
-// Two cheaper modes, chosen at compile time, fold the constants into the accumulator's START value (the first
-// dp4a adds it for free): MODE 0, div == 1: start = bias, result = acc.  MODE 1, div = 2^m (m >= 1):
-// floor((2*acc + div) / (2*div)) + bias = (acc + div/2 + bias*div) >> m with an arithmetic shift, so
-// start = div/2 + bias*div and the result is one shift.  MODE 2 is the general multiply-high form.
-struct ConvRound {
-    uint32_t M, shift;  // shift = l - 1, applied to the high word of n * M
-    int32_t add, K, bias;  // n = 2*acc + add, add = div + d*K
-    int32_t mode, start, m;
-    template <int MODE>
-    __device__ __forceinline__ int32_t quotient(int32_t acc) const  // before the 0..255 clamp
-    {
-        if (MODE == 0) return acc;
-        if (MODE == 1) return acc >> m;
-        uint32_t n = (uint32_t)(2 * acc + add);
-        return (int32_t)(__umulhi(n, M) >> shift) - K + bias;
-    }
-    // four results clamped to 0..255 and packed, result 0 in the low byte: two I2IP instructions
-    template <int MODE>
-    __device__ __forceinline__ uint32_t pack4(int32_t a0, int32_t a1, int32_t a2, int32_t a3) const
-    {
-        if (MODE == 3)  // coefficients pre-scaled by 256 / div, start 128: the quotient IS byte 1 of the sum (it can not leave 0..255)
-            return __byte_perm(__byte_perm((uint32_t)a0, (uint32_t)a1, 0x0051), __byte_perm((uint32_t)a2, (uint32_t)a3, 0x0051), 0x5410);
-        uint32_t hi, out;
-        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(quotient<MODE>(a3)), "r"(quotient<MODE>(a2)), "r"(0));
-        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(quotient<MODE>(a1)), "r"(quotient<MODE>(a0)), "r"(hi));
-        return out;
-    }
-};
-
-static bool make_conv_round(int64_t sum_abs, int32_t div, int32_t bias, ConvRound *r)
-{
-    const uint64_t d = 2ull * (uint64_t)div;
-    int l = 0;
-    while ((1ull << l) < d) l++;
-    if (l < 1 || l > 30) return false;
-    const uint64_t K = (2ull * 255ull * (uint64_t)sum_abs + d - 1) / d + 1;  // makes every numerator >= 0
-    const uint64_t nmax = 2ull * 255ull * (uint64_t)sum_abs + (uint64_t)div + d * K;
-    if (nmax >= (1ull << 31) || K >= (1ull << 30)) return false;
-    const unsigned __int128 pw = (unsigned __int128)1 << (31 + l);
-    r->M = (uint32_t)((pw + d - 1) / d);
-    r->shift = (uint32_t)(l - 1);
-    r->add = (int32_t)((uint64_t)div + d * K);
-    r->K = (int32_t)K;
-    r->bias = bias;
-    r->mode = 2;
-    r->start = 0;
-    r->m = 0;
-    const int64_t folded = (int64_t)div / 2 + (int64_t)bias * div;  // MODE 1 start value
-    if (div == 1 && bias > -(1 << 20) && bias < (1 << 20)) {
-        r->mode = 0;
-        r->start = bias;
-    } else if ((d & (d - 1)) == 0 && folded > -(1ll << 28) && folded < (1ll << 28)) {
-        r->mode = 1;
-        r->start = (int32_t)folded;
-        r->m = l - 1;  // div = 2^(l-1)
-    }
-    return true;
-}
 
 // ---- generic kernel: any odd k <= 15, any coefficients, any width; scalar MACs ---------------
 struct ConvCoefGeneric {
@@ -130,13 +66,6 @@ __global__ void __launch_bounds__(256) conv_kernel(RowSource rs, uint8_t *__rest
 constexpr int FC_TW = 128;  // tile width in pixels; the tile is 8 * RV rows tall (RV rows per thread)
 constexpr int FC_PITCH = FC_TW + 32;  // one 16-pixel group of halo on each side
 
-// unsigned pixel bytes times signed coefficient bytes (the CUDA intrinsic has no mixed form)
-__device__ __forceinline__ int32_t dp4a_u8s8(uint32_t px4, uint32_t coef4, int32_t acc)
-{
-    int32_t d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px4), "r"(coef4), "r"(acc));
-    return d;
-}
 
 template <int K>
 struct ConvCoefPacked {
@@ -281,10 +210,7 @@ __global__ void __launch_bounds__(256) conv_dp4a_kernel(RowSource rs, uint8_t *_
 // and right of the thread's vector comes from L1 (it is the neighbouring lane's vector), or from the mirror
 // rule at the raster's edge.  Instruction mix per output byte: 3 IDP (fma pipe), ~1.1 PRMT + 0.75..1.5
 // finishing (alu pipe) -- both pipes issue 64 lanes/clk/SM (tools/int_peak.cu), so the kernel is bound by HBM.
-struct Conv3Coef {
-    uint32_t a[3], b[3];    // per tap column dx = -1, 0, +1: the coefficient bytes for the upper / lower row of a pair
-    uint32_t ah[3], bh[3];  // WIDE kernels only: coefficients beyond a signed byte are split c = 128 * hi + lo
-};
+// (struct Conv3Coef: ppmx_conv.cuh)
 
 template <int MODE>
 __device__ __forceinline__ uint32_t strip_pack4(const ConvRound &rnd, int32_t a0, int32_t a1, int32_t a2, int32_t a3)
@@ -442,6 +368,7 @@ __global__ void __launch_bounds__(BLOCK) conv3_strip_kernel(RowSource rs, uint8_
     else conv3_strip_body<MODE, RH, PF, false, WIDE>(rs, dst, nchunks, cx, ys, cf, rnd);
 }
 
+#ifdef PPMX_TUNING
 // any width, any alignment: 4 rows per strip, one warp = 32 chunks of a row (lanes beyond the row's last chunk idle along)
 template <int MODE, bool WIDE>
 __global__ void __launch_bounds__(128) conv3_strip_ua_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks,
@@ -456,6 +383,7 @@ __global__ void __launch_bounds__(128) conv3_strip_ua_kernel(RowSource rs, uint8
     if (ys >= 1 && ys + 4 + 1 <= rs.h) conv3_strip_body<MODE, 4, 2, true, WIDE, true>(rs, dst, nchunks, cx, ys, cf, rnd, row_bytes, stage_all[warp], cx0);
     else conv3_strip_body<MODE, 4, 2, false, WIDE, true>(rs, dst, nchunks, cx, ys, cf, rnd, row_bytes, stage_all[warp], cx0);
 }
+#endif
 
 static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef,
                                ConvRound rnd, int32_t div, int32_t bias, cudaStream_t s, bool unaligned = false)
@@ -503,7 +431,9 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
         cf.ah[dx] = hi[0] | hi[1] << 8 | hi[2] << 16;
         cf.bh[dx] = hi[0] << 8 | hi[1] << 16 | hi[2] << 24;
     }
-    if (unaligned) {
+    if (unaligned && PPMX_VARIANT != 20) return conv3_ua_launch(rs, dst, w, h, cf, rnd, mode, wide, s);  // ppmx_conv_ua.cu
+#ifdef PPMX_TUNING
+    if (unaligned) {  // the first any-alignment kernel (three aligned vectors per thread and row, word selects): variant 20
         const uint32_t row_bytes = w * 3u, nch = (row_bytes + 15u) / 16u;
         dim3 grid((nch + 127) / 128, (h + 3) / 4);
         if (grid.y > 65535u) return cudaErrorInvalidValue;
@@ -519,6 +449,7 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
 #undef PPMX_CONV3_UA
         return PPMX_LAUNCHED();
     }
+#endif
     const uint32_t nchunks = w * 3 / 16;
 #define PPMX_CONV3_LAUNCH(MODE, RH, PF, BLOCK)                                                                   \
     do {                                                                                                         \
@@ -759,34 +690,6 @@ static cudaError_t conv_box(const RowSource &rs, uint8_t *dst, uint32_t w, uint3
     return PPMX_LAUNCHED();
 }
 
-// coef = u * v^T with integer factors, v within int8?  (box, binomial/"Gaussian" blurs are; sharpen and
-// edge kernels are not)
-template <int K>
-static bool rank_one(const int32_t *coef, int32_t (&u)[K], int32_t (&v)[K])
-{
-    int r0 = -1, c0 = -1;
-    for (int i = 0; i < K * K && r0 < 0; i++)
-        if (coef[i]) { r0 = i / K; c0 = i % K; }
-    if (r0 < 0) return false;
-    // v = row r0 divided by the gcd of its entries, so that u stays integral whenever a factorisation exists
-    int64_t g = 0;
-    for (int x = 0; x < K; x++) {
-        int64_t a = coef[r0 * K + x] < 0 ? -(int64_t)coef[r0 * K + x] : coef[r0 * K + x], b = g;
-        while (b) { int64_t t = a % b; a = b; b = t; }
-        g = a;
-    }
-    for (int x = 0; x < K; x++) {
-        v[x] = (int32_t)(coef[r0 * K + x] / g);
-        if (v[x] < -128 || v[x] > 127) return false;
-    }
-    for (int y = 0; y < K; y++) {
-        if (coef[y * K + c0] % v[c0]) return false;
-        u[y] = coef[y * K + c0] / v[c0];
-        for (int x = 0; x < K; x++)
-            if ((int64_t)u[y] * v[x] != coef[y * K + x]) return false;
-    }
-    return true;
-}
 
 // ---- rank-1 kernels (coef = u v^T: Gaussian / binomial blurs, Sobel-like derivatives), K = 5 or 7 ----------
 // Same thread layout as the box kernel (16 byte columns per thread walking down RH rows, warps overlapped by two
@@ -1082,8 +985,14 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         return conv_box<11>(rs, dst, w, h, bm, bc, s);
     }
     const bool rnd_ok = make_conv_round(sum_abs, div, bias, &rnd);
+    [[maybe_unused]] const int strip_rh = PPMX_VARIANT >= 15 && PPMX_VARIANT <= 18 ? PPMX_VARIANT - 14 : 0;  // strip geometry (tuning build)
+    if (rnd_ok && fast_layout && (k == 5 || k == 7) && PPMX_VARIANT != 7 && PPMX_VARIANT != 2 && PPMX_VARIANT != 14 && aligned16(dst)) {
+        // rank-1 whose column sums fit 16 bits (ppmx_conv_sep.cu): packed pairs, dp2a along the row
+        cudaError_t e = cudaSuccess;
+        if (conv_sep16(rs, dst, w, h, k, coef, div, bias, rnd, strip_rh, s, &e)) return e;
+    }
     if (rnd_ok && fast_layout && (k == 5 || k == 7) && PPMX_VARIANT != 7 && PPMX_VARIANT != 2 && aligned16(dst)) {
-        // rank-1 (only the two factors must be small, not their products): sliding vertical words
+        // rank-1 (only the two factors must be small, not their products): sliding vertical words, 32-bit column sums
         cudaError_t e = cudaSuccess;
         if (k == 5 ? conv_sep<5>(rs, dst, w, h, coef, rnd, s, &e) : conv_sep<7>(rs, dst, w, h, coef, rnd, s, &e)) return e;
     }
@@ -1092,6 +1001,11 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         bool splittable = true;
         for (int i = 0; i < 9; i++) splittable = splittable && coef[i] >= -16320 && coef[i] <= 16320;
         if (splittable) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s);
+    }
+    if (s8 && (k == 5 || k == 7) && fast_layout && aligned16(dst) && rnd_ok && PPMX_VARIANT != 7 && PPMX_VARIANT != 14) {
+        // dense 5x5 / 7x7: two dp4a per tap column on the vertical words (ppmx_conv_sep.cu)
+        cudaError_t e = cudaSuccess;
+        if (conv_dense_strip(rs, dst, w, h, k, coef, rnd, strip_rh, s, &e)) return e;
     }
     if (s8 && (k == 3 || k == 5 || k == 7) && fast_layout && aligned4(dst) && rnd_ok) {
         // variant 7 keeps the row-wise (planar dp4a) kernel for 3x3; the strip kernel is the default

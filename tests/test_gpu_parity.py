@@ -271,6 +271,13 @@ KERNELS["blur3_div256"] = (np.array([[16, 32, 16], [32, 64, 32], [16, 32, 16]]),
 KERNELS["cross3_div4"] = (np.array([[0, 1, 0], [1, 0, 1], [0, 1, 0]]), 4, 0)                  #   the quotient is byte 1 of the scaled sum
 KERNELS["pair3_div2"] = (np.array([[0, 0, 0], [0, 1, 1], [0, 0, 0]]), 2, 0)                   # scaled coefficient 128 > 127: shift form
 KERNELS["big5"] = (np.array([[300, -200, 0, 5, 1]] * 5), 7, -3)  # coefficients beyond int8: generic kernel
+_rng7 = np.random.RandomState(7)
+KERNELS["dense7_mix"] = (_rng7.randint(-128, 128, (7, 7)), 173, 5)          # dense 7x7, full signed-byte range: vertical-word strip kernel
+KERNELS["dense7_pos_pow2"] = (_rng7.randint(0, 6, (7, 7)), 128, 0)           # dense 7x7, power-of-two divisor (shift form)
+KERNELS["dense5_div1"] = (_rng7.randint(-3, 4, (5, 5)), 1, 64)               # dense 5x5, div 1
+KERNELS["sep7_u16_edge"] = (np.outer([36, 36, 37, 37, 37, 37, 37], [1, 2, 3, 4, 3, 2, 1]), 4112, 0)  # rank 1, column sums up to 65535: the 16-bit limit
+KERNELS["sep7_u16_over"] = (np.outer([36, 37, 37, 37, 37, 37, 37], [1, 2, 3, 4, 3, 2, 1]), 4128, 0)  # one beyond it: the 32-bit rank-1 kernel
+KERNELS["sep5_s16_edge"] = (np.outer([-25, 26, -26, 26, -25], [1, -2, 3, -2, 1]), 9, 128)             # signed rank 1, |column sums| up to 32640
 
 
 def test_extension_conv(gpu, orc):
@@ -282,6 +289,25 @@ def test_extension_conv(gpu, orc):
                 assert np.array_equal(gpu.conv(img, coef, div, bias), orc.conv(img, coef, div, bias)), (w, h, pname, kname)
 
 
+def test_extension_conv3_any_width(gpu_tuning, orc):
+    """3x3 at widths that are no multiple of 16 (ppmx_conv_ua.cu): the row's end at every position of a 16-byte chunk,
+    rows of one warp, several warps and several CTAs, strips cut short by the raster's end; the first any-alignment kernel
+    (tuning variant 20) gives the same bytes."""
+    gpu = gpu_tuning
+    widths = list(range(16, 33)) + [47, 63, 65, 170, 171, 172, 173, 341, 683, 684, 685, 1367, 2731]
+    try:
+        for v in (0, 20):
+            gpu.set_tuning("variant", v)
+            for w in widths:
+                h = max(9, -(-4096 // w) + (w % 4))
+                img = P.lcg(w, h, 1000 + w)
+                for kname in ("blur3", "edge3", "wide3", "mix3_div8_biasneg"):
+                    coef, div, bias = KERNELS[kname]
+                    assert np.array_equal(gpu.conv(img, coef, div, bias), orc.conv(img, coef, div, bias)), (v, w, h, kname)
+    finally:
+        gpu.set_tuning("variant", 0)
+
+
 def test_extension_conv_row_bands(gpu, orc):
     """A raster cut into row bands, each convolved separately with halo rows read through the band
     pointers (here: the neighbour band in the same HBM), equals the whole-raster result."""
@@ -289,6 +315,8 @@ def test_extension_conv_row_bands(gpu, orc):
     import imageprocessingtools_b200.ppmx as pp
     for (w, h, k, cuts, kname) in [(128, 96, 3, [0, 32, 64, 96], None), (128, 96, 7, [0, 24, 48, 72, 96], None),
                                    (64, 50, 5, [0, 7, 13, 50], "emboss5"), (37, 23, 3, [0, 10, 23], None),
+                                   (301, 60, 3, [0, 13, 30, 31, 60], "edge3"), (1000, 21, 3, [0, 2, 9, 21], "blur3"),   # any-width strip kernel
+                                   (2048, 70, 7, [0, 17, 40, 70], "dense7_mix"), (2048, 70, 5, [0, 35, 70], "sep5_s16_edge"),
                                    (256, 40, 7, [0, 3, 6, 40], None),
                                    (128, 96, 5, [0, 32, 64, 96], "gauss5"), (256, 40, 7, [0, 3, 6, 40], "gauss7"),   # rank-1 kernel
                                    (64, 50, 5, [0, 7, 13, 50], "sep5_asym"), (128, 200, 3, [0, 67, 134, 200], "edge3"),
@@ -534,6 +562,25 @@ def test_extension_conv3_strip_variants(gpu_tuning, orc):
                 for k in names:
                     assert np.array_equal(gpu.conv(img, *KERNELS[k]), exp[(i, k)]), (v, i, k)
             assert np.array_equal(gpu.conv(imgs[0], np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]]) * 4, 64, 0), exp_big), v
+    finally:
+        gpu.set_tuning("variant", 0)
+
+
+def test_extension_conv_vertical_word_kernels(gpu_tuning, orc):
+    """5x5 / 7x7 on the vertical-word strip kernels (ppmx_conv_sep.cu): rank-1 with 16-bit column sums (unsigned, scaled
+    "byte 2" quotient, signed) and dense, at sizes with many strips, inner and edge warps and an odd last row; the strip
+    geometries of the tuning build (variants 15-18) and the older kernels (variant 14) give the same bytes."""
+    gpu = gpu_tuning
+    names = ("gauss7", "gauss5", "sep5_signed", "sep7_div3", "sep7_div1_neg", "sep7_u16_edge", "sep7_u16_over", "sep5_s16_edge",
+             "dense7_mix", "dense7_pos_pow2", "dense5_div1", "emboss5", "neg7_div64_bias", "box7_sat")
+    imgs = [P.lcg(2048, 301, 21), P.const(496, 70, 255), P.all_patterns(1008, 37)["mixed"]]
+    exp = {(i, k): orc.conv(img, *KERNELS[k]) for i, img in enumerate(imgs) for k in names}
+    try:
+        for v in (0, 14, 15, 16, 17, 18):
+            gpu.set_tuning("variant", v)
+            for i, img in enumerate(imgs):
+                for k in names:
+                    assert np.array_equal(gpu.conv(img, *KERNELS[k]), exp[(i, k)]), (v, i, k)
     finally:
         gpu.set_tuning("variant", 0)
 
