@@ -1014,7 +1014,7 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         if (k == 5) return conv_fast<5>(rs, dst, w, h, coef, rnd, s);
         return conv_fast<7>(rs, dst, w, h, coef, rnd, s);
     }
-    if (k == 3 && rnd_ok && !fast_layout && w >= 16 && (size_t)w * h >= 4096 && PPMX_VARIANT == 0) {
+    if (k == 3 && rnd_ok && !fast_layout && w >= 16 && (size_t)w * h >= 4096 && (PPMX_VARIANT == 0 || (PPMX_VARIANT >= 20 && PPMX_VARIANT <= 22))) {
         // 3x3 at any width / alignment (whole rasters and row bands alike): the strip kernel's unaligned form
         bool ok16 = true;
         for (int i = 0; i < 9; i++) ok16 = ok16 && coef[i] >= -16320 && coef[i] <= 16320;

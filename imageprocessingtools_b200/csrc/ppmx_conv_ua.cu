@@ -20,82 +20,109 @@
 
 namespace ppmx {
 
-constexpr int UA_PITCH = 544;  // staged row: 520-byte window + 3 bytes of shift = 131 words, + the 8-word reads of the last lanes
+constexpr int UA_PITCH = 656;   // staged source row: 520-byte window + 3 bytes of shift = 131 words; inner warps copy 160 words (no predicate)
+constexpr int UA_OPITCH = 544;  // staged result row: 512 bytes + the word behind it
 
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void *gmem_src)
 {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
-
-// `nb` bytes from shared memory (16-byte aligned, 4 bytes of slack behind the run) to any global address, by one warp
+// the same at a constant byte offset OFF of both addresses (an immediate in the instruction: no address arithmetic per copy)
+template <int OFF>
+__device__ __forceinline__ void cp_async4_at(uint32_t smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0 + %2], [%1 + %2], 4;" ::"r"(smem_dst), "l"(gmem_src), "n"(OFF) : "memory");
+}
+// `nb` bytes from shared memory (16-byte aligned, 4 bytes of slack behind the run) to any global address, by one warp: whole
+// 4-byte words of the destination as coalesced stores (lane l: words l, l+32, ...), the up to 3 bytes in front of the first
+// and behind the last word by lanes 0..2 and 3..5
 __device__ __forceinline__ void ua_store_run(uint8_t *g, const uint8_t *srow, uint32_t nb, uint32_t lane)
 {
     const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u);
-    const uint32_t hb = min(nb, (4u - a) & 3u), nw = (nb - hb) >> 2, tb = nb - hb - 4u * nw;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(srow);
-    uint32_t *gw = reinterpret_cast<uint32_t *>(g + hb);
-    const uint32_t sh = 8u * hb;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(srow) + lane;
+    uint32_t hb, nw, tb;
+    if (nb == 512u) {  // a full run (all warps but a row's last): only the last word of the last lane may be missing
+        hb = (4u - a) & 3u;
+        nw = hb ? 127u : 128u;
+        tb = hb ? 4u - hb : 0u;
+        uint32_t *gw = reinterpret_cast<uint32_t *>(g + hb) + lane;
+        const uint32_t sh = 8u * hb;
 #pragma unroll
-    for (uint32_t t = 0; t < 4u; t++) {
-        const uint32_t j = lane + 32u * t;
-        if (j < nw) gw[j] = __funnelshift_r(sw[j], sw[j + 1], sh);
+        for (uint32_t t = 0; t < 3u; t++) gw[32u * t] = __funnelshift_r(sw[32u * t], sw[32u * t + 1], sh);
+        if (lane < 31u || !hb) gw[96] = __funnelshift_r(sw[96], sw[97], sh);
+    } else {
+        hb = min(nb, (4u - a) & 3u);
+        nw = (nb - hb) >> 2;
+        tb = nb - hb - 4u * nw;
+        uint32_t *gw = reinterpret_cast<uint32_t *>(g + hb) + lane;
+        const uint32_t sh = 8u * hb;
+#pragma unroll
+        for (uint32_t t = 0; t < 4u; t++)
+            if (lane + 32u * t < nw) gw[32u * t] = __funnelshift_r(sw[32u * t], sw[32u * t + 1], sh);
     }
-    if (lane < hb) g[lane] = srow[lane];
-    if (lane < tb) g[hb + 4u * nw + lane] = srow[hb + 4u * nw + lane];
+    const bool tail = lane >= 3u;
+    const uint32_t k = tail ? lane - 3u : lane, pos = tail ? hb + 4u * nw + k : k;
+    if (k < (tail ? tb : hb) && lane < 6u) g[pos] = srow[pos];
 }
 
-template <int MODE, bool WIDE>
+template <int MODE, bool WIDE, int RH>
 __global__ void __launch_bounds__(128) conv3_ua_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks, uint32_t row_bytes,
                                                        const Conv3Coef cf, const ConvRound rnd)
 {
     pdl_trigger();
-    __shared__ __align__(16) uint8_t s_in[4][6][UA_PITCH];
-    __shared__ __align__(16) uint8_t s_out[4][2][UA_PITCH];
+    constexpr int NR = RH + 2, NG = RH / 2;  // source rows of a strip; row pairs = cp.async groups
+    __shared__ __align__(16) uint8_t s_in[4][NR][UA_PITCH];
+    __shared__ __align__(16) uint8_t s_out[4][2][UA_OPITCH];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t c0 = blockIdx.x * 128u + warp * 32u;  // the warp's first chunk
     if (c0 >= nchunks) return;                            // (a whole warp)
-    const int ys = blockIdx.y * 4;                        // first output row of the strip, band-local
+    const int ys = blockIdx.y * RH;                       // first output row of the strip, band-local
     const size_t pitch = row_bytes;
-    const bool inner = ys >= 1 && ys + 5 <= rs.h;  // source rows ys-1 .. ys+4 all in the own band
+    const bool inner = ys >= 1 && ys + RH + 1 <= rs.h;  // source rows ys-1 .. ys+RH all in the own band
     const int gy0 = rs.y0 + ys;
-    const bool left = c0 == 0, right = 16u * c0 + 516u > row_bytes;  // the window reaches beyond the row's first / last byte
+    // the window reaches beyond the row's first / last byte; `far`: 640 bytes from the window's start still lie inside the row
+    const bool left = c0 == 0, right = 16u * c0 + 516u > row_bytes, far = 16u * c0 + 640u <= row_bytes;
     const int64_t base_b = (int64_t)16 * c0 - 4;                     // row byte of the window's first byte
     uint8_t(*sin)[UA_PITCH] = s_in[warp];
     pdl_wait();
 
-    // ---- in: six row windows -> shared memory, 4 bytes per copy, coalesced ----
-    uint32_t shift[6];
+    // ---- in: the row windows -> shared memory, 4 bytes per copy, coalesced; rows 0..3 are group 0, every further pair one more ----
+    uint32_t shift[NR];
+    const uint8_t *rowp = rs.own + (ptrdiff_t)(ys - 1) * (ptrdiff_t)pitch;  // (inner strips: plain pointer steps)
+    const uint32_t sdst0 = (uint32_t)__cvta_generic_to_shared(sin[0]) + 4u * lane;
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
-        const uint8_t *rowp = inner ? rs.own + (size_t)(ys - 1 + r) * pitch : rs.row(gy0 - 1 + r, pitch);
+    for (int r = 0; r < NR; r++) {
+        if (!inner) rowp = rs.row(gy0 - 1 + r, pitch);
         const uintptr_t g = reinterpret_cast<uintptr_t>(rowp) + (uintptr_t)base_b;
-        const uintptr_t g4 = g & ~(uintptr_t)3;
         shift[r] = 8u * (uint32_t)(g & 3u);
-        uint8_t *srow = sin[r];
-        if (!left && !right) {
-#pragma unroll
-            for (uint32_t t = 0; t < 4u; t++) cp_async4(srow + 4u * (lane + 32u * t), reinterpret_cast<const void *>(g4 + 4u * (lane + 32u * t)));
-            if (lane < 3u) cp_async4(srow + 4u * (lane + 128u), reinterpret_cast<const void *>(g4 + 4u * (lane + 128u)));
+        const uint8_t *gsrc = reinterpret_cast<const uint8_t *>(g & ~(uintptr_t)3) + 4u * lane;  // this lane's first word of the window
+        const uint32_t sdst = sdst0 + (uint32_t)(r * UA_PITCH);
+        if (!left && far) {  // 5 x 32 words, the last 29 of them unused
+            cp_async4_at<0>(sdst, gsrc);
+            cp_async4_at<128>(sdst, gsrc);
+            cp_async4_at<256>(sdst, gsrc);
+            cp_async4_at<384>(sdst, gsrc);
+            cp_async4_at<512>(sdst, gsrc);
         } else {  // only words holding at least one byte of the row
             const uintptr_t lo = reinterpret_cast<uintptr_t>(rowp) & ~(uintptr_t)3;
             const uintptr_t hi = (reinterpret_cast<uintptr_t>(rowp) + row_bytes - 1u) & ~(uintptr_t)3;
 #pragma unroll
             for (uint32_t t = 0; t < 5u; t++) {
-                const uint32_t j = lane + 32u * t;
-                const uintptr_t wa = g4 + 4u * j;
-                if (j < 131u && wa >= lo && wa <= hi) cp_async4(srow + 4u * j, reinterpret_cast<const void *>(wa));
+                const uintptr_t wa = reinterpret_cast<uintptr_t>(gsrc) + 128u * t;
+                if (lane + 32u * t < 131u && wa >= lo && wa <= hi) cp_async4(sdst + 128u * t, reinterpret_cast<const void *>(wa));
             }
         }
+        if (inner) rowp += pitch;
+        if (r >= 3 && (r & 1)) asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
     if (left || right) {  // pixel -1 mirrors to pixel 0, pixel W to pixel W-1: three bytes each, per row
-        if (lane < 18u) {
-            const uint32_t r = lane / 3u, k = lane - 3u * r, s = shift[0] >> 3;  // (shift[r] below: selected without dynamic indexing)
-            uint32_t sr = s;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (lane < 3u * NR) {
+            const uint32_t r = lane / 3u, k = lane - 3u * r;
+            uint32_t sr = shift[0] >> 3;  // (shift[r]: selected without dynamic indexing)
 #pragma unroll
-            for (int q = 1; q < 6; q++) sr = r == (uint32_t)q ? (shift[q] >> 3) : sr;
+            for (int q = 1; q < NR; q++) sr = r == (uint32_t)q ? (shift[q] >> 3) : sr;
             uint8_t *srow = sin[r];
             if (left) srow[sr + 1u + k] = srow[sr + 4u + k];
             if (right) {
@@ -118,6 +145,8 @@ __global__ void __launch_bounds__(128) conv3_ua_kernel(RowSource rs, uint8_t *__
         w6[4] = __funnelshift_r(y.x, y.y, sh);
         w6[5] = __funnelshift_r(y.y, y.z, sh);
     };
+    asm volatile("cp.async.wait_group %0;" ::"n"(NG - 1) : "memory");  // rows 0..3 (group 0) before the first pair
+    __syncwarp();
     uint32_t tlo[6], thi[6];
     {
         uint32_t a[6], b[6];
@@ -130,10 +159,14 @@ __global__ void __launch_bounds__(128) conv3_ua_kernel(RowSource rs, uint8_t *__
         }
     }
     const uint32_t run = min(512u, row_bytes - 16u * c0);
-    uint8_t(*sout)[UA_PITCH] = s_out[warp];
+    uint8_t(*sout)[UA_OPITCH] = s_out[warp];
 #pragma unroll
-    for (int g = 0; g < 2; g++) {
+    for (int g = 0; g < NG; g++) {
         if (!inner && ys + 2 * g >= rs.h) return;
+        if (g == 1) asm volatile("cp.async.wait_group %0;" ::"n"(NG >= 2 ? NG - 2 : 0) : "memory");
+        if (g == 2) asm volatile("cp.async.wait_group %0;" ::"n"(NG >= 3 ? NG - 3 : 0) : "memory");
+        if (g == 3) asm volatile("cp.async.wait_group %0;" ::"n"(NG >= 4 ? NG - 4 : 0) : "memory");
+        if (g >= 1) __syncwarp();
         uint32_t ulo[6], uhi[6];
         {
             uint32_t a[6], b[6];
@@ -183,16 +216,17 @@ __global__ void __launch_bounds__(128) conv3_ua_kernel(RowSource rs, uint8_t *__
     }
 }
 
-cudaError_t conv3_ua_launch(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const Conv3Coef &cf, const ConvRound &rnd,
-                            int mode, bool wide, cudaStream_t s)
+template <int RH>
+static cudaError_t conv3_ua_rh(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const Conv3Coef &cf, const ConvRound &rnd,
+                               int mode, bool wide, cudaStream_t s)
 {
     const uint32_t row_bytes = w * 3u, nch = (row_bytes + 15u) / 16u;
-    dim3 grid((nch + 127) / 128, (h + 3) / 4);
+    dim3 grid((nch + 127) / 128, (h + RH - 1) / RH);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
-#define PPMX_CONV3_UA(MODE)                                                                                       \
-    do {                                                                                                          \
-        if (wide) launch(conv3_ua_kernel<MODE, true>, grid, dim3(128), 0, s, rs, dst, nch, row_bytes, cf, rnd);   \
-        else launch(conv3_ua_kernel<MODE, false>, grid, dim3(128), 0, s, rs, dst, nch, row_bytes, cf, rnd);       \
+#define PPMX_CONV3_UA(MODE)                                                                                           \
+    do {                                                                                                              \
+        if (wide) launch(conv3_ua_kernel<MODE, true, RH>, grid, dim3(128), 0, s, rs, dst, nch, row_bytes, cf, rnd);   \
+        else launch(conv3_ua_kernel<MODE, false, RH>, grid, dim3(128), 0, s, rs, dst, nch, row_bytes, cf, rnd);       \
     } while (0)
     if (mode == 0) PPMX_CONV3_UA(0);
     else if (mode == 1) PPMX_CONV3_UA(1);
@@ -200,6 +234,16 @@ cudaError_t conv3_ua_launch(const RowSource &rs, uint8_t *dst, uint32_t w, uint3
     else PPMX_CONV3_UA(2);
 #undef PPMX_CONV3_UA
     return PPMX_LAUNCHED();
+}
+
+cudaError_t conv3_ua_launch(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const Conv3Coef &cf, const ConvRound &rnd,
+                            int mode, bool wide, cudaStream_t s)
+{
+#ifdef PPMX_TUNING
+    if (PPMX_VARIANT == 21) return conv3_ua_rh<8>(rs, dst, w, h, cf, rnd, mode, wide, s);
+    if (PPMX_VARIANT == 22) return conv3_ua_rh<2>(rs, dst, w, h, cf, rnd, mode, wide, s);
+#endif
+    return conv3_ua_rh<4>(rs, dst, w, h, cf, rnd, mode, wide, s);
 }
 
 }  // namespace ppmx
