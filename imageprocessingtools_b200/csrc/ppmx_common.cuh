@@ -40,6 +40,16 @@ static inline int sm_count()
 // arithmetic runs before the wait, all global-memory traffic after it.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// A load that stays BEHIND pdl_wait().  __ldg / `const __restrict__` loads are ld.global.nc: the compiler treats their target as
+// read-only for the kernel's lifetime and may hoist them above the wait (seen with predicated 4-byte __ldg in the tile kernel's
+// staging: LDG.E.CONSTANT scheduled before ACQBULK, the predecessor's output read while it was still being written).  A plain
+// ld.global in a volatile asm keeps its place; tests/test_sass_checks.py scans every kernel for global accesses before the wait.
+__device__ __forceinline__ uint32_t ld_global_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 #define PDL_PROLOGUE() \
     do {               \
         pdl_trigger(); \

@@ -36,8 +36,7 @@ struct GeomOut {
 };
 
 // A row piece of `nbytes` (<= 208) bytes from shared memory (4-byte aligned row, piece at byte `soff`) to any global
-// address, by HALF a warp (hl = 0..15): up to 15 bytes each at the piece's ends go out one by one, everything between
-// as 16-byte vectors to aligned addresses, each assembled from five shared-memory words by a funnel shift.
+// address, by HALF a warp (hl = 0..15).
 template <int STORE>
 __device__ __forceinline__ void store_piece(uint8_t *g, const uint8_t *srow, uint32_t soff, uint32_t nbytes, uint32_t hl)
 {
@@ -46,13 +45,20 @@ __device__ __forceinline__ void store_piece(uint8_t *g, const uint8_t *srow, uin
         for (uint32_t k = hl; k < nbytes / 8u; k += 16u) reinterpret_cast<uint2 *>(g)[k] = s[k];
         return;
     }
-    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
-    const uint32_t hb = min(nbytes, (16u - a) & 15u), nv = (nbytes - hb) >> 4, tb = nbytes - hb - 16u * nv;
-    if (hl < nv) reinterpret_cast<uint4 *>(g + hb)[hl] = smem_vec_at(srow, soff + hb + 16u * hl);
-    for (uint32_t b = hl; b < hb + tb; b += 16u) {
-        const uint32_t pos = b < hb ? b : nbytes - tb + (b - hb);
-        g[pos] = srow[soff + pos];
-    }
+    // whole 4-byte words of the destination, coalesced over the half warp and each assembled from two shared-memory words by one
+    // funnel shift; the up to 3 bytes in front of the first and behind the last word by lanes 0..2 and 3..5.  (The first form
+    // wrote aligned 16-byte vectors and up to 15 bytes at either end one by one: 30 of a 192-byte piece went out as byte stores.)
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u);
+    const uint32_t hb = min(nbytes, (4u - a) & 3u), nw = (nbytes - hb) >> 2, tb = nbytes - hb - 4u * nw;
+    const uint32_t q0 = soff + hb, sh = 8u * (q0 & 3u);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(srow + (q0 & ~3u)) + hl;
+    uint32_t *gw = reinterpret_cast<uint32_t *>(g + hb) + hl;
+#pragma unroll
+    for (uint32_t t = 0; t < 4u; t++)  // (nbytes <= 208: at most 52 words)
+        if (hl + 16u * t < nw) gw[16u * t] = __funnelshift_r(sw[16u * t], sw[16u * t + 1], sh);
+    const bool tail = hl >= 3u;
+    const uint32_t k = tail ? hl - 3u : hl, pos = tail ? hb + 4u * nw + k : k;
+    if (hl < 6u && k < (tail ? tb : hb)) g[pos] = srow[soff + pos];
 }
 
 // TRANSPOSE 1: out row <- source column x (REV_Y: row w-1-x), out pixel <- source row y (REV_X: pixel h-1-y)
@@ -70,9 +76,8 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
     const uint32_t tx0 = blockIdx.x * 64u, ty0 = blockIdx.y * 64u;
     const uint32_t nc = min(64u, w - tx0), nr = min(64u, h - ty0);
     const uintptr_t g0 = reinterpret_cast<uintptr_t>(src) + (size_t)ty0 * in_pitch + (size_t)tx0 * 3;
-    // rows staged as aligned 16-byte vectors keep their 0..15 bytes of misalignment in front of them in tin
-    const uint32_t a0 = LOAD == GL_BULK ? 0u : (uint32_t)(g0 & 15u), ap = LOAD == GL_BULK ? 0u : (in_pitch & 15u);
-
+    // (rows staged without the bulk-copy engine are byte-realigned on the way in: pixel tx0 of a row is byte 0 of its staged row)
+    constexpr uint32_t a0 = 0u, ap = 0u;
     // ---- 1. the tile's source rows -> tin ------------------------------------------------------------------
     if (LOAD == GL_BULK) {
         if (tid == 0) {
@@ -102,22 +107,36 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
             : "memory");
     } else {
         pdl_wait();
-        // aligned 16-byte vectors covering [g, g + 3 nc), half a warp per row (at most 13 vectors), four row pairs in flight
+        // Half a warp per row, four row pairs in flight.  A lane copies the words hl, hl+16, hl+32 of the row piece: each is cut
+        // out of the two aligned global words that hold it (coalesced 4-byte loads, the second one an L1 hit of the neighbour's
+        // first) by a funnel shift whose amount is the same for the whole row -- the misalignment is gone before the pixels
+        // are cut out.  (The first form staged aligned 16-byte vectors and left every pixel read to undo its row's offset: ten
+        // instructions per pixel instead of three.)
         const uint32_t hl = lane & 15u, hr = lane >> 4;
+        const uint32_t nwords = (nc * 3u + 3u) >> 2;
+        uint32_t *tin32w = reinterpret_cast<uint32_t *>(tin);
 #pragma unroll
         for (uint32_t i4 = 0; i4 < 8u; i4 += 4u) {
-            uint4 v[4];
+            uint32_t lo[4][3], hi[4][3], sh[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const uint32_t r = warp * 16u + 2u * (i4 + u) + hr;
                 const uintptr_t g = g0 + (size_t)r * in_pitch;
-                const uint32_t a = (uint32_t)(g & 15u), nvec = r < nr ? (a + nc * 3u + 15u) >> 4 : 0u;
-                v[u] = hl < nvec ? __ldg(reinterpret_cast<const uint4 *>(g - a) + hl) : make_uint4(0u, 0u, 0u, 0u);
+                const uintptr_t last = (g + nc * 3u - 1u) & ~(uintptr_t)3;  // the last aligned word holding a byte of the piece
+                const uint32_t *gw = reinterpret_cast<const uint32_t *>(g & ~(uintptr_t)3) + hl;
+                sh[u] = 8u * (uint32_t)(g & 3u);
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const bool on = r < nr && hl + 16u * t < nwords;
+                    lo[u][t] = on ? ld_global_u32(gw + 16 * t) : 0u;  // (not __ldg: see ld_global_u32)
+                    hi[u][t] = on && reinterpret_cast<uintptr_t>(gw + 16 * t + 1) <= last ? ld_global_u32(gw + 16 * t + 1) : 0u;
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const uint32_t r = warp * 16u + 2u * (i4 + u) + hr;
-                if (hl < 13u) reinterpret_cast<uint4 *>(tin + r * GI_PITCH)[hl] = v[u];
+#pragma unroll
+                for (int t = 0; t < 3; t++) tin32w[r * (GI_PITCH / 4) + hl + 16u * t] = __funnelshift_r(lo[u][t], hi[u][t], sh[u]);
             }
         }
         __syncthreads();
