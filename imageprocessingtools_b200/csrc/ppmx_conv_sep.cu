@@ -116,9 +116,10 @@ struct Sep16Coef {
     uint32_t ua_lo, ua_hi, ub_lo, ub_hi;
     uint32_t v[2];   // v[0 .. K-2] as bytes, tap 2p, 2p+1 = byte pair p
     int32_t v_last;  // v[K-1]
+    int32_t centre;  // CENTRE kernels: coef = u v^T + centre * delta (unsharp masks: (1 + k) div delta - k G)
 };
 
-template <int K, int MODE, bool SIGNED, int RH, bool INNER, bool EDGE>
+template <int K, int MODE, bool SIGNED, bool CENTRE, int RH, bool INNER, bool EDGE>
 __device__ __forceinline__ void conv_sep16_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, int chunk, int ys,
                                                 const Sep16Coef<K> &cf, const ConvRound &rnd)
 {
@@ -151,7 +152,8 @@ __device__ __forceinline__ void conv_sep16_body(const RowSource &rs, uint8_t *__
         W.init(f);
     }
 
-    auto emit = [&](uint32_t ulo, uint32_t uhi, uint8_t *o) {
+    // cw / csel: the window words and the byte of them that hold the output row itself (the centre tap of CENTRE kernels)
+    auto emit = [&](uint32_t ulo, uint32_t uhi, uint8_t *o, const uint32_t(&cw)[16], uint32_t csel) {
         int32_t S[16 + SH];  // column sums of byte columns 0 .. 15 + SH
 #pragma unroll
         for (int c = 0; c < 16; c++) S[c] = vdot4<SIGNED>(W.hi[c], uhi, vdot4<SIGNED>(W.lo[c], ulo, 0));
@@ -185,7 +187,7 @@ __device__ __forceinline__ void conv_sep16_body(const RowSource &rs, uint8_t *__
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int c = 4 * b + j;
-                int32_t t = rnd.start;
+                int32_t t = CENTRE ? rnd.start + cf.centre * (int32_t)__byte_perm(cw[c], 0u, csel) : rnd.start;
 #pragma unroll
                 for (int p = 0; p < NP; p++) {  // taps 2p, 2p+1 at byte columns c + 3 (2p - R), c + 3 (2p + 1 - R)
                     const uint32_t q = Q[H + c + 3 * (2 * p - R)];
@@ -211,14 +213,14 @@ __device__ __forceinline__ void conv_sep16_body(const RowSource &rs, uint8_t *__
                 nb[u][1] = load_row(7 + 2 * (g + PF));
             }
             W.slide(A, B);
-            emit(cf.ua_lo, cf.ua_hi, out);
-            if (INNER || ys + 2 * g + 1 < rs.h) emit(cf.ub_lo, cf.ub_hi, out + pitch);
+            emit(cf.ua_lo, cf.ua_hi, out, W.lo, 0x4443u);  // row y = byte 3 of W_lo
+            if (INNER || ys + 2 * g + 1 < rs.h) emit(cf.ub_lo, cf.ub_hi, out + pitch, W.hi, 0x4440u);  // row y+1 = byte 0 of W_hi
             out += 2 * pitch;
         }
     }
 }
 
-template <int K, int MODE, bool SIGNED, int RH, int MINB>
+template <int K, int MODE, bool SIGNED, bool CENTRE, int RH, int MINB>
 __global__ void __launch_bounds__(128, MINB) conv_sep16_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks,
                                                             const Sep16Coef<K> cf, const ConvRound rnd)
 {
@@ -229,9 +231,9 @@ __global__ void __launch_bounds__(128, MINB) conv_sep16_kernel(RowSource rs, uin
     const int ys = blockIdx.y * RH;
     const bool inner = ys >= 3 && ys + RH + 3 <= rs.h;  // window rows ys-3 .. ys+RH+2 all in the own band
     const bool edge = wg == 0 || wg * 30 + 30 >= (int)nchunks;
-    if (inner && !edge) conv_sep16_body<K, MODE, SIGNED, RH, true, false>(rs, dst, nchunks, chunk, ys, cf, rnd);
-    else if (inner) conv_sep16_body<K, MODE, SIGNED, RH, true, true>(rs, dst, nchunks, chunk, ys, cf, rnd);
-    else conv_sep16_body<K, MODE, SIGNED, RH, false, true>(rs, dst, nchunks, chunk, ys, cf, rnd);
+    if (inner && !edge) conv_sep16_body<K, MODE, SIGNED, CENTRE, RH, true, false>(rs, dst, nchunks, chunk, ys, cf, rnd);
+    else if (inner) conv_sep16_body<K, MODE, SIGNED, CENTRE, RH, true, true>(rs, dst, nchunks, chunk, ys, cf, rnd);
+    else conv_sep16_body<K, MODE, SIGNED, CENTRE, RH, false, true>(rs, dst, nchunks, chunk, ys, cf, rnd);
 }
 
 template <int K, int RH, int MINB>
@@ -240,27 +242,68 @@ static cudaError_t conv_sep16_launch(const RowSource &rs, uint8_t *dst, uint32_t
 {
     dim3 grid((nchunks + 119) / 120, (h + RH - 1) / RH);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
-#define PPMX_SEP16(MODE, SGN) launch(conv_sep16_kernel<K, MODE, SGN, RH, MINB>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd)
-    if (sgn) {
-        if (mode == 0) PPMX_SEP16(0, true);
-        else if (mode == 1) PPMX_SEP16(1, true);
-        else PPMX_SEP16(2, true);
+#define PPMX_SEP16(MODE, SGN, CEN) launch(conv_sep16_kernel<K, MODE, SGN, CEN, RH, MINB>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd)
+    if (cf.centre) {  // (always the signed form)
+        if (mode == 0) PPMX_SEP16(0, true, true);
+        else if (mode == 1) PPMX_SEP16(1, true, true);
+        else PPMX_SEP16(2, true, true);
+    } else if (sgn) {
+        if (mode == 0) PPMX_SEP16(0, true, false);
+        else if (mode == 1) PPMX_SEP16(1, true, false);
+        else PPMX_SEP16(2, true, false);
     } else {
-        if (mode == 4) PPMX_SEP16(4, false);
-        else if (mode == 0) PPMX_SEP16(0, false);
-        else if (mode == 1) PPMX_SEP16(1, false);
-        else PPMX_SEP16(2, false);
+        if (mode == 4) PPMX_SEP16(4, false, false);
+        else if (mode == 0) PPMX_SEP16(0, false, false);
+        else if (mode == 1) PPMX_SEP16(1, false, false);
+        else PPMX_SEP16(2, false, false);
     }
 #undef PPMX_SEP16
     return PPMX_LAUNCHED();
+}
+
+// coef = u v^T + delta at the centre element only (unsharp masks, "identity plus blur")?  The rank-1 part is fixed by any row and
+// column that avoid the centre.
+template <int K>
+static bool rank_one_centre(const int32_t *coef, int32_t (&u)[K], int32_t (&v)[K], int32_t *delta)
+{
+    constexpr int R = K / 2;
+    for (int r0 = 0; r0 < K; r0++) {
+        if (r0 == R) continue;
+        int c0 = -1;
+        for (int x = 0; x < K && c0 < 0; x++)
+            if (x != R && coef[r0 * K + x]) c0 = x;
+        if (c0 < 0) continue;
+        int64_t g = 0;
+        for (int x = 0; x < K; x++) {
+            int64_t a = coef[r0 * K + x] < 0 ? -(int64_t)coef[r0 * K + x] : coef[r0 * K + x], b = g;
+            while (b) { int64_t t = a % b; a = b; b = t; }
+            g = a;
+        }
+        for (int x = 0; x < K; x++) {
+            v[x] = (int32_t)(coef[r0 * K + x] / g);
+            if (v[x] < -128 || v[x] > 127) return false;
+        }
+        for (int y = 0; y < K; y++) {
+            if (coef[y * K + c0] % v[c0]) return false;
+            u[y] = coef[y * K + c0] / v[c0];
+        }
+        for (int y = 0; y < K; y++)
+            for (int x = 0; x < K; x++)
+                if (!(y == R && x == R) && (int64_t)u[y] * v[x] != coef[y * K + x]) return false;
+        const int64_t d = (int64_t)coef[R * K + R] - (int64_t)u[R] * v[R];
+        if (d < -(1ll << 24) || d > (1ll << 24)) return false;
+        *delta = (int32_t)d;
+        return true;
+    }
+    return false;
 }
 
 template <int K>
 static bool conv_sep16_k(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef, int32_t div, int32_t bias,
                          ConvRound rnd, int rh, cudaStream_t s, cudaError_t *err)
 {
-    int32_t u[K], v[K];
-    if (!rank_one<K>(coef, u, v)) return false;
+    int32_t u[K], v[K], centre = 0;
+    if (!rank_one<K>(coef, u, v) && !rank_one_centre<K>(coef, u, v, &centre)) return false;
     bool upos = true, uneg = true, vpos = true, vneg = true;
     int64_t su = 0, sabs = 0, sv = 0;
     for (int i = 0; i < K; i++) {
@@ -274,7 +317,7 @@ static bool conv_sep16_k(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t
     for (int i = 0; i < K; i++) su += u[i], sv += v[i];
     int mode = rnd.mode;
     bool sgn = true;
-    if (upos && vpos && 255 * su <= 65535) {
+    if (upos && vpos && 255 * su <= 65535 && !centre) {
         sgn = false;
         for (int i = 0; i < K; i++)
             if (u[i] > 255 || v[i] > 255) return false;
@@ -303,6 +346,7 @@ static bool conv_sep16_k(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t
     cf.v[0] = cf.v[1] = 0;
     for (int i = 0; i < K - 1; i++) cf.v[i >> 2] |= (uint32_t)(uint8_t)v[i] << (8 * (i & 3));
     cf.v_last = v[K - 1];
+    cf.centre = centre;
     const uint32_t nchunks = w * 3 / 16;
     // rows per strip / CTAs per SM (register budget).  7x7 binomial at 8192^2: 16/3 (168 registers) 0.574 of the HBM roofline,
     // 16/4 (128 registers, a few spills) 0.561, 32/4 0.549, 32/3 0.556, 64/4 0.51; the 32-bit kernel this replaces 0.457.

@@ -277,6 +277,10 @@ KERNELS["dense7_pos_pow2"] = (_rng7.randint(0, 6, (7, 7)), 128, 0)           # d
 KERNELS["dense5_div1"] = (_rng7.randint(-3, 4, (5, 5)), 1, 64)               # dense 5x5, div 1
 KERNELS["sep7_u16_edge"] = (np.outer([36, 36, 37, 37, 37, 37, 37], [1, 2, 3, 4, 3, 2, 1]), 4112, 0)  # rank 1, column sums up to 65535: the 16-bit limit
 KERNELS["sep7_u16_over"] = (np.outer([36, 37, 37, 37, 37, 37, 37], [1, 2, 3, 4, 3, 2, 1]), 4128, 0)  # one beyond it: the 32-bit rank-1 kernel
+_g7, _g5 = np.outer([1, 6, 15, 20, 15, 6, 1], [1, 6, 15, 20, 15, 6, 1]), np.outer([1, 4, 6, 4, 1], [1, 4, 6, 4, 1])
+KERNELS["unsharp7"] = (-_g7 + 2 * 4096 * (np.arange(49).reshape(7, 7) == 24), 4096, 0)      # rank 1 + centre: 2 I - G (7x7 sharpen)
+KERNELS["unsharp5_bias"] = (-3 * _g5 + 4 * 256 * (np.arange(25).reshape(5, 5) == 12), 256, -7)  # 4 I - 3 G, bias
+KERNELS["blurid5_div3"] = (_g5 + 77 * (np.arange(25).reshape(5, 5) == 12), 333, 0)            # G + 77 I, general divisor
 KERNELS["sep5_s16_edge"] = (np.outer([-25, 26, -26, 26, -25], [1, -2, 3, -2, 1]), 9, 128)             # signed rank 1, |column sums| up to 32640
 
 
@@ -317,6 +321,7 @@ def test_extension_conv_row_bands(gpu, orc):
                                    (64, 50, 5, [0, 7, 13, 50], "emboss5"), (37, 23, 3, [0, 10, 23], None),
                                    (301, 60, 3, [0, 13, 30, 31, 60], "edge3"), (1000, 21, 3, [0, 2, 9, 21], "blur3"),   # any-width strip kernel
                                    (2048, 70, 7, [0, 17, 40, 70], "dense7_mix"), (2048, 70, 5, [0, 35, 70], "sep5_s16_edge"),
+                                   (1024, 45, 7, [0, 16, 33, 45], "unsharp7"),
                                    (256, 40, 7, [0, 3, 6, 40], None),
                                    (128, 96, 5, [0, 32, 64, 96], "gauss5"), (256, 40, 7, [0, 3, 6, 40], "gauss7"),   # rank-1 kernel
                                    (64, 50, 5, [0, 7, 13, 50], "sep5_asym"), (128, 200, 3, [0, 67, 134, 200], "edge3"),
@@ -572,7 +577,8 @@ def test_extension_conv_vertical_word_kernels(gpu_tuning, orc):
     geometries of the tuning build (variants 15-18) and the older kernels (variant 14) give the same bytes."""
     gpu = gpu_tuning
     names = ("gauss7", "gauss5", "sep5_signed", "sep7_div3", "sep7_div1_neg", "sep7_u16_edge", "sep7_u16_over", "sep5_s16_edge",
-             "dense7_mix", "dense7_pos_pow2", "dense5_div1", "emboss5", "neg7_div64_bias", "box7_sat")
+             "dense7_mix", "dense7_pos_pow2", "dense5_div1", "emboss5", "neg7_div64_bias", "box7_sat", "unsharp7", "unsharp5_bias",
+             "blurid5_div3")
     imgs = [P.lcg(2048, 301, 21), P.const(496, 70, 255), P.all_patterns(1008, 37)["mixed"]]
     exp = {(i, k): orc.conv(img, *KERNELS[k]) for i, img in enumerate(imgs) for k in names}
     try:
