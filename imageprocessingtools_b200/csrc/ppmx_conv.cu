@@ -997,12 +997,12 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         if (k == 5 ? conv_sep<5>(rs, dst, w, h, coef, rnd, s, &e) : conv_sep<7>(rs, dst, w, h, coef, rnd, s, &e)) return e;
     }
     if (k == 3 && !s8 && rnd_ok && fast_layout && aligned16(dst) && PPMX_VARIANT != 7) {
-        // coefficients beyond a signed byte (up to +-16320): the strip kernel splits them into two dp4a chains
+        // coefficients beyond a signed byte (-16320 .. 16319 = 128 * (-127 .. 127) + (-64 .. 63)): the strip kernel splits them into two dp4a chains
         bool splittable = true;
-        for (int i = 0; i < 9; i++) splittable = splittable && coef[i] >= -16320 && coef[i] <= 16320;
+        for (int i = 0; i < 9; i++) splittable = splittable && coef[i] >= -16320 && coef[i] <= 16319;
         if (splittable) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s);
     }
-    if (s8 && (k == 5 || k == 7) && fast_layout && aligned16(dst) && rnd_ok && PPMX_VARIANT != 7 && PPMX_VARIANT != 14) {
+    if ((k == 5 || k == 7) && fast_layout && aligned16(dst) && rnd_ok && PPMX_VARIANT != 7 && PPMX_VARIANT != 14) {  // (coefficients -16320 .. 16319)
         // dense 5x5 / 7x7: two dp4a per tap column on the vertical words (ppmx_conv_sep.cu)
         cudaError_t e = cudaSuccess;
         if (conv_dense_strip(rs, dst, w, h, k, coef, rnd, strip_rh, s, &e)) return e;
@@ -1017,7 +1017,7 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
     if (k == 3 && rnd_ok && !fast_layout && w >= 16 && (size_t)w * h >= 4096 && (PPMX_VARIANT == 0 || (PPMX_VARIANT >= 20 && PPMX_VARIANT <= 22))) {
         // 3x3 at any width / alignment (whole rasters and row bands alike): the strip kernel's unaligned form
         bool ok16 = true;
-        for (int i = 0; i < 9; i++) ok16 = ok16 && coef[i] >= -16320 && coef[i] <= 16320;
+        for (int i = 0; i < 9; i++) ok16 = ok16 && coef[i] >= -16320 && coef[i] <= 16319;
         if (ok16) return conv3_strip(rs, dst, w, h, coef, rnd, div, bias, s, true);
     }
     // a whole raster that only lacks the layout for the vector kernels goes through a padded copy (variant 1 = never)

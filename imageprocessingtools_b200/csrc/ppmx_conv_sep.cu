@@ -379,9 +379,10 @@ struct DenseCoef {
     uint32_t a_lo[K], a_hi[K], b_lo[K], b_hi[K];  // per tap column: the coefficient column in the window's bytes (upper / lower row)
 };
 
-template <int K, int MODE, int RH, bool INNER, bool EDGE>
+// WIDE: coefficients beyond a signed byte (-16320 .. 16319) are split c = 128 * hi + lo: a second chain of dot products, weighted 128
+template <int K, int MODE, bool WIDE, int RH, bool INNER, bool EDGE>
 __device__ __forceinline__ void conv_dense_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, int chunk, int ys,
-                                                const DenseCoef<K> &cf, const ConvRound &rnd)
+                                                const DenseCoef<K> &cf, const DenseCoef<K> &cfh, const ConvRound &rnd)
 {
     constexpr int R = K / 2, H = 3 * R, PF = 2;
     static_assert(RH % (2 * PF) == 0, "strip height");
@@ -455,14 +456,18 @@ __device__ __forceinline__ void conv_dense_body(const RowSource &rs, uint8_t *__
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int c = 4 * b + j;
-                        int32_t t = rnd.start;
+                        int32_t t = rnd.start, th = 0;
 #pragma unroll
                         for (int k = 0; k < K; k++) {
                             const int cc = c + 3 * (k - R);
                             t = vdot4<true>(XL(cc), half ? cf.b_lo[k] : cf.a_lo[k], t);
                             t = vdot4<true>(XH(cc), half ? cf.b_hi[k] : cf.a_hi[k], t);
+                            if (WIDE) {
+                                th = vdot4<true>(XL(cc), half ? cfh.b_lo[k] : cfh.a_lo[k], th);
+                                th = vdot4<true>(XH(cc), half ? cfh.b_hi[k] : cfh.a_hi[k], th);
+                            }
                         }
-                        a[j] = t;
+                        a[j] = WIDE ? t + (th << 7) : t;
                     }
                     ov[b] = rnd.template pack4<MODE>(a[0], a[1], a[2], a[3]);
                 }
@@ -473,9 +478,9 @@ __device__ __forceinline__ void conv_dense_body(const RowSource &rs, uint8_t *__
     }
 }
 
-template <int K, int MODE, int RH>
+template <int K, int MODE, bool WIDE, int RH>
 __global__ void __launch_bounds__(128, 3) conv_dense_strip_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks,
-                                                                  const DenseCoef<K> cf, const ConvRound rnd)
+                                                                  const DenseCoef<K> cf, const DenseCoef<K> cfh, const ConvRound rnd)
 {
     pdl_trigger();
     const int wg = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -484,20 +489,26 @@ __global__ void __launch_bounds__(128, 3) conv_dense_strip_kernel(RowSource rs, 
     const int ys = blockIdx.y * RH;
     const bool inner = ys >= 3 && ys + RH + 3 <= rs.h;
     const bool edge = wg == 0 || wg * 30 + 30 >= (int)nchunks;
-    if (inner && !edge) conv_dense_body<K, MODE, RH, true, false>(rs, dst, nchunks, chunk, ys, cf, rnd);
-    else if (inner) conv_dense_body<K, MODE, RH, true, true>(rs, dst, nchunks, chunk, ys, cf, rnd);
-    else conv_dense_body<K, MODE, RH, false, true>(rs, dst, nchunks, chunk, ys, cf, rnd);
+    if (inner && !edge) conv_dense_body<K, MODE, WIDE, RH, true, false>(rs, dst, nchunks, chunk, ys, cf, cfh, rnd);
+    else if (inner) conv_dense_body<K, MODE, WIDE, RH, true, true>(rs, dst, nchunks, chunk, ys, cf, cfh, rnd);
+    else conv_dense_body<K, MODE, WIDE, RH, false, true>(rs, dst, nchunks, chunk, ys, cf, cfh, rnd);
 }
 
 template <int K, int RH>
 static cudaError_t conv_dense_launch(const RowSource &rs, uint8_t *dst, uint32_t nchunks, uint32_t h, const DenseCoef<K> &cf,
-                                     const ConvRound &rnd, cudaStream_t s)
+                                     const DenseCoef<K> &cfh, bool wide, const ConvRound &rnd, cudaStream_t s)
 {
     dim3 grid((nchunks + 119) / 120, (h + RH - 1) / RH);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
-    if (rnd.mode == 0) launch(conv_dense_strip_kernel<K, 0, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd);
-    else if (rnd.mode == 1) launch(conv_dense_strip_kernel<K, 1, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd);
-    else launch(conv_dense_strip_kernel<K, 2, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd);
+#define PPMX_DENSE(MODE)                                                                                                   \
+    do {                                                                                                                   \
+        if (wide) launch(conv_dense_strip_kernel<K, MODE, true, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, cfh, rnd);    \
+        else launch(conv_dense_strip_kernel<K, MODE, false, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, cfh, rnd);        \
+    } while (0)
+    if (rnd.mode == 0) PPMX_DENSE(0);
+    else if (rnd.mode == 1) PPMX_DENSE(1);
+    else PPMX_DENSE(2);
+#undef PPMX_DENSE
     return PPMX_LAUNCHED();
 }
 
@@ -505,22 +516,30 @@ template <int K>
 static bool conv_dense_k(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, const int32_t *coef, const ConvRound &rnd, int rh,
                          cudaStream_t s, cudaError_t *err)
 {
-    DenseCoef<K> cf;
+    DenseCoef<K> cf, cfh;
+    bool wide = false;
     for (int k = 0; k < K; k++) {
-        int32_t col[K];
-        for (int i = 0; i < K; i++) {
-            col[i] = coef[i * K + k];
-            if (col[i] < -128 || col[i] > 127) return false;
+        int32_t lo[K], hi[K];
+        for (int i = 0; i < K; i++) {  // c = 128 * hi + lo with lo in -64..63; hi == 0 for every byte-sized coefficient
+            const int32_t v = coef[i * K + k];
+            if (v < -16320 || v > 16319) return false;  // (16320 would need hi = 128)
+            lo[i] = v, hi[i] = 0;
+            if (v < -128 || v > 127) {
+                lo[i] = ((v + 64) & 127) - 64;
+                hi[i] = (v - lo[i]) / 128;
+                wide = true;
+            }
         }
-        window_coef<K>(col, cf.a_lo[k], cf.a_hi[k], cf.b_lo[k], cf.b_hi[k]);
+        window_coef<K>(lo, cf.a_lo[k], cf.a_hi[k], cf.b_lo[k], cf.b_hi[k]);
+        window_coef<K>(hi, cfh.a_lo[k], cfh.a_hi[k], cfh.b_lo[k], cfh.b_hi[k]);
     }
     const uint32_t nchunks = w * 3 / 16;
 #ifdef PPMX_TUNING
-    if (rh == 2 || rh == 3) *err = conv_dense_launch<K, 32>(rs, dst, nchunks, h, cf, rnd, s);
-    else if (rh == 4) *err = conv_dense_launch<K, 64>(rs, dst, nchunks, h, cf, rnd, s);
+    if (rh == 2 || rh == 3) *err = conv_dense_launch<K, 32>(rs, dst, nchunks, h, cf, cfh, wide, rnd, s);
+    else if (rh == 4) *err = conv_dense_launch<K, 64>(rs, dst, nchunks, h, cf, cfh, wide, rnd, s);
     else
 #endif
-    *err = conv_dense_launch<K, 16>(rs, dst, nchunks, h, cf, rnd, s);
+    *err = conv_dense_launch<K, 16>(rs, dst, nchunks, h, cf, cfh, wide, rnd, s);
     return true;
 }
 

@@ -261,6 +261,8 @@ KERNELS["sep7_div3"] = (np.outer([1, 1, 2, 3, 2, 1, 1], [1, 2, 3, 4, 3, 2, 1]), 
 KERNELS["sep7_div1_neg"] = (np.outer([0, -1, 2, -3, 2, -1, 0], [1, 0, -2, 3, -2, 0, 1]), 1, 100)    # rank 1, zeros and signs, div 1
 KERNELS["gauss5"] = (np.outer([1, 4, 6, 4, 1], [1, 4, 6, 4, 1]), 256, 0)
 KERNELS["wide3"] = (np.array([[-300, 200, 129], [-129, 5000, -128], [127, 128, -16320]]), 997, 40)   # 3x3 beyond int8: split dp4a chains
+KERNELS["wide3_limits"] = (np.array([[16319, -16320, 0], [0, 16320, 1], [-64, 63, 128]]), 30011, 0)  # the split's limits; 16320 is one beyond (generic kernel)
+KERNELS["wide3_max"] = (np.array([[16319, -16320, 16319], [-16320, 16319, -16320], [64, -65, 0]]), 8192, 1)
 KERNELS["wide3_pow2"] = (np.array([[256, 512, 256], [512, 1024, 512], [256, 512, 256]]), 4096, 0)
 KERNELS["box9"] = (np.ones((9, 9), np.int64), 81, 0)
 KERNELS["box11"] = (np.ones((11, 11), np.int64), 121, 0)
@@ -281,6 +283,10 @@ _g7, _g5 = np.outer([1, 6, 15, 20, 15, 6, 1], [1, 6, 15, 20, 15, 6, 1]), np.oute
 KERNELS["unsharp7"] = (-_g7 + 2 * 4096 * (np.arange(49).reshape(7, 7) == 24), 4096, 0)      # rank 1 + centre: 2 I - G (7x7 sharpen)
 KERNELS["unsharp5_bias"] = (-3 * _g5 + 4 * 256 * (np.arange(25).reshape(5, 5) == 12), 256, -7)  # 4 I - 3 G, bias
 KERNELS["blurid5_div3"] = (_g5 + 77 * (np.arange(25).reshape(5, 5) == 12), 333, 0)            # G + 77 I, general divisor
+_d7w = _rng7.randint(-300, 301, (7, 7)) * (np.arange(49).reshape(7, 7) % 5 != 0)
+_d7w[3, 3], _d7w[0, 6] = 16319, -16320                                    # the limits of the split (16320 would need hi = 128)
+KERNELS["dense7_wide"] = (_d7w, 9973, 3)                                   # dense 7x7 beyond int8: two chains of dot products
+KERNELS["dense5_wide"] = (_rng7.randint(-2000, 2001, (5, 5)), 4096, 0)   # dense 5x5, every coefficient split
 KERNELS["sep5_s16_edge"] = (np.outer([-25, 26, -26, 26, -25], [1, -2, 3, -2, 1]), 9, 128)             # signed rank 1, |column sums| up to 32640
 
 
@@ -578,7 +584,7 @@ def test_extension_conv_vertical_word_kernels(gpu_tuning, orc):
     gpu = gpu_tuning
     names = ("gauss7", "gauss5", "sep5_signed", "sep7_div3", "sep7_div1_neg", "sep7_u16_edge", "sep7_u16_over", "sep5_s16_edge",
              "dense7_mix", "dense7_pos_pow2", "dense5_div1", "emboss5", "neg7_div64_bias", "box7_sat", "unsharp7", "unsharp5_bias",
-             "blurid5_div3")
+             "blurid5_div3", "dense7_wide", "dense5_wide")
     imgs = [P.lcg(2048, 301, 21), P.const(496, 70, 255), P.all_patterns(1008, 37)["mixed"]]
     exp = {(i, k): orc.conv(img, *KERNELS[k]) for i, img in enumerate(imgs) for k in names}
     try:
