@@ -50,7 +50,7 @@ def _run(cmd, verbose):
 def build_all(force: bool = False, verbose: bool = False) -> None:
     hdrs = [os.path.join(PKG, "..", "include", "ppmx_gpu.h"), os.path.join(PKG, "..", "include", "ppmx_host.h"),
             os.path.join(CSRC, "ppmx_kernels.h"), os.path.join(CSRC, "ppmx_common.cuh"), os.path.join(CSRC, "ppmx_ctx.h"), os.path.join(CSRC, "ppmx_conv.cuh")]
-    cu = [os.path.join(CSRC, f) for f in ("ppmx_color.cu", "ppmx_geometry.cu", "ppmx_bicubic.cu", "ppmx_conv.cu", "ppmx_conv_sep.cu", "ppmx_conv_ua.cu",
+    cu = [os.path.join(CSRC, f) for f in ("ppmx_color.cu", "ppmx_geometry.cu", "ppmx_bicubic.cu", "ppmx_conv.cu", "ppmx_conv_sep.cu", "ppmx_conv_ua.cu", "ppmx_conv_vw.cu",
                                           "ppmx_fused.cu", "ppmx_gpu.cu", "ppmx_chain.cu")]
     cu = [f for f in cu if os.path.exists(f)]
     # the release library, and the same sources with -DPPMX_TUNING (alternative kernel variants behind

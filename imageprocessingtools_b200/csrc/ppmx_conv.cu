@@ -1014,6 +1014,11 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         if (k == 5) return conv_fast<5>(rs, dst, w, h, coef, rnd, s);
         return conv_fast<7>(rs, dst, w, h, coef, rnd, s);
     }
+    if (s8 && k >= 9 && fast_layout && aligned16(dst) && rnd_ok && PPMX_VARIANT != 7 && PPMX_VARIANT != 14) {
+        // dense 9x9 .. 15x15: vertical words in shared memory (ppmx_conv_vw.cu); it was the scalar kernel
+        cudaError_t e = cudaSuccess;
+        if (conv_vw(rs, dst, w, h, k, coef, rnd, s, &e)) return e;
+    }
     if (k == 3 && rnd_ok && !fast_layout && w >= 16 && (size_t)w * h >= 4096 && (PPMX_VARIANT == 0 || (PPMX_VARIANT >= 20 && PPMX_VARIANT <= 22))) {
         // 3x3 at any width / alignment (whole rasters and row bands alike): the strip kernel's unaligned form
         bool ok16 = true;
@@ -1023,7 +1028,7 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
     // a whole raster that only lacks the layout for the vector kernels goes through a padded copy (variant 1 = never)
     const bool layout_only = ((w % 16u) != 0 || !aligned16(src) || !aligned16(dst)) && !band.full_h && PPMX_VARIANT != 1 &&
                              PPMX_VARIANT != 7 && w >= 16 && (size_t)w * h >= 4096 &&
-                             (k <= 7 || (k <= 11 && box_constants(coef, k, div, bias, &bm, &bc)));  // a vector kernel exists
+                             (k <= 7 || s8 || (k <= 11 && box_constants(coef, k, div, bias, &bm, &bc)));  // a vector kernel exists
     if (layout_only) return conv_padded(src, dst, w, h, k, coef, div, bias, s);
     ConvCoefGeneric cf;
     for (int i = 0; i < CONV_MAXK * CONV_MAXK; i++) cf.c[i] = i < k * k ? coef[i] : 0;

@@ -126,4 +126,8 @@ bool conv_sep16(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, int k
 bool conv_dense_strip(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef, const ConvRound &rnd,
                       int rh, cudaStream_t s, cudaError_t *err);
 
+// ppmx_conv_vw.cu: dense k x k for k = 9, 11, 13, 15 with signed-byte coefficients, vertical words in shared memory
+bool conv_vw(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef, const ConvRound &rnd, cudaStream_t s,
+             cudaError_t *err);
+
 }  // namespace ppmx

@@ -287,6 +287,11 @@ _d7w = _rng7.randint(-300, 301, (7, 7)) * (np.arange(49).reshape(7, 7) % 5 != 0)
 _d7w[3, 3], _d7w[0, 6] = 16319, -16320                                    # the limits of the split (16320 would need hi = 128)
 KERNELS["dense7_wide"] = (_d7w, 9973, 3)                                   # dense 7x7 beyond int8: two chains of dot products
 KERNELS["dense5_wide"] = (_rng7.randint(-2000, 2001, (5, 5)), 4096, 0)   # dense 5x5, every coefficient split
+_rng9 = np.random.RandomState(9)
+KERNELS["gauss9"] = (np.outer([1, 8, 28, 56, 70, 56, 28, 8, 1], [1, 8, 28, 56, 70, 56, 28, 8, 1]) // 64, 1044, 0)  # 9x9 blur (dense after the floor)
+KERNELS["dense11_mix"] = (_rng9.randint(-128, 128, (11, 11)), 977, -2)
+KERNELS["dense13_pow2"] = (_rng9.randint(-3, 9, (13, 13)), 512, 0)
+KERNELS["dense15_div1"] = (_rng9.randint(-2, 3, (15, 15)) * (_rng9.randint(0, 4, (15, 15)) == 0), 1, 90)
 KERNELS["sep5_s16_edge"] = (np.outer([-25, 26, -26, 26, -25], [1, -2, 3, -2, 1]), 9, 128)             # signed rank 1, |column sums| up to 32640
 
 
@@ -327,7 +332,8 @@ def test_extension_conv_row_bands(gpu, orc):
                                    (64, 50, 5, [0, 7, 13, 50], "emboss5"), (37, 23, 3, [0, 10, 23], None),
                                    (301, 60, 3, [0, 13, 30, 31, 60], "edge3"), (1000, 21, 3, [0, 2, 9, 21], "blur3"),   # any-width strip kernel
                                    (2048, 70, 7, [0, 17, 40, 70], "dense7_mix"), (2048, 70, 5, [0, 35, 70], "sep5_s16_edge"),
-                                   (1024, 45, 7, [0, 16, 33, 45], "unsharp7"),
+                                   (1024, 45, 7, [0, 16, 33, 45], "unsharp7"), (512, 90, 9, [0, 30, 61, 90], "gauss9"),
+                                   (256, 64, 15, [0, 7, 40, 64], "dense15_div1"),
                                    (256, 40, 7, [0, 3, 6, 40], None),
                                    (128, 96, 5, [0, 32, 64, 96], "gauss5"), (256, 40, 7, [0, 3, 6, 40], "gauss7"),   # rank-1 kernel
                                    (64, 50, 5, [0, 7, 13, 50], "sep5_asym"), (128, 200, 3, [0, 67, 134, 200], "edge3"),
@@ -584,7 +590,7 @@ def test_extension_conv_vertical_word_kernels(gpu_tuning, orc):
     gpu = gpu_tuning
     names = ("gauss7", "gauss5", "sep5_signed", "sep7_div3", "sep7_div1_neg", "sep7_u16_edge", "sep7_u16_over", "sep5_s16_edge",
              "dense7_mix", "dense7_pos_pow2", "dense5_div1", "emboss5", "neg7_div64_bias", "box7_sat", "unsharp7", "unsharp5_bias",
-             "blurid5_div3", "dense7_wide", "dense5_wide")
+             "blurid5_div3", "dense7_wide", "dense5_wide", "gauss9", "dense11_mix", "dense13_pow2", "dense15_div1")
     imgs = [P.lcg(2048, 301, 21), P.const(496, 70, 255), P.all_patterns(1008, 37)["mixed"]]
     exp = {(i, k): orc.conv(img, *KERNELS[k]) for i, img in enumerate(imgs) for k in names}
     try:
