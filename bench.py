@@ -79,6 +79,7 @@ WORKLOADS = {
     "gauss5": (8192, 8192, 2, 6.0, "8192x8192 5x5 binomial blur (1 4 6 4 1)^2 / 256 (extension), 2 rasters per step"),
     "dense5": (8192, 8192, 2, 6.0, "8192x8192 dense (rank > 1) 5x5 kernel (extension), 2 rasters per step"),
     "dense7": (8192, 8192, 2, 6.0, "8192x8192 dense (rank > 1) 7x7 kernel (extension), 2 rasters per step"),
+    "gauss9": (8192, 8192, 2, 6.0, "8192x8192 9x9 binomial blur (1 8 28 56 70 56 28 8 1)^2 / 65536 (extension), 2 rasters per step"),
     "dense9": (8192, 8192, 2, 6.0, "8192x8192 dense 9x9 kernel (floored binomial blur, extension), 2 rasters per step"),
     "sharpen7": (8192, 8192, 2, 6.0, "8192x8192 7x7 sharpen = unsharp mask 2 I - binomial 7x7 (extension, config 3), 2 rasters per step"),
     "sharpen3": (8192, 8192, 2, 6.0, "8192x8192 3x3 sharpen (0 -1 0; -1 5 -1; 0 -1 0) (extension, config 3), 2 rasters per step"),
@@ -90,7 +91,7 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "conv3_bands"
 PER_OP = ["gray", "gray_hist", "gray_hist_const", "mono", "fliph", "flipv", "rot90", "rot180", "rot90_1080p", "gray_16k",
           "mono_16k", "fliph_16k", "rot90_16k", "levels", "conv3", "conv7", "sharpen3", "edge3", "gauss5", "gauss7", "sharpen7", "dense5",
-          "dense7", "dense9", "gray_4090", "mono_4090", "fliph_4090", "flipv_4090", "rot90_4090", "rot180_4090", "conv3_odd",
+          "dense7", "gauss9", "dense9", "gray_4090", "mono_4090", "fliph_4090", "flipv_4090", "rot90_4090", "rot180_4090", "conv3_odd",
           "resize_up", "resize_down", "rot30"]
 
 
@@ -308,6 +309,8 @@ def conv_spec(name):
         return np.outer([1, 6, 15, 20, 15, 6, 1], [1, 6, 15, 20, 15, 6, 1]).astype(np.int32), 4096
     if name == "gauss5":
         return np.outer([1, 4, 6, 4, 1], [1, 4, 6, 4, 1]).astype(np.int32), 256
+    if name == "gauss9":
+        return np.outer([1, 8, 28, 56, 70, 56, 28, 8, 1], [1, 8, 28, 56, 70, 56, 28, 8, 1]).astype(np.int32), 65536
     if name == "dense9":  # a 9x9 blur whose integer coefficients are floored: not rank 1 any more
         c = (np.outer([1, 8, 28, 56, 70, 56, 28, 8, 1], [1, 8, 28, 56, 70, 56, 28, 8, 1]) // 64).astype(np.int32)
         return c, int(c.sum())
@@ -617,7 +620,7 @@ class OpRunner:
             self.ops = [(op, op.new_width, op.new_height, op.new_width * op.new_height * 3)]
         elif name == "levels":
             self.ops = [(g.levels_op(g.levels_lut_linear(16, 235)), w, h, w * h * 3)]
-        elif name in ("conv3", "conv7", "sharpen3", "edge3", "gauss5", "gauss7", "sharpen7", "conv3_odd", "dense5", "dense7", "dense9"):
+        elif name in ("conv3", "conv7", "sharpen3", "edge3", "gauss5", "gauss7", "sharpen7", "conv3_odd", "dense5", "dense7", "dense9", "gauss9"):
             coef, div = conv_spec(name)
             self.ops = [(g.conv_op(coef, div, 0), w, h, w * h * 3)]
         elif name in ("resize_up", "resize_down"):

@@ -915,7 +915,7 @@ static cudaError_t conv_fast(const RowSource &rs, uint8_t *dst, uint32_t w, uint
 // columns are copied out again: two extra passes through the copy engine's 2-D path.
 // The rows themselves move by cudaMemcpy2DAsync (device to device, any pitch); this kernel only fills the
 // wp - w mirrored pixels at the end of every padded row.
-__global__ void __launch_bounds__(64) conv_pad_edge_kernel(uint8_t *__restrict__ padded, uint32_t w, uint32_t wp)
+__global__ void __launch_bounds__(96) conv_pad_edge_kernel(uint8_t *__restrict__ padded, uint32_t w, uint32_t wp)
 {
     PDL_PROLOGUE();
     const uint32_t t = threadIdx.x, y = blockIdx.x;  // byte t of the mirrored tail of padded row y
@@ -941,10 +941,10 @@ static cudaError_t conv_padded(const uint8_t *src, uint8_t *dst, uint32_t w, uin
         cudaFreeAsync(tin, s);
         return e;
     }
-    // (wp - w <= k/2 + 15 <= 20 pixels = 60 bytes: one 64-thread CTA per row)
+    // (one 96-thread CTA per row)
     if (e == cudaSuccess) e = geom_repitch(src, tin, w, h, w * 3u, wp * 3u, s);  // (the copy engine's 2-D path is several times slower)
     if (e == cudaSuccess) {
-        launch(conv_pad_edge_kernel, dim3(h), dim3(64), 0, s, tin, w, wp);
+        launch(conv_pad_edge_kernel, dim3(h), dim3(96), 0, s, tin, w, wp);  // (wp - w <= k/2 + 15 <= 22 pixels = 66 bytes)
         e = PPMX_LAUNCHED();
     }
     if (e == cudaSuccess) e = conv(tin, tout, wp, h, k, coef, div, bias, Band(), s);
@@ -1014,6 +1014,11 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         if (k == 5) return conv_fast<5>(rs, dst, w, h, coef, rnd, s);
         return conv_fast<7>(rs, dst, w, h, coef, rnd, s);
     }
+    if (k >= 9 && fast_layout && aligned16(dst) && rnd_ok && PPMX_VARIANT != 7 && PPMX_VARIANT != 14 && PPMX_VARIANT != 2) {
+        // rank-1 9x9 .. 15x15 blurs: column sums in shared memory, dp2a along the row (ppmx_conv_vw.cu)
+        cudaError_t e = cudaSuccess;
+        if (conv_vwsep(rs, dst, w, h, k, coef, div, bias, rnd, s, &e)) return e;
+    }
     if (s8 && k >= 9 && fast_layout && aligned16(dst) && rnd_ok && PPMX_VARIANT != 7 && PPMX_VARIANT != 14) {
         // dense 9x9 .. 15x15: vertical words in shared memory (ppmx_conv_vw.cu); it was the scalar kernel
         cudaError_t e = cudaSuccess;
@@ -1028,7 +1033,7 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
     // a whole raster that only lacks the layout for the vector kernels goes through a padded copy (variant 1 = never)
     const bool layout_only = ((w % 16u) != 0 || !aligned16(src) || !aligned16(dst)) && !band.full_h && PPMX_VARIANT != 1 &&
                              PPMX_VARIANT != 7 && w >= 16 && (size_t)w * h >= 4096 &&
-                             (k <= 7 || s8 || (k <= 11 && box_constants(coef, k, div, bias, &bm, &bc)));  // a vector kernel exists
+                             (k <= 7 || s8 || k >= 9);  // a vector kernel may exist (the padded call falls through to the scalar kernel if not)
     if (layout_only) return conv_padded(src, dst, w, h, k, coef, div, bias, s);
     ConvCoefGeneric cf;
     for (int i = 0; i < CONV_MAXK * CONV_MAXK; i++) cf.c[i] = i < k * k ? coef[i] : 0;

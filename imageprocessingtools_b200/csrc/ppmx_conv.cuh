@@ -127,6 +127,9 @@ bool conv_dense_strip(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h,
                       int rh, cudaStream_t s, cudaError_t *err);
 
 // ppmx_conv_vw.cu: dense k x k for k = 9, 11, 13, 15 with signed-byte coefficients, vertical words in shared memory
+// ... and rank-1 non-negative kernels of those sizes whose column sums fit 16 bits (Gaussian / binomial blurs)
+bool conv_vwsep(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef, int32_t div, int32_t bias,
+                const ConvRound &rnd, cudaStream_t s, cudaError_t *err);
 bool conv_vw(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t h, int k, const int32_t *coef, const ConvRound &rnd, cudaStream_t s,
              cudaError_t *err);
 

@@ -292,6 +292,12 @@ KERNELS["gauss9"] = (np.outer([1, 8, 28, 56, 70, 56, 28, 8, 1], [1, 8, 28, 56, 7
 KERNELS["dense11_mix"] = (_rng9.randint(-128, 128, (11, 11)), 977, -2)
 KERNELS["dense13_pow2"] = (_rng9.randint(-3, 9, (13, 13)), 512, 0)
 KERNELS["dense15_div1"] = (_rng9.randint(-2, 3, (15, 15)) * (_rng9.randint(0, 4, (15, 15)) == 0), 1, 90)
+_b9 = [1, 8, 28, 56, 70, 56, 28, 8, 1]
+KERNELS["binom9"] = (np.outer(_b9, _b9), 65536, 0)                                  # rank-1 9x9: 16-bit column sums, byte-2 quotient
+KERNELS["gauss11_div"] = (np.outer([1, 2, 4, 7, 10, 11, 10, 7, 4, 2, 1], [1, 3, 6, 10, 14, 16, 14, 10, 6, 3, 1]), 4957, 1)  # rank-1 11x11, general divisor
+KERNELS["gauss13_asym"] = (np.outer([1, 1, 2, 3, 5, 8, 13, 8, 5, 3, 2, 1, 1], [0, 1, 2, 4, 8, 16, 32, 16, 8, 4, 2, 1, 0]), 4096, 0)
+KERNELS["sep15_sat"] = (np.outer([1] * 15, [17] * 15), 2000, 0)                     # box would apply only up to 11; rank-1, saturates
+KERNELS["binom11"] = (np.outer([1, 10, 45, 120, 210, 252, 210, 120, 45, 10, 1], [1, 10, 45, 120, 210, 252, 210, 120, 45, 10, 1]), 1 << 20, 0)  # column sums beyond 16 bits: not that kernel
 KERNELS["sep5_s16_edge"] = (np.outer([-25, 26, -26, 26, -25], [1, -2, 3, -2, 1]), 9, 128)             # signed rank 1, |column sums| up to 32640
 
 
@@ -323,6 +329,16 @@ def test_extension_conv3_any_width(gpu_tuning, orc):
         gpu.set_tuning("variant", 0)
 
 
+def test_extension_conv_large_k_odd_widths(gpu, orc):
+    """9x9 .. 15x15 at widths that are no multiple of 16: the padded copy (up to 22 mirrored pixels behind every row) in front of
+    the shared-memory vertical-word kernels."""
+    for (w, h) in [(130, 70), (301, 41), (1000, 33), (77, 60)]:
+        img = P.lcg(w, h, 4000 + w)
+        for kname in ("binom9", "gauss11_div", "gauss13_asym", "dense15_div1", "dense11_mix", "sep15_sat", "box11"):
+            coef, div, bias = KERNELS[kname]
+            assert np.array_equal(gpu.conv(img, coef, div, bias), orc.conv(img, coef, div, bias)), (w, h, kname)
+
+
 def test_extension_conv_row_bands(gpu, orc):
     """A raster cut into row bands, each convolved separately with halo rows read through the band
     pointers (here: the neighbour band in the same HBM), equals the whole-raster result."""
@@ -333,7 +349,8 @@ def test_extension_conv_row_bands(gpu, orc):
                                    (301, 60, 3, [0, 13, 30, 31, 60], "edge3"), (1000, 21, 3, [0, 2, 9, 21], "blur3"),   # any-width strip kernel
                                    (2048, 70, 7, [0, 17, 40, 70], "dense7_mix"), (2048, 70, 5, [0, 35, 70], "sep5_s16_edge"),
                                    (1024, 45, 7, [0, 16, 33, 45], "unsharp7"), (512, 90, 9, [0, 30, 61, 90], "gauss9"),
-                                   (256, 64, 15, [0, 7, 40, 64], "dense15_div1"),
+                                   (256, 64, 15, [0, 7, 40, 64], "dense15_div1"), (512, 90, 9, [0, 30, 61, 90], "binom9"),
+                                   (256, 64, 13, [0, 6, 40, 64], "gauss13_asym"),
                                    (256, 40, 7, [0, 3, 6, 40], None),
                                    (128, 96, 5, [0, 32, 64, 96], "gauss5"), (256, 40, 7, [0, 3, 6, 40], "gauss7"),   # rank-1 kernel
                                    (64, 50, 5, [0, 7, 13, 50], "sep5_asym"), (128, 200, 3, [0, 67, 134, 200], "edge3"),
@@ -590,7 +607,8 @@ def test_extension_conv_vertical_word_kernels(gpu_tuning, orc):
     gpu = gpu_tuning
     names = ("gauss7", "gauss5", "sep5_signed", "sep7_div3", "sep7_div1_neg", "sep7_u16_edge", "sep7_u16_over", "sep5_s16_edge",
              "dense7_mix", "dense7_pos_pow2", "dense5_div1", "emboss5", "neg7_div64_bias", "box7_sat", "unsharp7", "unsharp5_bias",
-             "blurid5_div3", "dense7_wide", "dense5_wide", "gauss9", "dense11_mix", "dense13_pow2", "dense15_div1")
+             "blurid5_div3", "dense7_wide", "dense5_wide", "gauss9", "dense11_mix", "dense13_pow2", "dense15_div1", "binom9", "gauss11_div", "gauss13_asym",
+             "sep15_sat", "binom11")
     imgs = [P.lcg(2048, 301, 21), P.const(496, 70, 255), P.all_patterns(1008, 37)["mixed"]]
     exp = {(i, k): orc.conv(img, *KERNELS[k]) for i, img in enumerate(imgs) for k in names}
     try:
