@@ -339,6 +339,73 @@ def test_extension_conv_large_k_odd_widths(gpu, orc):
             assert np.array_equal(gpu.conv(img, coef, div, bias), orc.conv(img, coef, div, bias)), (w, h, kname)
 
 
+def test_extension_conv_fuzz(gpu, orc):
+    """Seeded random sweep over the convolution dispatch: every kernel size 3..15, widths with and without the 16-byte layout,
+    coefficient classes that select each vector kernel (box, rank-1 unsigned / signed / with a centre term, dense within and beyond a
+    signed byte, sparse, oversized: the scalar kernel), divisors 1 / power of two / normalising / arbitrary, biases; the whole
+    raster against the self-oracle, and for a third of the cases cut into row bands with halo rows."""
+    import torch
+    import imageprocessingtools_b200.ppmx as pp
+    rng = np.random.RandomState(20261018)
+    dev = torch.device("cuda", 0)
+
+    def coefs(k, cls):
+        if cls == "box":
+            return np.full((k, k), rng.randint(1, 4), np.int64)
+        if cls in ("r1u", "r1s", "r1c"):
+            lo = 0 if cls == "r1u" else -6
+            u, v = rng.randint(lo, 12, k), rng.randint(lo, 12, k)
+            u[k // 2] += 1
+            v[k // 2] += 1
+            c = np.outer(u, v).astype(np.int64)
+            if cls == "r1c":
+                c[k // 2, k // 2] += rng.randint(-3000, 9000)
+            return c
+        if cls == "dense":
+            return rng.randint(-128, 128, (k, k)).astype(np.int64)
+        if cls == "wide":
+            return rng.randint(-16320, 16320, (k, k)).astype(np.int64)
+        if cls == "sparse":
+            return (rng.randint(-9, 10, (k, k)) * (rng.randint(0, 5, (k, k)) == 0)).astype(np.int64)
+        return rng.randint(-40000, 40000, (k, k)).astype(np.int64)  # "huge"
+
+    n = 0
+    for it in range(260):
+        k = int(rng.choice([3, 3, 5, 5, 7, 7, 9, 11, 13, 15]))
+        cls = str(rng.choice(["box", "r1u", "r1u", "r1s", "r1c", "dense", "dense", "wide", "sparse", "huge"]))
+        w = int(rng.randint(1, 45)) * 16 if rng.randint(0, 3) else int(rng.randint(16, 700))
+        h = int(rng.randint(1, 90))
+        coef = coefs(k, cls)
+        tot = int(coef.sum())
+        div = int(rng.choice([1, 2 ** int(rng.randint(1, 13)), max(1, abs(tot)), int(rng.randint(1, 5000))]))
+        bias = int(rng.choice([0, 0, rng.randint(-40, 200)]))
+        if 255 * int(np.abs(coef).sum()) >= 2 ** 30:
+            continue
+        img = P.lcg(w, h, 7000 + it)
+        exp = orc.conv(img, coef, div, bias)
+        assert np.array_equal(gpu.conv(img, coef, div, bias), exp), (it, k, cls, w, h, div, bias)
+        n += 1
+        r = k // 2
+        if it % 3 == 0 and h >= 2 * r + 2:  # two or three row bands with halo rows through the band pointers
+            cuts = sorted(set([0, h] + [int(c) for c in rng.randint(r, h - r + 1, 2)]))
+            if any(b - a < r for a, b in zip(cuts[:-1], cuts[1:])):
+                continue
+            bands = [torch.from_numpy(img[a:b].copy()).to(dev) for a, b in zip(cuts[:-1], cuts[1:])]
+            outs = [torch.zeros_like(b) for b in bands]
+            op = gpu.conv_op(coef, div, bias)
+            for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+                band = pp.PpmxBand(full_h=h, y0=a, halo=r)
+                if i > 0:
+                    band.d_top = bands[i - 1].data_ptr() + (bands[i - 1].shape[0] - r) * w * 3
+                if i < len(bands) - 1:
+                    band.d_bottom = bands[i + 1].data_ptr()
+                gpu.launch(op, bands[i].data_ptr(), w, b - a, pp.LAYOUT_RGB8, outs[i].data_ptr(), band)
+            torch.cuda.synchronize()
+            got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+            assert np.array_equal(got, exp), ("bands", it, k, cls, w, h, cuts)
+    assert n > 200
+
+
 def test_extension_conv_row_bands(gpu, orc):
     """A raster cut into row bands, each convolved separately with halo rows read through the band
     pointers (here: the neighbour band in the same HBM), equals the whole-raster result."""
