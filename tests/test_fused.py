@@ -47,6 +47,39 @@ def test_fused_chains_match_oracle(gpu, orc):
     assert fused_seen > 100  # most of these chains are ONE kernel
 
 
+def test_fused_chain_fuzz(gpu, orc):
+    """Seeded random sweep: sizes from 1 x 1 to a few hundred pixels a side (rows at every alignment, ragged tiles on both axes),
+    every combination of right-angle rotation, grey / mono and flips the command line accepts, against the oracle's chain."""
+    rng = np.random.RandomState(19)
+    for it in range(220):
+        w, h = int(rng.randint(1, 330)), int(rng.randint(1, 260))
+        if it % 7 == 0:
+            w = 16 * int(rng.randint(1, 20))
+        if it % 11 == 0:
+            h = 8 * int(rng.randint(1, 30))
+        kw = {}
+        a = int(rng.choice([0, 90, 180, 270, 90, 270]))
+        if a:
+            kw["angle"] = a
+        t = int(rng.randint(0, 3))
+        if t == 1:
+            kw["gray"] = True
+        elif t == 2:
+            kw["mono"] = True
+        f = int(rng.randint(0, 3))
+        if f == 1:
+            kw["flipv"] = True
+        elif f == 2:
+            kw["fliph"] = True
+        if not kw:
+            kw["flipv"] = True
+        img = P.lcg(w, h, 500 + it)
+        exp, ew, eh, eft = orc.process(img, **kw)
+        got, gw, gh, gft = gpu.process(img, **kw)
+        assert (gw, gh, gft) == (ew, eh, eft), (it, w, h, kw)
+        assert np.array_equal(got, exp), (it, w, h, kw)
+
+
 def test_config5_chains_kernel_counts(gpu, orc):
     """BASELINE config 5 chains on a 1920x1080 frame: "-r90 -mono -fh" is one kernel, "-w960 -r90 -gray -fv" three."""
     import imageprocessingtools_b200.ppmx as pp
