@@ -465,11 +465,17 @@ __global__ void __launch_bounds__(128) rows_kernel(const uint8_t *__restrict__ s
             for (int k = 0; k < 16; k++) bits |= val[REV_X ? 15 - k : k] << (15 - k);
             const uint32_t valid = 16u * lane < npx ? min(16u, npx - 16u * lane) : 0u;  // pixels beyond the row are pad bits: zero
             if (valid < 16u) bits &= REV_X ? (0xFFFFu >> (16u - valid)) : (0xFFFFu << (16u - valid));
+            // Two bytes per lane, 64 per warp: straight to the destination row (no staging, no run store: for this tail they cost
+            // more than the arithmetic).  Byte b of the run = staging byte b + 2 (a mirrored row of bits has w % 8 == 0, so P is a
+            // multiple of 8; the ragged last group of a mirrored row starts one byte before the run).
             if (inrun) {
-                uint8_t *q = stage + (P >> 3);  // (a mirrored row of bits has w % 8 == 0, so P is a multiple of 8)
-                q[0] = (uint8_t)(bits >> 8);
-                q[1] = (uint8_t)bits;
+                const uint32_t oy = go.rev_y ? h - 1u - y : y, xs = REV_X ? w - px0 - npx : px0;
+                const int b0 = (int)(P >> 3) - 2, nb = (int)((npx + 7u) >> 3);
+                uint8_t *g = dst + (size_t)oy * out_pitch + (xs >> 3) + b0;
+                if (b0 >= 0 && b0 < nb) g[0] = (uint8_t)(bits >> 8);
+                if (b0 + 1 >= 0 && b0 + 1 < nb) g[1] = (uint8_t)bits;
             }
+            return;
         } else {
             uint32_t o[4];
 #pragma unroll
