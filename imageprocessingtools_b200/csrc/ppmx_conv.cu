@@ -226,7 +226,7 @@ __device__ __forceinline__ uint32_t strip_pack4(const ConvRound &rnd, int32_t a0
 // aligned vectors (store_run) -- the padded copy the kernel used to need (two more passes over the raster) is gone.
 constexpr int C3_STAGE = 32 * 16 + 16;
 
-template <int MODE, int RH, int PF, bool INNER, bool WIDE, bool UA = false>
+template <int MODE, int RH, int PF, bool INNER, bool WIDE, bool UA = false, bool BINOM = false>
 __device__ __forceinline__ void conv3_strip_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, uint32_t cx,
                                                  int ys, const Conv3Coef &cf, const ConvRound &rnd, uint32_t row_bytes = 0,
                                                  uint8_t *stage = nullptr, uint32_t cx0 = 0)
@@ -318,12 +318,29 @@ __device__ __forceinline__ void conv3_strip_body(const RowSource &rs, uint8_t *_
                 thi[wc] = uhi[wc];
             }
             uint32_t oa[4], ob[4];
+            // BINOM (tuning build, variant 23; measured and NOT adopted): the filter is s * (1 2 1)^T (1 2 1).  One dot product per byte
+            // column gives the vertical sum, the horizontal (1 2 1) is two adds: 1.4 dp4a + 2 adds per byte instead of 3 dp4a.  The idea
+            // was that under the 1 kW cap fewer multipliers switching would keep the clock up; it is the instruction COUNT that
+            // matters: 8192^2, 60 ms: 0.85 against 0.92; 2.6 s back to back: 0.76 against 0.82.
+            int32_t SA[24], SB[24];
+            if (BINOM) {
+#pragma unroll
+                for (int i = 1; i <= 22; i++) {
+                    SA[i] = dp4a_u8s8(V[i], cf.a[0], 0);
+                    SB[i] = dp4a_u8s8(V[i], cf.b[0], 0);
+                }
+            }
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 int32_t accA[4], accB[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int c = 4 * b + j + 4;
+                    if (BINOM) {
+                        accA[j] = SA[c - 3] + SA[c + 3] + (2 * SA[c] + rnd.start);
+                        accB[j] = SB[c - 3] + SB[c + 3] + (2 * SB[c] + rnd.start);
+                        continue;
+                    }
                     accA[j] = dp4a_u8s8(V[c + 3], cf.a[2], dp4a_u8s8(V[c], cf.a[1], dp4a_u8s8(V[c - 3], cf.a[0], rnd.start)));
                     accB[j] = dp4a_u8s8(V[c + 3], cf.b[2], dp4a_u8s8(V[c], cf.b[1], dp4a_u8s8(V[c - 3], cf.b[0], rnd.start)));
                     if (WIDE) {  // the high parts of the coefficients: a second dp4a chain, weighted 128
@@ -354,7 +371,7 @@ __device__ __forceinline__ void conv3_strip_body(const RowSource &rs, uint8_t *_
     }
 }
 
-template <int MODE, int RH, int PF, int BLOCK, bool WIDE = false>
+template <int MODE, int RH, int PF, int BLOCK, bool WIDE = false, bool BINOM = false>
 __global__ void __launch_bounds__(BLOCK) conv3_strip_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks,
                                                             const Conv3Coef cf, const ConvRound rnd)
 {
@@ -364,8 +381,8 @@ __global__ void __launch_bounds__(BLOCK) conv3_strip_kernel(RowSource rs, uint8_
     const int ys = blockIdx.y * RH;  // first output row of the strip, band-local
     // source rows ys-1 .. ys+RH all inside the own band (all strips but the first and last of a band): plain
     // pointer steps; otherwise every row goes through the mirror / halo resolver
-    if (ys >= 1 && ys + RH + 1 <= rs.h) conv3_strip_body<MODE, RH, PF, true, WIDE>(rs, dst, nchunks, cx, ys, cf, rnd);
-    else conv3_strip_body<MODE, RH, PF, false, WIDE>(rs, dst, nchunks, cx, ys, cf, rnd);
+    if (ys >= 1 && ys + RH + 1 <= rs.h) conv3_strip_body<MODE, RH, PF, true, WIDE, false, BINOM>(rs, dst, nchunks, cx, ys, cf, rnd);
+    else conv3_strip_body<MODE, RH, PF, false, WIDE, false, BINOM>(rs, dst, nchunks, cx, ys, cf, rnd);
 }
 
 #ifdef PPMX_TUNING
@@ -477,6 +494,13 @@ static cudaError_t conv3_strip(const RowSource &rs, uint8_t *dst, uint32_t w, ui
         return PPMX_LAUNCHED();
     }
 #ifdef PPMX_TUNING
+    // s * (1 2 1)^T (1 2 1) in the byte-extraction form: vertical dot product + two adds (variant 23)
+    if (PPMX_VARIANT == 23 && mode == 3 && cf.a[2] == cf.a[0] && cf.a[1] == 2u * cf.a[0] && cf.b[2] == cf.b[0] && cf.b[1] == 2u * cf.b[0]) {
+        dim3 grid((nchunks + 127) / 128, (h + 3) / 4);
+        if (grid.y > 65535u) return cudaErrorInvalidValue;
+        launch(conv3_strip_kernel<3, 4, 2, 128, false, true>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, rnd);
+        return PPMX_LAUNCHED();
+    }
     if (PPMX_VARIANT == 9) PPMX_CONV3_MODES(2, 1, 128);
     else if (PPMX_VARIANT == 10) PPMX_CONV3_MODES(4, 2, 256);
     else if (PPMX_VARIANT == 11) PPMX_CONV3_MODES(8, 2, 128);
