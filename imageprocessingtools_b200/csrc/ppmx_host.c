@@ -249,6 +249,23 @@ void ppmx_renewBuffer(ppmx_image_handler *h)
 static const int32_t k_blur3[9] = {1, 2, 1, 2, 4, 2, 1, 2, 1};
 static const int32_t k_sharpen[9] = {0, -1, 0, -1, 5, -1, 0, -1, 0};
 static const int32_t k_edge[9] = {-1, -1, -1, -1, 8, -1, -1, -1, -1};
+/* binomial blurs and the 7x7 unsharp mask, filled on first use (outer products of a row of Pascal's triangle) */
+static int32_t k_gauss5[25], k_gauss7[49], k_sharpen7[49], k_gauss9[81];
+static void fill_binomial_presets(void)
+{
+    static const int32_t b5[5] = {1, 4, 6, 4, 1}, b7[7] = {1, 6, 15, 20, 15, 6, 1}, b9[9] = {1, 8, 28, 56, 70, 56, 28, 8, 1};
+    int i, j;
+    if (k_gauss5[0]) return; /* (idempotent: a racing second caller writes the same values) */
+    for (i = 0; i < 7; i++)
+        for (j = 0; j < 7; j++) {
+            k_gauss7[i * 7 + j] = b7[i] * b7[j];
+            k_sharpen7[i * 7 + j] = -b7[i] * b7[j] + (i == 3 && j == 3 ? 2 * 4096 : 0);
+        }
+    for (i = 0; i < 9; i++)
+        for (j = 0; j < 9; j++) k_gauss9[i * 9 + j] = b9[i] * b9[j];
+    for (i = 4; i >= 0; i--)
+        for (j = 4; j >= 0; j--) k_gauss5[i * 5 + j] = b5[i] * b5[j]; /* (element 0 last: it is the "filled" flag) */
+}
 static const int32_t k_box7[49] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
                                    1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
 
@@ -347,6 +364,10 @@ int ppmx_plan_chain_ext2(const ppmx_args_flag *f, unsigned int output_width_size
         case PPMX_CONV_BLUR7: op->conv_k = 7; op->conv_div = 49; op->conv_coef = k_box7; break;
         case PPMX_CONV_SHARPEN: op->conv_k = 3; op->conv_div = 1; op->conv_coef = k_sharpen; break;
         case PPMX_CONV_EDGE: op->conv_k = 3; op->conv_div = 1; op->conv_coef = k_edge; break;
+        case PPMX_CONV_GAUSS5: fill_binomial_presets(); op->conv_k = 5; op->conv_div = 256; op->conv_coef = k_gauss5; break;
+        case PPMX_CONV_GAUSS7: fill_binomial_presets(); op->conv_k = 7; op->conv_div = 4096; op->conv_coef = k_gauss7; break;
+        case PPMX_CONV_SHARPEN7: fill_binomial_presets(); op->conv_k = 7; op->conv_div = 4096; op->conv_coef = k_sharpen7; break;
+        case PPMX_CONV_GAUSS9: fill_binomial_presets(); op->conv_k = 9; op->conv_div = 65536; op->conv_coef = k_gauss9; break;
         default: printf("Error: unknown convolution preset\n"); goto bad;
         }
         renew = 1;
@@ -1063,10 +1084,13 @@ int ppmx_main(int argc, char *argv[])
             hd.angle = (double)atoi(a + 2);
             if (hd.angle < 0 || hd.angle >= 360) BAIL("Error: invalid option for rotate.\n");
         } else if (strcmp(a + 1, "blur") == 0 || strcmp(a + 1, "blur7") == 0 || strcmp(a + 1, "sharpen") == 0 ||
-                   strcmp(a + 1, "edge") == 0) { /* EXTENSION flags: the reference rejects them (ref:175) */
+                   strcmp(a + 1, "edge") == 0 || strcmp(a + 1, "gauss5") == 0 || strcmp(a + 1, "gauss7") == 0 ||
+                   strcmp(a + 1, "gauss9") == 0 || strcmp(a + 1, "sharpen7") == 0) { /* EXTENSION flags: the reference rejects them (ref:175) */
             if (hd.conv_preset) BAIL("Error: Duplicate options not allowed\n");
-            hd.conv_preset = a[1] == 's' ? PPMX_CONV_SHARPEN : a[1] == 'e' ? PPMX_CONV_EDGE
-                             : a[5] == '7' ? PPMX_CONV_BLUR7 : PPMX_CONV_BLUR3;
+            hd.conv_preset = strcmp(a + 1, "blur") == 0 ? PPMX_CONV_BLUR3 : strcmp(a + 1, "blur7") == 0 ? PPMX_CONV_BLUR7
+                             : strcmp(a + 1, "sharpen") == 0 ? PPMX_CONV_SHARPEN : strcmp(a + 1, "edge") == 0 ? PPMX_CONV_EDGE
+                             : strcmp(a + 1, "gauss5") == 0 ? PPMX_CONV_GAUSS5 : strcmp(a + 1, "gauss7") == 0 ? PPMX_CONV_GAUSS7
+                             : strcmp(a + 1, "gauss9") == 0 ? PPMX_CONV_GAUSS9 : PPMX_CONV_SHARPEN7;
         } else if (strncmp(a + 1, "levels", 6) == 0) { /* EXTENSION flag -levelsLO-HI, e.g. -levels16-235 */
             int lo = -1, hi = -1, used = 0;
             if (hd.levels_enable) BAIL("Error: Duplicate options not allowed\n");

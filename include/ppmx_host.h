@@ -49,7 +49,7 @@ typedef struct ppmx_image_handler {
     unsigned int output_width_size;
     double angle;
     char norotate;
-    int conv_preset;            /* extension flags -blur/-blur7/-sharpen/-edge (0 = none); not in the reference */
+    int conv_preset;            /* extension flags -blur/-blur7/-sharpen/-edge/-gauss5/-gauss7/-gauss9/-sharpen7 (0 = none); not in the reference */
     int levels_enable, levels_lo, levels_hi; /* extension flag -levelsLO-HI (black/white point); not in the reference */
 } ppmx_image_handler;
 
@@ -100,6 +100,10 @@ int ppmx_plan_chain(const ppmx_args_flag *flags, unsigned int output_width_size,
 #define PPMX_CONV_BLUR7 2
 #define PPMX_CONV_SHARPEN 3
 #define PPMX_CONV_EDGE 4
+#define PPMX_CONV_GAUSS5 5   /* -gauss5: binomial (1 4 6 4 1)^2 / 256 */
+#define PPMX_CONV_GAUSS7 6   /* -gauss7: binomial (1 6 15 20 15 6 1)^2 / 4096 */
+#define PPMX_CONV_SHARPEN7 7 /* -sharpen7: unsharp mask 2 I - gauss7 */
+#define PPMX_CONV_GAUSS9 8   /* -gauss9: binomial (1 8 28 56 70 56 28 8 1)^2 / 65536 */
 int ppmx_plan_chain_ext(const ppmx_args_flag *flags, unsigned int output_width_size, double angle,
                         unsigned int width, unsigned int height, int conv_preset, ppmx_plan *plan);
 /* The same plus a second EXTENSION stage after the convolution: levels with black point lo and white point hi

@@ -708,7 +708,8 @@ def test_extension_cli_conv_presets(gpu, orc, tmp_path):
     import imageprocessingtools_b200.ppmx as pp
     img = P.lcg(64, 40, 5)
     presets = {"-blur": KERNELS["blur3"], "-blur7": (np.ones((7, 7), np.int64), 49, 0), "-sharpen": KERNELS["sharpen3"],
-               "-edge": KERNELS["edge3"]}
+               "-edge": KERNELS["edge3"], "-gauss5": KERNELS["gauss5"], "-gauss7": KERNELS["gauss7"], "-sharpen7": KERNELS["unsharp7"],
+               "-gauss9": KERNELS["binom9"]}
     path = str(tmp_path / "x.ppm")
     for flag, (coef, div, bias) in presets.items():
         oracle.write_p6(path, img)
@@ -816,6 +817,7 @@ def test_operator_level_host_api_stepwise(gpu, tmp_path):
 # ---- round 2: row parts, row bands, several devices, CUDA graphs ------------------------------------------
 
 PART_CHAINS = [dict(conv_preset=1), dict(conv_preset=2, mono=True, flipv=True), dict(resize_w=300, gray=True),
+               dict(conv_preset=6), dict(conv_preset=7, mono=True), dict(conv_preset=8, flipv=True), dict(resize_w=208, conv_preset=5, gray=True),
                dict(resize_w=97, conv_preset=4, fliph=True), dict(flipv=True), dict(angle=180, levels=(16, 235)),
                dict(gray=True, flipv=True), dict(mono=True), dict(resize_w=201, angle=180, conv_preset=3, mono=True, flipv=True),
                dict(angle=90, gray=True), dict(angle=33)]
@@ -832,7 +834,8 @@ def _orc_chain(orc, img, resize_w=None, angle=None, gray=False, mono=False, flip
         cur = orc.rotate(cur, angle)
     if conv_preset:
         coef, div = {1: (KERNELS["blur3"][0], 16), 2: (np.ones((7, 7), np.int64), 49), 3: (KERNELS["sharpen3"][0], 1),
-                     4: (KERNELS["edge3"][0], 1)}[conv_preset]
+                     4: (KERNELS["edge3"][0], 1), 5: KERNELS["gauss5"][:2], 6: KERNELS["gauss7"][:2], 7: KERNELS["unsharp7"][:2],
+                     8: KERNELS["binom9"][:2]}[conv_preset]
         cur = orc.conv(cur, coef, div, 0)
     if levels is not None:
         cur = orc.levels(cur, orc.levels_lut_linear(*levels))
