@@ -55,7 +55,7 @@ __device__ __forceinline__ void store_piece(uint8_t *g, const uint8_t *srow, uin
     uint32_t *gw = reinterpret_cast<uint32_t *>(g + hb) + hl;
 #pragma unroll
     for (uint32_t t = 0; t < 4u; t++)  // (nbytes <= 208: at most 52 words)
-        if (hl + 16u * t < nw) gw[16u * t] = __funnelshift_r(sw[16u * t], sw[16u * t + 1], sh);
+        if (hl + 16u * t < nw) gw[16u * t] = sh ? __funnelshift_r(sw[16u * t], sw[16u * t + 1], sh) : sw[16u * t];
     const bool tail = hl >= 3u;
     const uint32_t k = tail ? hl - 3u : hl, pos = tail ? hb + 4u * nw + k : k;
     if (hl < 6u && k < (tail ? tb : hb)) g[pos] = srow[soff + pos];
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(128) geom_kernel(const uint8_t *__restrict__ s
                 for (int t = 0; t < 3; t++) {
                     const bool on = r < nr && hl + 16u * t < nwords;
                     lo[u][t] = on ? ld_global_u32(gw + 16 * t) : 0u;  // (not __ldg: see ld_global_u32)
-                    hi[u][t] = on && reinterpret_cast<uintptr_t>(gw + 16 * t + 1) <= last ? ld_global_u32(gw + 16 * t + 1) : 0u;
+                    // (a row that starts on a word boundary needs no second word: sh is the same for the whole half warp)
+                    hi[u][t] = on && sh[u] != 0u && reinterpret_cast<uintptr_t>(gw + 16 * t + 1) <= last ? ld_global_u32(gw + 16 * t + 1) : 0u;
                 }
             }
 #pragma unroll
