@@ -165,21 +165,19 @@ __device__ __forceinline__ void conv_sep16_body(const RowSource &rs, uint8_t *__
 #pragma unroll
             for (int i = 0; i < SH; i++) S[16 + i] = right ? (int32_t)Smr(i) : S[16 + i];
         }
+        // the left neighbour's last H column sums too, in the same shuffle round (packing the halo pairs here costs H + QR more
+        // PRMT than shuffling the neighbours' packed pairs would, but a second, dependent round of shuffles is gone)
+        int32_t SL[H];
+#pragma unroll
+        for (int i = 0; i < H; i++) SL[i] = __shfl_up_sync(0xffffffffu, S[16 - H + i], 1);
+        if (EDGE) {  // pixel -m mirrors to pixel m-1: column -3m + ch comes from column 3 (m-1) + ch
+#pragma unroll
+            for (int i = 0; i < H; i++) SL[i] = left ? S[3 * (R - 1 - i / 3) + i % 3] : SL[i];
+        }
+        auto Sx = [&](int c) { return (uint32_t)(c >= 0 ? S[c] : SL[c + H]); };
         uint32_t Q[H + 16 + QR];  // Q[H + c] = S[c] | S[c+3] << 16 for c = -H .. 15 + QR
 #pragma unroll
-        for (int c = 0; c < 16; c++) Q[H + c] = __byte_perm((uint32_t)S[c], (uint32_t)S[c + 3], 0x5410);
-#pragma unroll
-        for (int i = 0; i < H; i++) Q[i] = __shfl_up_sync(0xffffffffu, Q[16 + i], 1);
-#pragma unroll
-        for (int i = 0; i < QR; i++) Q[H + 16 + i] = __shfl_down_sync(0xffffffffu, Q[H + i], 1);
-        if (EDGE) {
-            // pixel -m mirrors to pixel m-1: column -3m + ch comes from column 3 (m-1) + ch
-            auto Sx = [&](int c) { return (uint32_t)(c >= 0 ? S[c] : S[3 * ((-c + 2) / 3 - 1) + ((c % 3) + 3) % 3]); };
-#pragma unroll
-            for (int i = 0; i < H; i++) Q[i] = left ? __byte_perm(Sx(i - H), Sx(i - H + 3), 0x5410) : Q[i];
-#pragma unroll
-            for (int i = 0; i < QR; i++) Q[H + 16 + i] = right ? __byte_perm(Smr(i), Smr(i + 3), 0x5410) : Q[H + 16 + i];
-        }
+        for (int c = -H; c < 16 + QR; c++) Q[H + c] = __byte_perm(Sx(c), Sx(c + 3), 0x5410);
         uint32_t ov[4];
 #pragma unroll
         for (int b = 0; b < 4; b++) {
