@@ -1009,7 +1009,7 @@ cudaError_t conv(const uint8_t *src, uint8_t *dst, uint32_t w, uint32_t h, int k
         return conv_box<11>(rs, dst, w, h, bm, bc, s);
     }
     const bool rnd_ok = make_conv_round(sum_abs, div, bias, &rnd);
-    [[maybe_unused]] const int strip_rh = PPMX_VARIANT >= 15 && PPMX_VARIANT <= 18 ? PPMX_VARIANT - 14 : 0;  // strip geometry (tuning build)
+    [[maybe_unused]] const int strip_rh = PPMX_VARIANT >= 15 && PPMX_VARIANT <= 19 ? PPMX_VARIANT - 14 : 0;  // strip geometry (tuning build)
     if (rnd_ok && fast_layout && (k == 5 || k == 7) && PPMX_VARIANT != 7 && PPMX_VARIANT != 2 && PPMX_VARIANT != 14 && aligned16(dst)) {
         // rank-1 whose column sums fit 16 bits (ppmx_conv_sep.cu): packed pairs, dp2a along the row
         cudaError_t e = cudaSuccess;

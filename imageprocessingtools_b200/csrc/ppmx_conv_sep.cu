@@ -119,11 +119,11 @@ struct Sep16Coef {
     int32_t centre;  // CENTRE kernels: coef = u v^T + centre * delta (unsharp masks: (1 + k) div delta - k G)
 };
 
-template <int K, int MODE, bool SIGNED, bool CENTRE, int RH, bool INNER, bool EDGE>
+template <int K, int MODE, bool SIGNED, bool CENTRE, int RH, bool INNER, bool EDGE, int PF = 2>
 __device__ __forceinline__ void conv_sep16_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, int chunk, int ys,
                                                 const Sep16Coef<K> &cf, const ConvRound &rnd)
 {
-    constexpr int R = K / 2, H = 3 * R, SH = H, QR = H > 6 ? H - 6 : 0, PF = 2, NP = (K - 1) / 2;
+    constexpr int R = K / 2, H = 3 * R, SH = H, QR = H > 6 ? H - 6 : 0, NP = (K - 1) / 2;
     static_assert(RH % (2 * PF) == 0, "strip height");
     const int lane = threadIdx.x & 31;
     const bool valid = chunk >= 0 && chunk < (int)nchunks;
@@ -229,9 +229,9 @@ __global__ void __launch_bounds__(128, MINB) conv_sep16_kernel(RowSource rs, uin
     const int ys = blockIdx.y * RH;
     const bool inner = ys >= 3 && ys + RH + 3 <= rs.h;  // window rows ys-3 .. ys+RH+2 all in the own band
     const bool edge = wg == 0 || wg * 30 + 30 >= (int)nchunks;
-    if (inner && !edge) conv_sep16_body<K, MODE, SIGNED, CENTRE, RH, true, false>(rs, dst, nchunks, chunk, ys, cf, rnd);
-    else if (inner) conv_sep16_body<K, MODE, SIGNED, CENTRE, RH, true, true>(rs, dst, nchunks, chunk, ys, cf, rnd);
-    else conv_sep16_body<K, MODE, SIGNED, CENTRE, RH, false, true>(rs, dst, nchunks, chunk, ys, cf, rnd);
+    if (inner && !edge) conv_sep16_body<K, MODE, SIGNED, CENTRE, RH, true, false, (MINB >= 4 ? 1 : 2)>(rs, dst, nchunks, chunk, ys, cf, rnd);
+    else if (inner) conv_sep16_body<K, MODE, SIGNED, CENTRE, RH, true, true, (MINB >= 4 ? 1 : 2)>(rs, dst, nchunks, chunk, ys, cf, rnd);
+    else conv_sep16_body<K, MODE, SIGNED, CENTRE, RH, false, true, (MINB >= 4 ? 1 : 2)>(rs, dst, nchunks, chunk, ys, cf, rnd);
 }
 
 template <int K, int RH, int MINB>
@@ -346,18 +346,21 @@ static bool conv_sep16_k(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t
     cf.v_last = v[K - 1];
     cf.centre = centre;
     const uint32_t nchunks = w * 3 / 16;
-    // rows per strip / CTAs per SM (register budget).  7x7 binomial at 8192^2: 16/3 (168 registers) 0.574 of the HBM roofline,
-    // 16/4 (128 registers, a few spills) 0.561, 32/4 0.549, 32/3 0.556, 64/4 0.51; the 32-bit kernel this replaces 0.457.
+    // rows per strip / CTAs per SM (register budget) / row pairs prefetched.  7x7 binomial at 8192^2, fraction of the HBM roofline:
+    // 16 / 4 / 1 (116 registers, no spills: the default) 0.600; 16 / 3 / 2 (168 registers) 0.570; 32 / 4 / 1 0.600; 16 / 5 / 1
+    // (96 registers) 0.571; with two pairs prefetched 4 CTAs per SM spill (0.561).  5x5: 0.666 / 0.624 / 0.654 / 0.664.  The
+    // schedulers had 2.8 warps each and one eligible in 1.28 of them per cycle at 3 CTAs per SM: occupancy, not the mix.
     // Measured and dropped: the odd tap as a shift-add, and the three middle taps of a symmetric v as one dp2a of
     // (S[c-3] + S[c+3], S[c]) -- ptxas issues the adds as IMAD.IADD on the same fma pipe, no change (0.561 vs 0.567).
 #ifdef PPMX_TUNING
-    if (rh == 1) *err = conv_sep16_launch<K, 16, 4>(rs, dst, nchunks, h, cf, rnd, mode, sgn, s);
+    if (rh == 1) *err = conv_sep16_launch<K, 16, 3>(rs, dst, nchunks, h, cf, rnd, mode, sgn, s);
     else if (rh == 2) *err = conv_sep16_launch<K, 32, 4>(rs, dst, nchunks, h, cf, rnd, mode, sgn, s);
     else if (rh == 3) *err = conv_sep16_launch<K, 32, 3>(rs, dst, nchunks, h, cf, rnd, mode, sgn, s);
     else if (rh == 4) *err = conv_sep16_launch<K, 64, 4>(rs, dst, nchunks, h, cf, rnd, mode, sgn, s);
+    else if (rh == 5) *err = conv_sep16_launch<K, 16, 5>(rs, dst, nchunks, h, cf, rnd, mode, sgn, s);
     else
 #endif
-    *err = conv_sep16_launch<K, 16, 3>(rs, dst, nchunks, h, cf, rnd, mode, sgn, s);
+    *err = conv_sep16_launch<K, 16, 4>(rs, dst, nchunks, h, cf, rnd, mode, sgn, s);
     return true;
 }
 
@@ -378,11 +381,11 @@ struct DenseCoef {
 };
 
 // WIDE: coefficients beyond a signed byte (-16320 .. 16319) are split c = 128 * hi + lo: a second chain of dot products, weighted 128
-template <int K, int MODE, bool WIDE, int RH, bool INNER, bool EDGE>
+template <int K, int MODE, bool WIDE, int RH, bool INNER, bool EDGE, int PF>
 __device__ __forceinline__ void conv_dense_body(const RowSource &rs, uint8_t *__restrict__ dst, uint32_t nchunks, int chunk, int ys,
                                                 const DenseCoef<K> &cf, const DenseCoef<K> &cfh, const ConvRound &rnd)
 {
-    constexpr int R = K / 2, H = 3 * R, PF = 2;
+    constexpr int R = K / 2, H = 3 * R;
     static_assert(RH % (2 * PF) == 0, "strip height");
     const int lane = threadIdx.x & 31;
     const bool valid = chunk >= 0 && chunk < (int)nchunks;
@@ -476,8 +479,8 @@ __device__ __forceinline__ void conv_dense_body(const RowSource &rs, uint8_t *__
     }
 }
 
-template <int K, int MODE, bool WIDE, int RH>
-__global__ void __launch_bounds__(128, 3) conv_dense_strip_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks,
+template <int K, int MODE, bool WIDE, int RH, int MINB>
+__global__ void __launch_bounds__(128, MINB) conv_dense_strip_kernel(RowSource rs, uint8_t *__restrict__ dst, uint32_t nchunks,
                                                                   const DenseCoef<K> cf, const DenseCoef<K> cfh, const ConvRound rnd)
 {
     pdl_trigger();
@@ -487,12 +490,12 @@ __global__ void __launch_bounds__(128, 3) conv_dense_strip_kernel(RowSource rs, 
     const int ys = blockIdx.y * RH;
     const bool inner = ys >= 3 && ys + RH + 3 <= rs.h;
     const bool edge = wg == 0 || wg * 30 + 30 >= (int)nchunks;
-    if (inner && !edge) conv_dense_body<K, MODE, WIDE, RH, true, false>(rs, dst, nchunks, chunk, ys, cf, cfh, rnd);
-    else if (inner) conv_dense_body<K, MODE, WIDE, RH, true, true>(rs, dst, nchunks, chunk, ys, cf, cfh, rnd);
-    else conv_dense_body<K, MODE, WIDE, RH, false, true>(rs, dst, nchunks, chunk, ys, cf, cfh, rnd);
+    if (inner && !edge) conv_dense_body<K, MODE, WIDE, RH, true, false, (MINB >= 4 ? 1 : 2)>(rs, dst, nchunks, chunk, ys, cf, cfh, rnd);
+    else if (inner) conv_dense_body<K, MODE, WIDE, RH, true, true, (MINB >= 4 ? 1 : 2)>(rs, dst, nchunks, chunk, ys, cf, cfh, rnd);
+    else conv_dense_body<K, MODE, WIDE, RH, false, true, (MINB >= 4 ? 1 : 2)>(rs, dst, nchunks, chunk, ys, cf, cfh, rnd);
 }
 
-template <int K, int RH>
+template <int K, int RH, int MINB>
 static cudaError_t conv_dense_launch(const RowSource &rs, uint8_t *dst, uint32_t nchunks, uint32_t h, const DenseCoef<K> &cf,
                                      const DenseCoef<K> &cfh, bool wide, const ConvRound &rnd, cudaStream_t s)
 {
@@ -500,8 +503,8 @@ static cudaError_t conv_dense_launch(const RowSource &rs, uint8_t *dst, uint32_t
     if (grid.y > 65535u) return cudaErrorInvalidValue;
 #define PPMX_DENSE(MODE)                                                                                                   \
     do {                                                                                                                   \
-        if (wide) launch(conv_dense_strip_kernel<K, MODE, true, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, cfh, rnd);    \
-        else launch(conv_dense_strip_kernel<K, MODE, false, RH>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, cfh, rnd);        \
+        if (wide) launch(conv_dense_strip_kernel<K, MODE, true, RH, MINB>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, cfh, rnd);    \
+        else launch(conv_dense_strip_kernel<K, MODE, false, RH, MINB>, grid, dim3(128), 0, s, rs, dst, nchunks, cf, cfh, rnd);        \
     } while (0)
     if (rnd.mode == 0) PPMX_DENSE(0);
     else if (rnd.mode == 1) PPMX_DENSE(1);
@@ -532,12 +535,14 @@ static bool conv_dense_k(const RowSource &rs, uint8_t *dst, uint32_t w, uint32_t
         window_coef<K>(hi, cfh.a_lo[k], cfh.a_hi[k], cfh.b_lo[k], cfh.b_hi[k]);
     }
     const uint32_t nchunks = w * 3 / 16;
+    // 4 CTAs per SM with one row pair prefetched (121 / 110 registers at 7x7 / 5x5) against 3 with two (variant: rh code 1)
 #ifdef PPMX_TUNING
-    if (rh == 2 || rh == 3) *err = conv_dense_launch<K, 32>(rs, dst, nchunks, h, cf, cfh, wide, rnd, s);
-    else if (rh == 4) *err = conv_dense_launch<K, 64>(rs, dst, nchunks, h, cf, cfh, wide, rnd, s);
+    if (rh == 1) *err = conv_dense_launch<K, 16, 3>(rs, dst, nchunks, h, cf, cfh, wide, rnd, s);
+    else if (rh == 2 || rh == 3) *err = conv_dense_launch<K, 32, 4>(rs, dst, nchunks, h, cf, cfh, wide, rnd, s);
+    else if (rh == 4) *err = conv_dense_launch<K, 64, 4>(rs, dst, nchunks, h, cf, cfh, wide, rnd, s);
     else
 #endif
-    *err = conv_dense_launch<K, 16>(rs, dst, nchunks, h, cf, cfh, wide, rnd, s);
+    *err = conv_dense_launch<K, 16, 4>(rs, dst, nchunks, h, cf, cfh, wide, rnd, s);
     return true;
 }
 
